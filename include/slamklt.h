@@ -1,0 +1,186 @@
+/*
+ * slamklt.h -- C ABI of libslamklt.so: the B200 (sm_100a) implementation of SLAM.jl's KLT
+ * front-end hot path (image pyramid, pyramidal Lucas-Kanade with forward-backward check,
+ * Shi-Tomasi extraction with NMS and grid bucketing).
+ *
+ * The reference reaches this path by ordinary Julia method dispatch (it has no FFI today);
+ * each entry point below names the reference method it stands behind (file:line relative to
+ * the SLAM.jl checkout).  INTEGRATION.md shows the `ccall` shim that forwards those methods.
+ *
+ * Conventions are the reference's own:
+ *   - images are column-major, element (y, x) at img[y + x*ld] (Julia Matrix{Gray{Float64}}, ld = H);
+ *   - points are dense pairs of Float64 in (y, x) order, 1-based (Vector{SVector{2,Float64}});
+ *   - extracted keypoints are dense pairs of Int64 (y, x), 1-based (Vector{CartesianIndex{2}}).
+ * Every function returns 0 on success or a negative SLAMKLT_E_* code; the message is available
+ * from slamklt_last_error() (thread-local).  No exceptions cross the boundary.  All pointers
+ * are caller-owned HOST pointers unless the name says `_dev`; the library copies.
+ * A context owns one CUDA stream; calls on one context are serialised by an internal mutex, so
+ * two Julia tasks (front-end and mapper, mapper.jl:51-60) may share it or use one context each.
+ */
+#ifndef SLAMKLT_H
+#define SLAMKLT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define SLAMKLT_VERSION 100
+
+/* error codes */
+#define SLAMKLT_OK 0
+#define SLAMKLT_E_INVALID (-1)    /* bad argument */
+#define SLAMKLT_E_CUDA (-2)       /* CUDA runtime error (sticky errors included) */
+#define SLAMKLT_E_LAYERS (-3)     /* "Not enough layers in pyramids." lucas_kanade.jl:12-15 */
+#define SLAMKLT_E_NODEVICE (-4)   /* no usable sm_100 device; there is no CPU fallback */
+#define SLAMKLT_E_CAPACITY (-5)   /* output buffer too small */
+
+/* pixel types accepted at the boundary */
+#define SLAMKLT_F64 0 /* Gray{Float64}: what the reference passes (SLAM.jl:22-26) */
+#define SLAMKLT_F32 1
+#define SLAMKLT_U8 2  /* value/255, i.e. Gray{N0f8} before the example's Gray{Float64}.() conversion */
+
+/* pyramid build modes */
+#define SLAMKLT_MODE_UPDATE 0 /* update!(pyr, img): replicate borders (pyramid.jl:81-103) */
+#define SLAMKLT_MODE_CTOR 1   /* LKPyramid(img, levels): NA-border blur, Fill(0) Scharr (pyramid.jl:40-79) */
+
+/* planes for slamklt_pyr_download (names follow LKPyramid / LKCache fields, pyramid.jl:1-24) */
+#define SLAMKLT_PLANE_LAYER 0
+#define SLAMKLT_PLANE_IY 1
+#define SLAMKLT_PLANE_IX 2
+#define SLAMKLT_PLANE_IYY 3 /* integral image of the smoothed Iy*Iy; rebuilt in Float64 on download */
+#define SLAMKLT_PLANE_IXX 4
+#define SLAMKLT_PLANE_IYX 5
+#define SLAMKLT_PLANE_SYY 6 /* smoothed products before integration (LKCache.filtered) */
+#define SLAMKLT_PLANE_SXX 7
+#define SLAMKLT_PLANE_SYX 8
+#define SLAMKLT_PLANE_BLUR 9 /* LKCache.gaussian_filtered (levels 0..L-1) */
+
+typedef struct slamklt_ctx slamklt_ctx;
+typedef struct slamklt_pyr slamklt_pyr;
+typedef struct slamklt_batch slamklt_batch;
+
+/* LucasKanade (lucas_kanade.jl:1-7) + fb_tracking!'s max_distance (tracker.jl:22) */
+typedef struct slamklt_lk_params {
+    int32_t iterations;          /* 30 */
+    int32_t window_size;         /* half width; 9 in Params (params.jl:65), <= 15 supported */
+    int32_t pyramid_levels;      /* 3 */
+    int32_t reserved;
+    double eigenvalue_threshold; /* 1e-4 */
+    double epsilon;              /* 1e-2 */
+    double max_distance;         /* params.max_ktl_distance = 1.0; wrapper default 0.5 */
+} slamklt_lk_params;
+
+/* Extractor (extractor.jl:7-22) + detect kwargs (extractor.jl:24,63) */
+typedef struct slamklt_detect_params {
+    int32_t max_points;
+    int32_t radius;
+    int32_t grid_h, grid_w; /* grid_resolution */
+    int32_t cell_size;      /* <= 64 */
+    int32_t reserved;
+    double sigma_mask;      /* 3.0; 0 skips the mask blur */
+    double min_response;    /* 1e-4 */
+} slamklt_detect_params;
+
+/* per-context timing / counters of the last call(s), filled by slamklt_get_stats */
+typedef struct slamklt_stats {
+    uint64_t kernel_launches; /* kernels launched by this context since creation */
+    uint64_t lk_window_iters; /* executed LK iterations x window pixels (device counter), since last reset */
+    uint64_t lk_iters;        /* executed LK iterations, since last reset */
+    uint64_t h2d_bytes, d2h_bytes; /* since creation */
+} slamklt_stats;
+
+const char* slamklt_last_error(void);
+int slamklt_version(void);
+int slamklt_device_count(void);
+
+/* ---- context --------------------------------------------------------------------------- */
+int slamklt_ctx_create(int device, slamklt_ctx** out);
+int slamklt_ctx_destroy(slamklt_ctx* ctx);
+int slamklt_ctx_sync(slamklt_ctx* ctx);
+int slamklt_get_stats(slamklt_ctx* ctx, slamklt_stats* out, int reset_lk_counters);
+/* CUDA-event stopwatch on the context's own stream (the stream every kernel here is launched on) */
+int slamklt_timer_start(slamklt_ctx* ctx);
+int slamklt_timer_stop(slamklt_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
+
+/* ---- LKPyramid ------------------------------------------------------------------------- */
+/* allocation of LKPyramid(image, levels; reusable=true) -- pyramid.jl:40-72 */
+int slamklt_pyr_create(slamklt_ctx* ctx, int H, int W, int levels, slamklt_pyr** out);
+int slamklt_pyr_destroy(slamklt_ctx* ctx, slamklt_pyr* pyr);
+/* LKPyramid ctor (mode CTOR, pyramid.jl:40-79) and update!(lk, img; sigma) (mode UPDATE, pyramid.jl:81-96) */
+int slamklt_pyr_build(slamklt_ctx* ctx, slamklt_pyr* pyr, const void* img, int dtype, int ld, double sigma, int mode);
+/* Base.copy!(dst::LKPyramid, src) -- pyramid.jl:28-38 */
+int slamklt_pyr_copy(slamklt_ctx* ctx, slamklt_pyr* dst, const slamklt_pyr* src);
+/* deepcopy(front_end.current_pyramid) -- SLAM.jl:216-219 */
+int slamklt_pyr_clone(slamklt_ctx* ctx, const slamklt_pyr* src, slamklt_pyr** out);
+/* O(1) replacement for copy!(previous, current) followed by update!(current, img) -- front_end.jl:459-461 */
+int slamklt_pyr_swap(slamklt_ctx* ctx, slamklt_pyr* a, slamklt_pyr* b);
+int slamklt_pyr_info(const slamklt_pyr* pyr, int* H, int* W, int* levels, int* built /* has_gradients, pyramid.jl:26 */);
+int slamklt_pyr_level_dims(const slamklt_pyr* pyr, int level, int* H, int* W);
+/* field access lk.layers[l+1], lk.Iy[l+1], ... as Float64 column-major H_l x W_l (level is 0-based) */
+int slamklt_pyr_download(slamklt_ctx* ctx, const slamklt_pyr* pyr, int level, int plane, double* out);
+
+/* ---- Lucas-Kanade ---------------------------------------------------------------------- */
+/* optflow!(displacement, first, second, points, algorithm) -- lucas_kanade.jl:9-100.
+ * disp_inout (n x 2, coarsest-level scale) is updated in place like the reference; status[i] in {0,1};
+ * *n_good receives the number of surviving points. */
+int slamklt_optflow(slamklt_ctx* ctx, const slamklt_pyr* first, const slamklt_pyr* second, const double* pts_yx,
+                    double* disp_inout, int n, const slamklt_lk_params* p, uint8_t* status, int* n_good);
+/* fb_tracking!(new_keypoints, previous, current, keypoints, algorithm; displacement, max_distance)
+ * -- tracker.jl:17-68.  disp_yx may be NULL (zeros).  out_pts_yx[i] is written only where the forward
+ * pass succeeded (as in the reference).  status bit0 = returned status, bit1 = forward-pass status. */
+int slamklt_fb_track(slamklt_ctx* ctx, const slamklt_pyr* previous, const slamklt_pyr* current, const double* pts_yx,
+                     const double* disp_yx, int n, const slamklt_lk_params* p, double* out_pts_yx, uint8_t* status);
+
+/* ---- Extractor ------------------------------------------------------------------------- */
+/* detect(e, image, current_points; sigma_mask) -- extractor.jl:63-95.  out_yx: cap pairs of Int64.
+ * *n_out receives the number of detected keypoints (no global cap, like the reference). */
+int slamklt_detect(slamklt_ctx* ctx, const void* img, int dtype, int H, int W, int ld, const double* cur_pts_yx,
+                   int n_cur, const slamklt_detect_params* p, int64_t* out_yx, int cap, int* n_out);
+
+/* ---- batched stream API (configs 2, 4, 5: many frames in flight, device-resident) --------------
+ * A batch owns n_frames+1 pyramid slots: slot 0 is the previous frame carried over from the last batch,
+ * slots 1..n_frames are the frames of this batch.  Pair i tracks points[i] from slot i to slot i+1
+ * (preprocess! + klt_tracking! of front_end.jl:454-481 for n_frames consecutive frames).  After
+ * slamklt_batch_rotate the last slot becomes slot 0 of the next batch (the copy!(previous, current)). */
+int slamklt_batch_create(slamklt_ctx* ctx, int H, int W, int levels, int n_frames, int max_points_per_frame,
+                         slamklt_batch** out);
+int slamklt_batch_destroy(slamklt_ctx* ctx, slamklt_batch* b);
+/* build slot 0 from one host image (first frame of a stream) */
+int slamklt_batch_prime(slamklt_ctx* ctx, slamklt_batch* b, const void* img, int dtype, int ld, double sigma, int mode);
+/* async H2D of n_frames images (frame f at img + f*frame_stride_bytes) and of n_frames x n_pts x 2 points */
+int slamklt_batch_upload(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, int dtype, int ld,
+                         size_t frame_stride_bytes, const double* pts_yx, int n_pts);
+/* device-side work only: build all n_frames pyramids, then forward-backward track every pair */
+int slamklt_batch_build(slamklt_ctx* ctx, slamklt_batch* b, double sigma, int mode);
+int slamklt_batch_track(slamklt_ctx* ctx, slamklt_batch* b, const slamklt_lk_params* p);
+/* async D2H of n_frames x n_pts x 2 tracked points and n_frames x n_pts status bytes, then stream sync */
+int slamklt_batch_download(slamklt_ctx* ctx, slamklt_batch* b, double* out_pts_yx, uint8_t* status);
+int slamklt_batch_rotate(slamklt_ctx* ctx, slamklt_batch* b);
+/* whole step through host buffers: upload + build + track + download + rotate */
+int slamklt_batch_step(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, int dtype, int ld,
+                       size_t frame_stride_bytes, const double* pts_yx, int n_pts, double sigma, int mode,
+                       const slamklt_lk_params* p, double* out_pts_yx, uint8_t* status);
+/* parity access: view of slot `slot` (0..n_frames) as a pyramid handle owned by the batch */
+int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out);
+/* batched detect on the frames last uploaded to the batch (config 5: re-extraction every frame).
+ * cur_pts: n_frames x n_cur x 2 (may be NULL when n_cur == 0); out_yx: n_frames x cap pairs; n_out: n_frames. */
+int slamklt_batch_detect(slamklt_ctx* ctx, slamklt_batch* b, const double* cur_pts_yx, int n_cur,
+                         const slamklt_detect_params* p, int64_t* out_yx, int cap, int* n_out);
+
+/* pinned host memory helpers (so that async copies really are asynchronous) */
+int slamklt_host_alloc(size_t bytes, void** out);
+int slamklt_host_free(void* p);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMKLT_H */

@@ -1,0 +1,458 @@
+"""slam.jl_b200 -- host-side mirror of SLAM.jl's KLT front-end interface over libslamklt.so.
+
+The reference's host language is Julia, which this image does not have; this Python layer mirrors the
+reference's operator interface for the path (same names, argument meaning and error behaviour) so the
+parity tests read like calls into the reference:
+
+    LKPyramid(image, levels; sigma, reusable)   pyramid.jl:40      -> LKPyramid(ctx, image, levels, sigma=...)
+    update!(pyr, image)                         pyramid.jl:81      -> pyr.update(image)
+    copy!(dst, src)                             pyramid.jl:28      -> dst.copy_from(src)
+    deepcopy(pyr)                               SLAM.jl:216        -> pyr.deepcopy()
+    optflow!(disp, first, second, points, alg)  lucas_kanade.jl:9  -> optflow(disp, first, second, points, alg)
+    fb_tracking!(prev, cur, keypoints; ...)     tracker.jl:70      -> fb_tracking(prev, cur, keypoints, ...)
+    Extractor(max_points, radius, grid, cell)   extractor.jl:21    -> Extractor(...)
+    detect(e, image, current_points)            extractor.jl:63    -> detect(ctx, e, image, current_points)
+
+Everything below is ctypes plumbing over the C ABI declared in include/slamklt.h.  There is NO CPU path:
+if the CUDA library is missing or no B200 is visible, construction fails loudly.
+
+Images are (H, W) arrays (converted to column-major like Julia's Matrix); points are (N, 2) float64 in
+1-based (y, x) order.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libslamklt.so")
+
+F64, F32, U8 = 0, 1, 2
+MODE_UPDATE, MODE_CTOR = 0, 1
+PLANES = {"layer": 0, "Iy": 1, "Ix": 2, "Iyy": 3, "Ixx": 4, "Iyx": 5, "Syy": 6, "Sxx": 7, "Syx": 8, "blur": 9}
+
+E_INVALID, E_CUDA, E_LAYERS, E_NODEVICE, E_CAPACITY = -1, -2, -3, -4, -5
+
+
+class SlamKltError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[slamklt {code}] {msg}")
+        self.code = code
+
+
+class LKParams(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("window_size", C.c_int32), ("pyramid_levels", C.c_int32),
+                ("reserved", C.c_int32), ("eigenvalue_threshold", C.c_double), ("epsilon", C.c_double),
+                ("max_distance", C.c_double)]
+
+
+class DetectParams(C.Structure):
+    _fields_ = [("max_points", C.c_int32), ("radius", C.c_int32), ("grid_h", C.c_int32), ("grid_w", C.c_int32),
+                ("cell_size", C.c_int32), ("reserved", C.c_int32), ("sigma_mask", C.c_double),
+                ("min_response", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("lk_window_iters", C.c_uint64), ("lk_iters", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+def build_library(force: bool = False) -> str:
+    """Compile libslamklt.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in ("api.cu", "pyramid.cu", "lk.cu", "detect.cu", "common.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "slamklt.h"))
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", _CSRC, "-j4", "libslamklt.so"], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+# every symbol include/slamklt.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "slamklt_last_error", "slamklt_version", "slamklt_device_count", "slamklt_ctx_create", "slamklt_ctx_destroy",
+    "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
+    "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
+    "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
+    "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
+    "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_download", "slamklt_batch_rotate",
+    "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
+]
+
+
+def lib():
+    """Load libslamklt.so.  Raises if it has not been built: the product never falls back to a CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SlamKltError(E_NODEVICE, f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, dp, u8p, ip, i64p = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int), C.POINTER(C.c_int64)
+        L.slamklt_last_error.restype = C.c_char_p
+        L.slamklt_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.slamklt_ctx_destroy.argtypes = [vp]
+        L.slamklt_ctx_sync.argtypes = [vp]
+        L.slamklt_get_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
+        L.slamklt_timer_start.argtypes = [vp]
+        L.slamklt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        L.slamklt_pyr_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.slamklt_pyr_destroy.argtypes = [vp, vp]
+        L.slamklt_pyr_build.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.slamklt_pyr_copy.argtypes = [vp, vp, vp]
+        L.slamklt_pyr_clone.argtypes = [vp, vp, C.POINTER(vp)]
+        L.slamklt_pyr_swap.argtypes = [vp, vp, vp]
+        L.slamklt_pyr_info.argtypes = [vp, ip, ip, ip, ip]
+        L.slamklt_pyr_level_dims.argtypes = [vp, C.c_int, ip, ip]
+        L.slamklt_pyr_download.argtypes = [vp, vp, C.c_int, C.c_int, dp]
+        L.slamklt_optflow.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), u8p, ip]
+        L.slamklt_fb_track.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), dp, u8p]
+        L.slamklt_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(DetectParams),
+                                     i64p, C.c_int, ip]
+        L.slamklt_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.slamklt_batch_destroy.argtypes = [vp, vp]
+        L.slamklt_batch_prime.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_int]
+        L.slamklt_batch_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_size_t, dp, C.c_int]
+        L.slamklt_batch_build.argtypes = [vp, vp, C.c_double, C.c_int]
+        L.slamklt_batch_track.argtypes = [vp, vp, C.POINTER(LKParams)]
+        L.slamklt_batch_download.argtypes = [vp, vp, dp, u8p]
+        L.slamklt_batch_rotate.argtypes = [vp, vp]
+        L.slamklt_batch_step.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, C.c_double, C.c_int,
+                                         C.POINTER(LKParams), dp, u8p]
+        L.slamklt_batch_slot.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        L.slamklt_batch_detect.argtypes = [vp, vp, dp, C.c_int, C.POINTER(DetectParams), i64p, C.c_int, ip]
+        L.slamklt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.slamklt_host_free.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc != 0:
+        raise SlamKltError(rc, lib().slamklt_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _image(img):
+    """(array in column-major order, dtype code).  float64 / float32 / uint8 are passed through unconverted."""
+    a = np.asarray(img)
+    if a.dtype == np.float64:
+        code = F64
+    elif a.dtype == np.float32:
+        code = F32
+    elif a.dtype == np.uint8:
+        code = U8
+    else:
+        a, code = a.astype(np.float64), F64
+    if a.ndim != 2:
+        raise SlamKltError(E_INVALID, "image must be 2-D")
+    return np.asfortranarray(a), code
+
+
+class Context:
+    """One CUDA device + stream.  Fails loudly when no B200 is visible."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        _ck(lib().slamklt_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def sync(self):
+        _ck(lib().slamklt_ctx_sync(self._h))
+
+    def stats(self, reset=False) -> dict:
+        s = Stats()
+        _ck(lib().slamklt_get_stats(self._h, C.byref(s), 1 if reset else 0))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def timer_start(self):
+        _ck(lib().slamklt_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _ck(lib().slamklt_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().slamklt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LucasKanade:
+    """lucas_kanade.jl:1-7"""
+
+    def __init__(self, iterations=30, window_size=9, pyramid_levels=3, eigenvalue_threshold=1e-4, eps=1e-2):
+        self.iterations, self.window_size, self.pyramid_levels = iterations, window_size, pyramid_levels
+        self.eigenvalue_threshold, self.eps = eigenvalue_threshold, eps
+
+    def _c(self, max_distance=0.5):
+        return LKParams(self.iterations, self.window_size, self.pyramid_levels, 0, self.eigenvalue_threshold,
+                        self.eps, float(max_distance))
+
+
+class LKPyramid:
+    """LKPyramid (pyramid.jl:16-96), device resident."""
+
+    def __init__(self, ctx: Context, image=None, levels: int = 3, sigma: float = 1.0, shape=None, _handle=None,
+                 _owner=None):
+        self.ctx = ctx
+        self._owner = _owner
+        if _handle is not None:
+            self._h = _handle
+        else:
+            if image is not None:
+                image, _ = _image(image)
+                shape = image.shape
+            h = C.c_void_p()
+            _ck(lib().slamklt_pyr_create(ctx._h, int(shape[0]), int(shape[1]), int(levels), C.byref(h)))
+            self._h = h
+            if image is not None:
+                self._build(image, sigma, MODE_CTOR)  # the constructor path: NA blur border, Fill(0) Scharr
+
+    def _build(self, image, sigma, mode):
+        a, code = _image(image)
+        H, W = self.shape
+        if a.shape != (H, W):
+            raise SlamKltError(E_INVALID, f"image shape {a.shape} != pyramid shape {(H, W)}")
+        _ck(lib().slamklt_pyr_build(self.ctx._h, self._h, a.ctypes.data_as(C.c_void_p), code, H, float(sigma), mode))
+        return self
+
+    def update(self, image, sigma: float = 1.0):
+        """update!(lk, img; sigma) pyramid.jl:81-96"""
+        return self._build(image, sigma, MODE_UPDATE)
+
+    def _info(self):
+        H, W, L, b = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _ck(lib().slamklt_pyr_info(self._h, C.byref(H), C.byref(W), C.byref(L), C.byref(b)))
+        return H.value, W.value, L.value, bool(b.value)
+
+    @property
+    def shape(self):
+        return self._info()[:2]
+
+    @property
+    def levels(self):
+        return self._info()[2]
+
+    def has_gradients(self):
+        return self._info()[3]
+
+    def level_shape(self, level):
+        H, W = C.c_int(), C.c_int()
+        _ck(lib().slamklt_pyr_level_dims(self._h, level, C.byref(H), C.byref(W)))
+        return H.value, W.value
+
+    def plane(self, level: int, name: str) -> np.ndarray:
+        """lk.layers[level+1], lk.Iy[level+1], ... as Float64 (H_l, W_l)."""
+        H, W = self.level_shape(level)
+        out = np.empty((H, W), dtype=np.float64, order="F")
+        _ck(lib().slamklt_pyr_download(self.ctx._h, self._h, level, PLANES[name], _dp(out)))
+        return out
+
+    def copy_from(self, src: "LKPyramid"):
+        """copy!(dst, src) pyramid.jl:28-38"""
+        _ck(lib().slamklt_pyr_copy(self.ctx._h, self._h, src._h))
+        return self
+
+    def deepcopy(self) -> "LKPyramid":
+        h = C.c_void_p()
+        _ck(lib().slamklt_pyr_clone(self.ctx._h, self._h, C.byref(h)))
+        return LKPyramid(self.ctx, _handle=h)
+
+    def swap(self, other: "LKPyramid"):
+        _ck(lib().slamklt_pyr_swap(self.ctx._h, self._h, other._h))
+
+    def __del__(self):
+        try:
+            if self._owner is None and getattr(self, "_h", None) and self.ctx._h:
+                lib().slamklt_pyr_destroy(self.ctx._h, self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def optflow(displacement, first: LKPyramid, second: LKPyramid, points, algorithm: LucasKanade):
+    """optflow! (lucas_kanade.jl:9-100).  Returns (displacement, status, n_good); raises like the reference's
+    throw("Not enough layers in pyramids.") when a pyramid is too shallow."""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+    disp = np.array(displacement, dtype=np.float64, copy=True).reshape(-1, 2)
+    st = np.zeros(len(pts), dtype=np.uint8)
+    ng = C.c_int()
+    p = algorithm._c()
+    _ck(lib().slamklt_optflow(first.ctx._h, first._h, second._h, _dp(pts), _dp(disp), len(pts), C.byref(p),
+                              st.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(ng)))
+    return disp, st.astype(bool), ng.value
+
+
+def fb_tracking(previous: LKPyramid, current: LKPyramid, keypoints, displacement=None, iterations=30, window_size=11,
+                pyramid_levels=3, max_distance=0.5, eigenvalue_threshold=1e-4, eps=1e-2):
+    """fb_tracking! (tracker.jl:17-82).  Returns None for empty input (tracker.jl:24), else
+    (new_keypoints, status, forward_status); new_keypoints rows are NaN where the forward pass failed
+    (undefined in the reference)."""
+    pts = np.ascontiguousarray(keypoints, dtype=np.float64).reshape(-1, 2)
+    n = len(pts)
+    if n == 0:
+        return None
+    out = np.full((n, 2), np.nan)
+    st = np.zeros(n, dtype=np.uint8)
+    d = None if displacement is None else np.ascontiguousarray(displacement, dtype=np.float64).reshape(-1, 2)
+    p = LKParams(iterations, window_size, pyramid_levels, 0, eigenvalue_threshold, eps, float(max_distance))
+    _ck(lib().slamklt_fb_track(previous.ctx._h, previous._h, current._h, _dp(pts), None if d is None else _dp(d), n,
+                               C.byref(p), _dp(out), st.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out, (st & 1).astype(bool), ((st >> 1) & 1).astype(bool)
+
+
+class Extractor:
+    """Extractor (extractor.jl:7-22); the BRIEF descriptor is out of scope."""
+
+    def __init__(self, max_points, radius, grid_resolution, cell_size):
+        self.max_points, self.radius = int(max_points), int(radius)
+        self.grid_resolution, self.cell_size = (int(grid_resolution[0]), int(grid_resolution[1])), int(cell_size)
+
+    def _c(self, sigma_mask=3.0, min_response=1e-4):
+        return DetectParams(self.max_points, self.radius, self.grid_resolution[0], self.grid_resolution[1],
+                            self.cell_size, 0, float(sigma_mask), float(min_response))
+
+
+def detect(ctx: Context, e: Extractor, image, current_points, sigma_mask=3.0, min_response=1e-4) -> np.ndarray:
+    """detect (extractor.jl:63-95).  Returns (n, 2) int64 1-based (y, x) keypoints."""
+    a, code = _image(image)
+    H, W = a.shape
+    cur = np.ascontiguousarray(current_points, dtype=np.float64).reshape(-1, 2)
+    k_cell = -(-max(e.max_points - len(cur), 0) // (e.grid_resolution[0] * e.grid_resolution[1]))
+    cap = max(1, min(k_cell, e.cell_size * e.cell_size) * e.grid_resolution[0] * e.grid_resolution[1])
+    out = np.empty((cap, 2), dtype=np.int64)
+    n = C.c_int()
+    p = e._c(sigma_mask, min_response)
+    _ck(lib().slamklt_detect(ctx._h, a.ctypes.data_as(C.c_void_p), code, H, W, H, _dp(cur) if len(cur) else None, len(cur),
+                             C.byref(p), out.ctypes.data_as(C.POINTER(C.c_int64)), cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _ck(lib().slamklt_host_alloc(max(self.nbytes, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().slamklt_host_free(self._p)
+            self._p = None
+
+
+class StreamBatch:
+    """n_frames consecutive frames of one stream processed in one go (preprocess! + klt_tracking! of
+    front_end.jl:454-481, batched).  Frames are (n_frames, W, H)-shaped C arrays, i.e. each frame column-major."""
+
+    def __init__(self, ctx: Context, H, W, levels, n_frames, max_points):
+        self.ctx, self.H, self.W, self.levels, self.n_frames, self.max_points = ctx, H, W, levels, n_frames, max_points
+        h = C.c_void_p()
+        _ck(lib().slamklt_batch_create(ctx._h, H, W, levels, n_frames, max_points, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def pack_frames(frames) -> np.ndarray:
+        """(n, H, W) array -> (n, W, H) C-contiguous (each frame column-major), dtype preserved."""
+        f = np.asarray(frames)
+        return np.ascontiguousarray(np.transpose(f, (0, 2, 1)))
+
+    @staticmethod
+    def _code(a):
+        return {np.dtype(np.float64): F64, np.dtype(np.float32): F32, np.dtype(np.uint8): U8}[a.dtype]
+
+    def prime(self, image, sigma=1.0, mode=MODE_CTOR):
+        a, code = _image(image)
+        _ck(lib().slamklt_batch_prime(self.ctx._h, self._h, a.ctypes.data_as(C.c_void_p), code, self.H, float(sigma), mode))
+
+    def upload(self, packed_frames: np.ndarray, points: np.ndarray):
+        assert packed_frames.shape == (self.n_frames, self.W, self.H) and packed_frames.flags.c_contiguous
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(self.n_frames, -1, 2)
+        _ck(lib().slamklt_batch_upload(self.ctx._h, self._h, packed_frames.ctypes.data_as(C.c_void_p), self._code(packed_frames),
+                                       self.H, packed_frames.strides[0], _dp(pts), pts.shape[1]))
+        self._npts = pts.shape[1]
+
+    def build(self, sigma=1.0, mode=MODE_UPDATE):
+        _ck(lib().slamklt_batch_build(self.ctx._h, self._h, float(sigma), mode))
+
+    def track(self, alg: LucasKanade, max_distance=1.0):
+        p = alg._c(max_distance)
+        _ck(lib().slamklt_batch_track(self.ctx._h, self._h, C.byref(p)))
+
+    def download(self, out_pts=None, status=None):
+        if out_pts is None:
+            out_pts = np.empty((self.n_frames, self._npts, 2))
+        if status is None:
+            status = np.empty((self.n_frames, self._npts), dtype=np.uint8)
+        _ck(lib().slamklt_batch_download(self.ctx._h, self._h, _dp(out_pts), status.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out_pts, status
+
+    def rotate(self):
+        _ck(lib().slamklt_batch_rotate(self.ctx._h, self._h))
+
+    def step(self, packed_frames, points, alg: LucasKanade, max_distance=1.0, sigma=1.0, mode=MODE_UPDATE, out_pts=None,
+             status=None):
+        """Whole step through host buffers (upload, build, track, download, rotate) in one C call."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(self.n_frames, -1, 2)
+        n = pts.shape[1]
+        if out_pts is None:
+            out_pts = np.empty((self.n_frames, n, 2))
+        if status is None:
+            status = np.empty((self.n_frames, n), dtype=np.uint8)
+        p = alg._c(max_distance)
+        _ck(lib().slamklt_batch_step(self.ctx._h, self._h, packed_frames.ctypes.data_as(C.c_void_p), self._code(packed_frames),
+                                     self.H, packed_frames.strides[0], _dp(pts), n, float(sigma), mode, C.byref(p), _dp(out_pts),
+                                     status.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._npts = n
+        return out_pts, status
+
+    def slot(self, i) -> LKPyramid:
+        h = C.c_void_p()
+        _ck(lib().slamklt_batch_slot(self._h, i, C.byref(h)))
+        return LKPyramid(self.ctx, _handle=h, _owner=self)
+
+    def detect(self, e: Extractor, current_points=None, sigma_mask=3.0, min_response=1e-4):
+        """Batched detect on the frames last uploaded.  Returns a list of (n_f, 2) int64 arrays."""
+        n_cur = 0 if current_points is None else np.asarray(current_points).reshape(self.n_frames, -1, 2).shape[1]
+        cur = None if n_cur == 0 else np.ascontiguousarray(current_points, dtype=np.float64).reshape(self.n_frames, -1, 2)
+        cells = e.grid_resolution[0] * e.grid_resolution[1]
+        k_cell = -(-max(e.max_points - n_cur, 0) // cells)
+        cap = max(1, min(k_cell, e.cell_size * e.cell_size) * cells)
+        out = np.empty((self.n_frames, cap, 2), dtype=np.int64)
+        n = np.zeros(self.n_frames, dtype=np.int32)
+        p = e._c(sigma_mask, min_response)
+        _ck(lib().slamklt_batch_detect(self.ctx._h, self._h, None if cur is None else _dp(cur), n_cur, C.byref(p),
+                                       out.ctypes.data_as(C.POINTER(C.c_int64)), cap, n.ctypes.data_as(C.POINTER(C.c_int))))
+        return [out[f, :n[f]].copy() for f in range(self.n_frames)]
+
+    def close(self):
+        if getattr(self, "_h", None) and self.ctx._h:
+            lib().slamklt_batch_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,887 @@
+// C ABI of libslamklt.so (see include/slamklt.h).  Host-side plumbing only: contexts, device memory,
+// copies, launch sequencing.  All compute is in pyramid.cu / lk.cu / detect.cu; there is no CPU fallback.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace sk;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(SLAMKLT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKL()                                                                                             \
+    do {                                                                                                  \
+        cudaError_t e_ = cudaGetLastError();                                                              \
+        if (e_ != cudaSuccess) return fail(SLAMKLT_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// recursive Gaussian design (host, double).  [3P] ImageFiltering KernelFactors.IIRGaussian / TriggsSdika.
+// ---------------------------------------------------------------------------------------------
+namespace sk {
+
+void iir_design(double sigma, double a[3], double* scale, double M[9]) {
+    const double m0 = 1.16680, m1 = 1.10783, m2 = 1.40586;
+    const double q = 1.31564 * (std::sqrt(1.0 + 0.490811 * sigma * sigma) - 1.0);
+    const double as = (m0 + q) * (m1 * m1 + m2 * m2 + 2 * m1 * q + q * q);
+    double B = m0 * (m1 * m1 + m2 * m2) / as;
+    *scale = B * B;
+    const double a1 = q * (2 * m0 * m1 + m1 * m1 + m2 * m2 + (2 * m0 + 4 * m1) * q + 3 * q * q) / as;
+    const double a2 = -q * q * (m0 + 2 * m1 + 3 * q) / as;
+    const double a3 = q * q * q / as;
+    a[0] = a1; a[1] = a2; a[2] = a3;
+    const double den = (1 + a1 - a2 + a3) * (1 - a1 - a2 - a3) * (1 + a2 + (a1 - a3) * a3);
+    M[0] = (-a3 * a1 + 1 - a3 * a3 - a2) / den;
+    M[1] = ((a3 + a1) * (a2 + a3 * a1)) / den;
+    M[2] = (a3 * (a1 + a3 * a2)) / den;
+    M[3] = (a1 + a3 * a2) / den;
+    M[4] = (-(a2 - 1) * (a2 + a3 * a1)) / den;
+    M[5] = (-(a3 * a1 + a3 * a3 + a2 - 1) * a3) / den;
+    M[6] = (a3 * a1 + a2 + a1 * a1 - a2 * a2) / den;
+    M[7] = (a1 * a2 + a3 * a2 * a2 - a1 * a3 * a3 - a3 * a3 * a3 - a3 * a2 + a3) / den;
+    M[8] = (a3 * (a1 + a3 * a2)) / den;
+}
+
+static void mat3_mul(const double* A, const double* B, double* C) {
+    double t[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += A[3 * i + k] * B[3 * k + j];
+            t[3 * i + j] = s;
+        }
+    std::memcpy(C, t, sizeof(t));
+}
+
+static void mat3_pow(const double* A, int n, double* out) {
+    double r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, b[9];
+    std::memcpy(b, A, sizeof(b));
+    while (n > 0) {
+        if (n & 1) mat3_mul(r, b, r);
+        mat3_mul(b, b, b);
+        n >>= 1;
+    }
+    std::memcpy(out, r, sizeof(r));
+}
+
+void iir_dev(double sigma, int K, int KRr, IirDev* o) {
+    double a[3], sc, M[9];
+    iir_design(sigma, a, &sc, M);
+    o->a1 = (float)a[0]; o->a2 = (float)a[1]; o->a3 = (float)a[2];
+    o->scale = (float)sc;
+    o->inv1ma = (float)(1.0 / (1.0 - (a[0] + a[1] + a[2])));
+    for (int i = 0; i < 9; ++i) o->M[i] = (float)M[i];
+    const double A[9] = {a[0], a[1], a[2], 1, 0, 0, 0, 1, 0};  // companion matrix of the recursion
+    double P[9];
+    for (int j = 0; j < 5; ++j) {
+        mat3_pow(A, K << j, P);
+        for (int i = 0; i < 9; ++i) o->P[j][i] = (float)P[i];
+    }
+    mat3_pow(A, KRr, P);
+    for (int i = 0; i < 9; ++i) o->PK[i] = (float)P[i];
+}
+
+void iir_line_host(double* x, int n, double sigma, double iminus, double iplus) {
+    double a[3], sc, M[9];
+    iir_design(sigma, a, &sc, M);
+    const double asum = a[0] + a[1] + a[2];
+    const double um = iminus / (1.0 - asum);
+    double u1 = um, u2 = um, u3 = um;
+    for (int i = 0; i < n; ++i) {
+        double u = x[i] + a[0] * u1 + a[1] * u2 + a[2] * u3;
+        x[i] = u; u3 = u2; u2 = u1; u1 = u;
+    }
+    const double up = iplus / (1.0 - asum), vp = up / (1.0 - asum);
+    const double d0 = x[n - 1] - up, d1 = x[n - 2] - up, d2 = x[n - 3] - up;
+    double v1 = M[0] * d0 + M[1] * d1 + M[2] * d2 + vp;
+    double v2 = M[3] * d0 + M[4] * d1 + M[5] * d2 + vp;
+    double v3 = M[6] * d0 + M[7] * d1 + M[8] * d2 + vp;
+    x[n - 1] = v1;
+    for (int i = n - 2; i >= 0; --i) {
+        double v = x[i] + a[0] * v1 + a[1] * v2 + a[2] * v3;
+        x[i] = v; v3 = v2; v2 = v1; v1 = v;
+    }
+    for (int i = 0; i < n; ++i) x[i] *= sc;
+}
+
+}  // namespace sk
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(SLAMKLT_E_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(SLAMKLT_E_CUDA, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct slamklt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    unsigned long long* d_counters = nullptr;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur;
+    HostBuf h_out, h_status, h_misc;
+    std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
+};
+
+struct slamklt_pyr {
+    PyrGeom g;
+    float* base = nullptr;
+    bool owns = false;
+    bool built = false;
+    int mode = 0;
+    slamklt_batch* parent = nullptr;
+    int logical_slot = 0;
+};
+
+struct slamklt_batch {
+    PyrGeom g;
+    float* base = nullptr;
+    int n_frames = 0, n_slots = 0, slot0 = 0, max_pts = 0, n_pts = 0;
+    int up_dtype = -1, up_ld = 0;
+    DevBuf staging, img64, pts, outp, status;
+    std::vector<slamklt_pyr*> views;
+    bool primed = false;
+};
+
+static int make_geom(int H, int W, int levels, PyrGeom* g) {
+    if (H < 4 || W < 4) return fail(SLAMKLT_E_INVALID, "image %dx%d too small", H, W);
+    if (levels < 0 || levels + 1 > MAX_LAYERS) return fail(SLAMKLT_E_INVALID, "pyramid_levels %d out of range [0,%d]", levels, MAX_LAYERS - 1);
+    std::memset(g, 0, sizeof(*g));
+    g->nl = levels + 1; g->H0 = H; g->W0 = W;
+    size_t off = 0;
+    int h = H, w = W;
+    for (int l = 0; l < g->nl; ++l) {
+        if (h < 4 || w < 4) return fail(SLAMKLT_E_INVALID, "level %d is %dx%d: recursive filter needs more than 3 samples per line", l, h, w);
+        if (pick_K(h) == 0) return fail(SLAMKLT_E_INVALID, "image height %d exceeds the supported 1088", h);
+        if (w > 2048) return fail(SLAMKLT_E_INVALID, "image width %d exceeds the supported 2048", w);
+        LevelGeom& L = g->lv[l];
+        L.H = h; L.W = w; L.pitch = (h + 3) & ~3;
+        L.plane_elems = (((size_t)L.pitch * w) + 31) & ~(size_t)31;
+        L.off = off;
+        off += L.plane_elems * DP_COUNT;
+        h = (h + 1) / 2; w = (w + 1) / 2;  // ceil(s/2), [3P] Images.gaussian_pyramid
+    }
+    g->frame_elems = off;
+    return 0;
+}
+
+static float* pyr_frame_base(const slamklt_pyr* p) {
+    if (p->parent) {
+        const slamklt_batch* b = p->parent;
+        return b->base + (size_t)((b->slot0 + p->logical_slot) % b->n_slots) * b->g.frame_elems;
+    }
+    return p->base;
+}
+static FrameSet fs_of(const slamklt_pyr* p) { return FrameSet{pyr_frame_base(p), p->g.frame_elems, 1, 0}; }
+static FrameSet fs_of(const slamklt_batch* b) { return FrameSet{b->base, b->g.frame_elems, b->n_slots, b->slot0}; }
+
+static int get_norms(slamklt_ctx* c, const PyrGeom& g, double sigma, const float** ny, const float** nx) {
+    long long bits;
+    std::memcpy(&bits, &sigma, sizeof(bits));
+    for (int l = 0; l + 1 < g.nl; ++l) {
+        for (int d = 0; d < 2; ++d) {
+            const int n = d == 0 ? g.lv[l].H : g.lv[l].W;
+            auto key = std::make_pair(n, bits);
+            auto it = c->norm_cache.find(key);
+            if (it == c->norm_cache.end()) {
+                std::vector<double> ones(n, 1.0);
+                iir_line_host(ones.data(), n, sigma, 0.0, 0.0);
+                std::vector<float> inv(n);
+                for (int i = 0; i < n; ++i) inv[i] = (float)(1.0 / ones[i]);
+                float* dptr = nullptr;
+                CK(cudaMalloc(&dptr, sizeof(float) * n));
+                CK(cudaMemcpyAsync(dptr, inv.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                it = c->norm_cache.emplace(key, dptr).first;
+            }
+            (d == 0 ? ny : nx)[l] = it->second;
+        }
+    }
+    return 0;
+}
+
+static size_t dtype_size(int dtype) { return dtype == SLAMKLT_F64 ? 8 : dtype == SLAMKLT_F32 ? 4 : 1; }
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* slamklt_last_error(void) { return g_err; }
+int slamklt_version(void) { return SLAMKLT_VERSION; }
+
+int slamklt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int slamklt_ctx_create(int device, slamklt_ctx** out) {
+    if (!out) return fail(SLAMKLT_E_INVALID, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(SLAMKLT_E_NODEVICE, "no CUDA device visible (%s); libslamklt has no CPU fallback", e == cudaSuccess ? "count 0" : cudaGetErrorString(e)); }
+    if (device < 0 || device >= n) return fail(SLAMKLT_E_INVALID, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SLAMKLT_E_NODEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CK(cudaSetDevice(device));
+    slamklt_ctx* c = new slamklt_ctx();
+    c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    *out = c;
+    return 0;
+}
+
+int slamklt_ctx_destroy(slamklt_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->norm_cache) cudaFree(kv.second);
+    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur};
+    for (DevBuf* b : bufs) b->release();
+    c->h_out.release(); c->h_status.release(); c->h_misc.release();
+    cudaFree(c->d_counters);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int slamklt_ctx_sync(slamklt_ctx* c) {
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slamklt_get_stats(slamklt_ctx* c, slamklt_stats* out, int reset) {
+    if (!c || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    out->kernel_launches = c->launches;
+    out->lk_window_iters = h[0]; out->lk_iters = h[1];
+    out->h2d_bytes = c->h2d; out->d2h_bytes = c->d2h;
+    if (reset) CK(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
+    return 0;
+}
+
+int slamklt_timer_start(slamklt_ctx* c) {
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    return 0;
+}
+
+int slamklt_timer_stop(slamklt_ctx* c, float* ms) {
+    if (!c || !ms) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
+// ---- pyramids --------------------------------------------------------------------------------
+int slamklt_pyr_create(slamklt_ctx* c, int H, int W, int levels, slamklt_pyr** out) {
+    if (!c || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    PyrGeom g;
+    int r = make_geom(H, W, levels, &g);
+    if (r) return r;
+    slamklt_pyr* p = new slamklt_pyr();
+    p->g = g;
+    cudaError_t e = cudaMalloc(&p->base, g.frame_elems * sizeof(float));
+    if (e != cudaSuccess) { delete p; return fail(SLAMKLT_E_CUDA, "cudaMalloc pyramid failed: %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(p->base, 0, g.frame_elems * sizeof(float), c->stream);
+    p->owns = true;
+    *out = p;
+    return 0;
+}
+
+int slamklt_pyr_destroy(slamklt_ctx* c, slamklt_pyr* p) {
+    if (!p) return 0;
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    if (p->parent) return fail(SLAMKLT_E_INVALID, "pyramid is a batch slot view; destroy the batch instead");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (p->owns && p->base) cudaFree(p->base);
+    delete p;
+    return 0;
+}
+
+static int upload_frames(slamklt_ctx* c, DevBuf& staging, const void* img, int dtype, int ld, size_t frame_stride_bytes, int n_frames, int H, int W) {
+    const size_t es = dtype_size(dtype);
+    int r = staging.ensure((size_t)n_frames * H * W * es);
+    if (r) return r;
+    if (ld == H && (n_frames == 1 || frame_stride_bytes == (size_t)H * W * es)) {
+        CK(cudaMemcpyAsync(staging.p, img, (size_t)n_frames * H * W * es, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        for (int f = 0; f < n_frames; ++f)
+            CK(cudaMemcpy2DAsync((char*)staging.p + (size_t)f * H * W * es, (size_t)H * es, (const char*)img + (size_t)f * frame_stride_bytes,
+                                 (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->h2d += (uint64_t)n_frames * H * W * es;
+    return 0;
+}
+
+static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const PyrGeom& g, const void* staged, int dtype, double sigma, int mode,
+                        double* img64) {
+    if (!(sigma > 0)) return fail(SLAMKLT_E_INVALID, "sigma must be positive");
+    const float* ny[MAX_LAYERS] = {nullptr};
+    const float* nx[MAX_LAYERS] = {nullptr};
+    if (mode == SLAMKLT_MODE_CTOR) {
+        int r = get_norms(c, g, sigma, ny, nx);
+        if (r) return r;
+    }
+    c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64);
+    CKL();
+    c->launches += launch_pyramid(c->stream, fs, f0, n_frames, g, sigma, mode, ny, nx);
+    CKL();
+    return 0;
+}
+
+int slamklt_pyr_build(slamklt_ctx* c, slamklt_pyr* p, const void* img, int dtype, int ld, double sigma, int mode) {
+    if (!c || !p || !img) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
+    if (ld < p->g.H0) return fail(SLAMKLT_E_INVALID, "ld %d < H %d", ld, p->g.H0);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, p->g.H0, p->g.W0);
+    if (r) return r;
+    r = build_frames(c, fs_of(p), 0, 1, p->g, c->staging.p, dtype, sigma, mode, nullptr);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));  // the caller may free img right after the call
+    p->built = true; p->mode = mode;
+    return 0;
+}
+
+int slamklt_pyr_copy(slamklt_ctx* c, slamklt_pyr* dst, const slamklt_pyr* src) {
+    if (!c || !dst || !src) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dst->g.H0 != src->g.H0 || dst->g.W0 != src->g.W0 || dst->g.nl != src->g.nl) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(dst->base, src->base, src->g.frame_elems * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    dst->built = src->built; dst->mode = src->mode;
+    return 0;
+}
+
+int slamklt_pyr_clone(slamklt_ctx* c, const slamklt_pyr* src, slamklt_pyr** out) {
+    if (!c || !src || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    slamklt_pyr* p = nullptr;
+    int r = slamklt_pyr_create(c, src->g.H0, src->g.W0, src->g.nl - 1, &p);
+    if (r) return r;
+    r = slamklt_pyr_copy(c, p, src);
+    if (r) { slamklt_pyr_destroy(c, p); return r; }
+    r = slamklt_ctx_sync(c);
+    if (r) return r;
+    *out = p;
+    return 0;
+}
+
+int slamklt_pyr_swap(slamklt_ctx* c, slamklt_pyr* a, slamklt_pyr* b) {
+    if (!c || !a || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (a->parent || b->parent) return fail(SLAMKLT_E_INVALID, "cannot swap batch slot views");
+    if (a->g.H0 != b->g.H0 || a->g.W0 != b->g.W0 || a->g.nl != b->g.nl) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::swap(a->base, b->base);
+    std::swap(a->built, b->built);
+    std::swap(a->mode, b->mode);
+    std::swap(a->owns, b->owns);
+    return 0;
+}
+
+int slamklt_pyr_info(const slamklt_pyr* p, int* H, int* W, int* levels, int* built) {
+    if (!p) return fail(SLAMKLT_E_INVALID, "pyr is NULL");
+    if (H) *H = p->g.H0;
+    if (W) *W = p->g.W0;
+    if (levels) *levels = p->g.nl - 1;
+    if (built) *built = p->built ? 1 : 0;
+    return 0;
+}
+
+int slamklt_pyr_level_dims(const slamklt_pyr* p, int level, int* H, int* W) {
+    if (!p) return fail(SLAMKLT_E_INVALID, "pyr is NULL");
+    if (level < 0 || level >= p->g.nl) return fail(SLAMKLT_E_INVALID, "level %d out of range", level);
+    if (H) *H = p->g.lv[level].H;
+    if (W) *W = p->g.lv[level].W;
+    return 0;
+}
+
+int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int plane, double* out) {
+    if (!c || !p || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (level < 0 || level >= p->g.nl) return fail(SLAMKLT_E_INVALID, "level %d out of range", level);
+    int dp;
+    bool sat = false;
+    switch (plane) {
+        case SLAMKLT_PLANE_LAYER: dp = DP_I; break;
+        case SLAMKLT_PLANE_IY: dp = DP_IY; break;
+        case SLAMKLT_PLANE_IX: dp = DP_IX; break;
+        case SLAMKLT_PLANE_IYY: dp = DP_SYY; sat = true; break;
+        case SLAMKLT_PLANE_IXX: dp = DP_SXX; sat = true; break;
+        case SLAMKLT_PLANE_IYX: dp = DP_SYX; sat = true; break;
+        case SLAMKLT_PLANE_SYY: dp = DP_SYY; break;
+        case SLAMKLT_PLANE_SXX: dp = DP_SXX; break;
+        case SLAMKLT_PLANE_SYX: dp = DP_SYX; break;
+        case SLAMKLT_PLANE_BLUR: dp = DP_BLUR; break;
+        default: return fail(SLAMKLT_E_INVALID, "unknown plane %d", plane);
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const LevelGeom& L = p->g.lv[level];
+    std::vector<float> tmp((size_t)L.H * L.W);
+    const float* src = pyr_frame_base(p) + plane_off(L, dp);
+    CK(cudaMemcpy2DAsync(tmp.data(), (size_t)L.H * sizeof(float), src, (size_t)L.pitch * sizeof(float), (size_t)L.H * sizeof(float), L.W,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += tmp.size() * sizeof(float);
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+    if (sat) {  // integral_image!, lucas_kanade.jl:131-138, in Float64 on the host (parity access only)
+        for (int x = 0; x < L.W; ++x) {
+            double acc = 0;
+            for (int y = 0; y < L.H; ++y) { acc += out[y + (size_t)x * L.H]; out[y + (size_t)x * L.H] = acc; }
+        }
+        for (int x = 1; x < L.W; ++x)
+            for (int y = 0; y < L.H; ++y) out[y + (size_t)x * L.H] += out[y + (size_t)(x - 1) * L.H];
+    }
+    return 0;
+}
+
+// ---- Lucas-Kanade ----------------------------------------------------------------------------
+static int fill_lk_levels(const PyrGeom& g, LKArgs* a) {
+    a->nl = g.nl;
+    for (int l = 0; l < g.nl; ++l) {
+        const LevelGeom& L = g.lv[l];
+        LKLevel& d = a->lv[l];
+        d.H = L.H; d.W = L.W; d.pitch = L.pitch;
+        d.oI = plane_off(L, DP_I); d.oIy = plane_off(L, DP_IY); d.oIx = plane_off(L, DP_IX);
+        d.oSyy = plane_off(L, DP_SYY); d.oSxx = plane_off(L, DP_SXX); d.oSyx = plane_off(L, DP_SYX);
+    }
+    return 0;
+}
+
+static int check_lk(const slamklt_lk_params* p, int nlA, int nlB) {
+    if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
+    if (p->window_size < 1 || p->window_size > 15) return fail(SLAMKLT_E_INVALID, "window_size %d outside [1,15]", p->window_size);
+    if (p->iterations < 0) return fail(SLAMKLT_E_INVALID, "iterations < 0");
+    if (p->pyramid_levels < 0) return fail(SLAMKLT_E_INVALID, "pyramid_levels < 0");
+    if (!(nlA > p->pyramid_levels && nlB > p->pyramid_levels)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");
+    return 0;
+}
+
+static int run_lk_single(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B, const double* pts, const double* disp_in, int n,
+                         const slamklt_lk_params* p, int mode) {
+    if (A->g.H0 != B->g.H0 || A->g.W0 != B->g.W0) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
+    if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    int r;
+    if ((r = c->pts.ensure((size_t)n * 16))) return r;
+    if ((r = c->disp.ensure((size_t)n * 16))) return r;
+    if ((r = c->outp.ensure((size_t)n * 16))) return r;
+    if ((r = c->status.ensure((size_t)n))) return r;
+    CK(cudaMemcpyAsync(c->pts.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += (uint64_t)n * 16;
+    if (disp_in) {
+        CK(cudaMemcpyAsync(c->disp.p, disp_in, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+        c->h2d += (uint64_t)n * 16;
+    }
+    LKArgs a{};
+    a.A = fs_of(A); a.B = fs_of(B); a.offA = 0; a.offB = 0;
+    fill_lk_levels(A->g, &a);
+    a.mode = mode;
+    a.pts = (const double*)c->pts.p;
+    a.disp_in = disp_in ? (const double*)c->disp.p : nullptr;
+    a.disp_out = (double*)c->disp.p;
+    a.out_pts = (double*)c->outp.p;
+    a.status = (uint8_t*)c->status.p;
+    a.n_per_frame = n; a.n_frames = 1;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters;
+    c->launches += launch_lk(c->stream, a);
+    CKL();
+    return 0;
+}
+
+int slamklt_optflow(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B, const double* pts, double* disp, int n,
+                    const slamklt_lk_params* p, uint8_t* status, int* n_good) {
+    if (!c || !A || !B) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    int r = check_lk(p, A->g.nl, B->g.nl);
+    if (r) return r;
+    if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
+    if (n == 0) { if (n_good) *n_good = 0; return 0; }
+    if (!pts || !disp || !status) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    r = run_lk_single(c, A, B, pts, disp, n, p, 0);
+    if (r) return r;
+    CK(cudaMemcpyAsync(disp, c->disp.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status, c->status.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += (uint64_t)n * 17;
+    int good = 0;
+    for (int i = 0; i < n; ++i) good += status[i] ? 1 : 0;
+    if (n_good) *n_good = good;
+    return 0;
+}
+
+int slamklt_fb_track(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B, const double* pts, const double* disp, int n,
+                     const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
+    if (!c || !A || !B) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    int r = check_lk(p, A->g.nl, B->g.nl);
+    if (r) return r;
+    if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
+    if (n == 0) return 0;  // isempty(keypoints) && return, tracker.jl:24
+    if (!pts || !out_pts || !status) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    r = run_lk_single(c, A, B, pts, disp, n, p, 1);
+    if (r) return r;
+    if ((r = c->h_out.ensure((size_t)n * 16))) return r;
+    CK(cudaMemcpyAsync(c->h_out.p, c->outp.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status, c->status.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += (uint64_t)n * 17;
+    const double* h = (const double*)c->h_out.p;
+    for (int i = 0; i < n; ++i)
+        if (status[i] & 2) { out_pts[2 * i] = h[2 * i]; out_pts[2 * i + 1] = h[2 * i + 1]; }  // tracker.jl:43 writes only where forward ok
+    return 0;
+}
+
+// ---- extractor -------------------------------------------------------------------------------
+static int fill_det(const slamklt_detect_params* p, int H, int W, int n_cur, DetArgs* a) {
+    if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
+    if (p->cell_size < 3 || p->cell_size > 64) return fail(SLAMKLT_E_INVALID, "cell_size %d outside [3,64]", p->cell_size);
+    if (p->grid_h < 1 || p->grid_w < 1) return fail(SLAMKLT_E_INVALID, "grid_resolution must be positive");
+    if (p->radius < 0) return fail(SLAMKLT_E_INVALID, "radius < 0");
+    std::memset(a, 0, sizeof(*a));
+    a->H = H; a->W = W; a->n_cur = n_cur;
+    a->radius = p->radius; a->grid_h = p->grid_h; a->grid_w = p->grid_w; a->cs = p->cell_size;
+    const int n_cells = p->grid_h * p->grid_w;
+    const long long n_detect = (long long)p->max_points - n_cur;
+    a->k_cell = (int)((n_detect + n_cells - 1) / n_cells);  // ceil(Int, n_detect / n_cells), extractor.jl:76
+    a->slots = a->k_cell < p->cell_size * p->cell_size ? a->k_cell : p->cell_size * p->cell_size;
+    if (a->slots < 1) a->slots = 1;
+    a->min_resp = p->min_response;
+    int hw = 0;
+    if (n_cur > 0 && p->sigma_mask > 0 && !(std::fabs(p->sigma_mask) < 1e-12)) {
+        hw = 2 * (int)std::ceil(p->sigma_mask);  // Kernel.gaussian(sigma): length 4*ceil(sigma)+1 [3P]
+        if (hw > 16) return fail(SLAMKLT_E_INVALID, "sigma_mask %g too large (max 8)", p->sigma_mask);
+        double s = 0;
+        for (int i = -hw; i <= hw; ++i) { a->kw[i + hw] = std::exp(-(double)i * i / (2 * p->sigma_mask * p->sigma_mask)); s += a->kw[i + hw]; }
+        for (int i = 0; i <= 2 * hw; ++i) a->kw[i] /= s;
+    }
+    a->hw = hw;
+    if (detect_smem_bytes(a->cs, a->hw) > 220 * 1024) return fail(SLAMKLT_E_INVALID, "cell_size/sigma_mask need too much shared memory");
+    return 0;
+}
+
+static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_frames, const double* cur_host, int cap, int64_t* out_yx, int* n_out) {
+    const int n_cells = a.grid_h * a.grid_w;
+    int r;
+    a.img = d_img; a.n_frames = n_frames; a.cap = cap;
+    if ((r = c->cell_out.ensure((size_t)n_frames * n_cells * a.slots * 16))) return r;
+    if ((r = c->cell_cnt.ensure((size_t)n_frames * n_cells * 4))) return r;
+    if ((r = c->det_out.ensure((size_t)n_frames * cap * 16 + 16))) return r;
+    if ((r = c->det_n.ensure((size_t)n_frames * 4))) return r;
+    if (a.n_cur > 0) {
+        if ((r = c->cur.ensure((size_t)n_frames * a.n_cur * 16))) return r;
+        CK(cudaMemcpyAsync(c->cur.p, cur_host, (size_t)n_frames * a.n_cur * 16, cudaMemcpyHostToDevice, c->stream));
+        c->h2d += (uint64_t)n_frames * a.n_cur * 16;
+        a.cur = (const double*)c->cur.p;
+    }
+    a.cell_out = (int64_t*)c->cell_out.p; a.cell_cnt = (int*)c->cell_cnt.p;
+    a.out = (int64_t*)c->det_out.p; a.n_out = (int*)c->det_n.p;
+    c->launches += launch_detect(c->stream, a);
+    CKL();
+    CK(cudaMemcpyAsync(n_out, c->det_n.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < n_frames; ++f) {
+        const int n = n_out[f] < cap ? n_out[f] : cap;
+        if (n > 0) CK(cudaMemcpyAsync(out_yx + (size_t)f * cap * 2, (char*)c->det_out.p + (size_t)f * cap * 16, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+        c->d2h += (uint64_t)n * 16 + 4;
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slamklt_detect(slamklt_ctx* c, const void* img, int dtype, int H, int W, int ld, const double* cur, int n_cur,
+                   const slamklt_detect_params* p, int64_t* out_yx, int cap, int* n_out) {
+    if (!c || !img || !n_out || (!out_yx && cap > 0)) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (H < 3 || W < 3 || ld < H || n_cur < 0 || cap < 0) return fail(SLAMKLT_E_INVALID, "bad shape");
+    if (n_cur > 0 && !cur) return fail(SLAMKLT_E_INVALID, "cur_pts is NULL");
+    if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
+    *n_out = 0;
+    if (n_cur >= p->max_points) return 0;  // extractor.jl:64
+    DetArgs a;
+    int r = fill_det(p, H, W, n_cur, &a);
+    if (r) return r;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if ((r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
+    const double* d_img;
+    if (dtype == SLAMKLT_F64) d_img = (const double*)c->staging.p;
+    else {
+        if ((r = c->img64.ensure((size_t)H * W * 8))) return r;
+        // reuse the convert kernel through a throw-away geometry: only the f64 copy is consumed
+        PyrGeom g;
+        if ((r = make_geom(H, W, 0, &g))) return r;
+        DevBuf& scratch = c->outp;  // any buffer large enough for one level-0 frame
+        if ((r = scratch.ensure(g.frame_elems * sizeof(float)))) return r;
+        FrameSet fs{(float*)scratch.p, g.frame_elems, 1, 0};
+        c->launches += launch_convert(c->stream, c->staging.p, dtype, H, (size_t)H * W, fs, 0, 1, g, (double*)c->img64.p);
+        CKL();
+        d_img = (const double*)c->img64.p;
+    }
+    r = run_detect(c, a, d_img, 1, cur, cap, out_yx, n_out);
+    if (r) return r;
+    if (*n_out > cap) return fail(SLAMKLT_E_CAPACITY, "detected %d keypoints but cap is %d", *n_out, cap);
+    return 0;
+}
+
+// ---- batch -----------------------------------------------------------------------------------
+int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames, int max_pts, slamklt_batch** out) {
+    if (!c || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (n_frames < 1 || max_pts < 0) return fail(SLAMKLT_E_INVALID, "bad batch shape");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    PyrGeom g;
+    int r = make_geom(H, W, levels, &g);
+    if (r) return r;
+    slamklt_batch* b = new slamklt_batch();
+    b->g = g; b->n_frames = n_frames; b->n_slots = n_frames + 1; b->slot0 = 0; b->max_pts = max_pts;
+    cudaError_t e = cudaMalloc(&b->base, g.frame_elems * sizeof(float) * b->n_slots);
+    if (e != cudaSuccess) { delete b; return fail(SLAMKLT_E_CUDA, "cudaMalloc batch (%zu bytes) failed: %s", g.frame_elems * sizeof(float) * b->n_slots, cudaGetErrorString(e)); }
+    cudaMemsetAsync(b->base, 0, g.frame_elems * sizeof(float) * b->n_slots, c->stream);
+    if ((r = b->pts.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
+    if ((r = b->outp.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
+    if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;
+    b->views.resize(b->n_slots, nullptr);
+    *out = b;
+    return 0;
+}
+
+int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
+    if (!b) return 0;
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto* v : b->views) delete v;
+    b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release();
+    cudaFree(b->base);
+    delete b;
+    return 0;
+}
+
+int slamklt_batch_prime(slamklt_ctx* c, slamklt_batch* b, const void* img, int dtype, int ld, double sigma, int mode) {
+    if (!c || !b || !img) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (ld < b->g.H0) return fail(SLAMKLT_E_INVALID, "ld < H");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, b->g.H0, b->g.W0);
+    if (r) return r;
+    r = build_frames(c, fs_of(b), 0, 1, b->g, c->staging.p, dtype, sigma, mode, nullptr);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    b->primed = true;
+    return 0;
+}
+
+int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
+                         const double* pts, int n_pts) {
+    if (!c || !b || !imgs) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (ld < b->g.H0) return fail(SLAMKLT_E_INVALID, "ld < H");
+    if (n_pts < 0 || n_pts > b->max_pts) return fail(SLAMKLT_E_INVALID, "n_pts %d outside [0,%d]", n_pts, b->max_pts);
+    if (n_pts > 0 && !pts) return fail(SLAMKLT_E_INVALID, "pts is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int r = upload_frames(c, b->staging, imgs, dtype, ld, frame_stride_bytes, b->n_frames, b->g.H0, b->g.W0);
+    if (r) return r;
+    if (n_pts > 0) {
+        CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)b->n_frames * n_pts * 16, cudaMemcpyHostToDevice, c->stream));
+        c->h2d += (uint64_t)b->n_frames * n_pts * 16;
+    }
+    b->n_pts = n_pts; b->up_dtype = dtype; b->up_ld = ld;
+    return 0;
+}
+
+int slamklt_batch_build(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return build_frames(c, fs_of(b), 1, b->n_frames, b->g, b->staging.p, b->up_dtype, sigma, mode, nullptr);
+}
+
+int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_params* p) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    int r = check_lk(p, b->g.nl, b->g.nl);
+    if (r) return r;
+    if (!b->primed) return fail(SLAMKLT_E_INVALID, "batch slot 0 was never built (call slamklt_batch_prime)");
+    if (b->n_pts == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    LKArgs a{};
+    a.A = fs_of(b); a.B = fs_of(b); a.offA = 0; a.offB = 1;
+    fill_lk_levels(b->g, &a);
+    a.mode = 1;
+    a.pts = (const double*)b->pts.p; a.disp_in = nullptr; a.disp_out = nullptr;
+    a.out_pts = (double*)b->outp.p; a.status = (uint8_t*)b->status.p;
+    a.n_per_frame = b->n_pts; a.n_frames = b->n_frames;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters;
+    c->launches += launch_lk(c->stream, a);
+    CKL();
+    return 0;
+}
+
+int slamklt_batch_download(slamklt_ctx* c, slamklt_batch* b, double* out_pts, uint8_t* status) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)b->n_frames * b->n_pts;
+    if (n > 0) {
+        if (out_pts) CK(cudaMemcpyAsync(out_pts, b->outp.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (status) CK(cudaMemcpyAsync(status, b->status.p, n, cudaMemcpyDeviceToHost, c->stream));
+        c->d2h += (out_pts ? n * 16 : 0) + (status ? n : 0);
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slamklt_batch_rotate(slamklt_ctx* c, slamklt_batch* b) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    b->slot0 = (b->slot0 + b->n_frames) % b->n_slots;  // last frame of this batch becomes slot 0
+    return 0;
+}
+
+int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
+                       const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
+    int r;
+    if ((r = slamklt_batch_upload(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts))) return r;
+    if ((r = slamklt_batch_build(c, b, sigma, mode))) return r;
+    if ((r = slamklt_batch_track(c, b, p))) return r;
+    if ((r = slamklt_batch_download(c, b, out_pts, status))) return r;
+    return slamklt_batch_rotate(c, b);
+}
+
+int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out) {
+    if (!b || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (slot < 0 || slot >= b->n_slots) return fail(SLAMKLT_E_INVALID, "slot %d out of range", slot);
+    slamklt_pyr*& v = b->views[slot];
+    if (!v) { v = new slamklt_pyr(); v->g = b->g; v->parent = b; v->logical_slot = slot; v->owns = false; }
+    v->built = true;
+    *out = v;
+    return 0;
+}
+
+int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, int n_cur, const slamklt_detect_params* p,
+                         int64_t* out_yx, int cap, int* n_out) {
+    if (!c || !b || !n_out || (!out_yx && cap > 0)) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (n_cur < 0 || cap < 0) return fail(SLAMKLT_E_INVALID, "bad shape");
+    if (n_cur > 0 && !cur) return fail(SLAMKLT_E_INVALID, "cur_pts is NULL");
+    if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
+    for (int f = 0; f < b->n_frames; ++f) n_out[f] = 0;
+    if (n_cur >= p->max_points) return 0;
+    DetArgs a;
+    int r = fill_det(p, b->g.H0, b->g.W0, n_cur, &a);
+    if (r) return r;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const double* d_img;
+    if (b->up_dtype == SLAMKLT_F64) d_img = (const double*)b->staging.p;
+    else {
+        if ((r = b->img64.ensure((size_t)b->n_frames * b->g.H0 * b->g.W0 * 8))) return r;
+        c->launches += launch_convert(c->stream, b->staging.p, b->up_dtype, b->g.H0, (size_t)b->g.H0 * b->g.W0, fs_of(b), 1, b->n_frames, b->g, (double*)b->img64.p);
+        CKL();
+        d_img = (const double*)b->img64.p;
+    }
+    r = run_detect(c, a, d_img, b->n_frames, cur, cap, out_yx, n_out);
+    if (r) return r;
+    for (int f = 0; f < b->n_frames; ++f)
+        if (n_out[f] > cap) return fail(SLAMKLT_E_CAPACITY, "frame %d: detected %d keypoints but cap is %d", f, n_out[f], cap);
+    return 0;
+}
+
+int slamklt_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(SLAMKLT_E_INVALID, "out is NULL");
+    CK(cudaMallocHost(out, bytes));
+    return 0;
+}
+
+int slamklt_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+}  // extern "C"
+

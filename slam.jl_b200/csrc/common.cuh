@@ -1,0 +1,112 @@
+// Internal declarations shared by the translation units of libslamklt.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/slamklt.h"
+
+namespace sk {
+
+constexpr int MAX_LAYERS = 8;   // pyramid_levels + 1 <= 8
+constexpr unsigned FULL = 0xffffffffu;
+
+// device planes kept per level (fp32, y contiguous, pitch = roundup4(H))
+enum DevPlane {
+    DP_I = 0, DP_IY, DP_IX, DP_SYY, DP_SXX, DP_SYX,  // the pyramid proper (LKPyramid fields)
+    DP_T0, DP_T1, DP_T2,                              // scratch: planes after the dim-1 recursive pass
+    DP_BLUR,                                          // LKCache.gaussian_filtered
+    DP_COUNT
+};
+
+struct LevelGeom {
+    int H, W, pitch;
+    int pad_;
+    size_t plane_elems;  // floats per plane (multiple of 32)
+    size_t off;          // float offset of this level's block inside a frame
+};
+
+struct PyrGeom {
+    int nl;  // layers = levels + 1
+    int H0, W0;
+    int pad_;
+    LevelGeom lv[MAX_LAYERS];
+    size_t frame_elems;  // floats per frame (all levels, all planes)
+};
+
+// A set of frames laid out with a constant stride; logical frame f lives in physical slot (slot0 + f) % n_slots.
+struct FrameSet {
+    float* base;
+    size_t frame_elems;
+    int n_slots;
+    int slot0;
+    __host__ __device__ float* frame(int f) const {
+        int s = slot0 + f;
+        s = s % n_slots;
+        return base + (size_t)s * frame_elems;
+    }
+};
+
+__host__ __device__ inline size_t plane_off(const LevelGeom& g, int plane) { return g.off + (size_t)plane * g.plane_elems; }
+
+// recursive Gaussian constants (host computes in double, device uses float)
+struct IirDev {
+    float a1, a2, a3, scale, inv1ma;  // inv1ma = 1/(1 - (a1+a2+a3))
+    float M[9];                       // Triggs-Sdika right-boundary matrix, row-major
+    float P[5][9];                    // A^(K*2^j), j = 0..4, for the warp scan of the dim-1 kernel
+    float PK[9];                      // A^KR for the chunk carries of the dim-2 kernel
+};
+
+struct LKLevel {
+    int H, W, pitch, pad_;
+    size_t oI, oIy, oIx, oSyy, oSxx, oSyx;
+};
+
+struct LKArgs {
+    FrameSet A, B;
+    int offA, offB;
+    int nl, mode;  // mode 0 = optflow!, 1 = fb_tracking!
+    LKLevel lv[MAX_LAYERS];
+    const double* pts;
+    const double* disp_in;  // nullable
+    double* disp_out;       // nullable
+    double* out_pts;        // nullable (mode 1)
+    uint8_t* status;
+    int n_per_frame, n_frames;
+    int iterations, window, levels, pad_;
+    double eig_thr, eps, max_dist;
+    unsigned long long* counters;  // [0] window px * iterations, [1] iterations
+};
+
+struct DetArgs {
+    const double* img;  // n_frames images, column-major H x W, frame stride H*W
+    int H, W;
+    const double* cur;  // n_frames x n_cur x 2, nullable
+    int n_cur, n_frames;
+    int radius, grid_h, grid_w, cs, k_cell, hw, slots, pad_;
+    double min_resp;
+    double kw[33];      // 1-D mask blur weights, length 2*hw+1
+    int64_t* cell_out;  // [frame][cell][slots][2]
+    int* cell_cnt;      // [frame][cell]
+    int64_t* out;       // [frame][cap][2]
+    int* n_out;         // [frame]
+    int cap;
+};
+
+// launchers (each returns the number of kernels it launched; errors are picked up by cudaGetLastError in api.cu)
+int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t src_frame_stride_elems, FrameSet dst, int dst_f0,
+                   int n_frames, const PyrGeom& g, double* dst64 /*nullable: also keep f64 copy, frame stride H*W*/);
+int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
+                   const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */);
+int launch_lk(cudaStream_t s, const LKArgs& a);
+int launch_detect(cudaStream_t s, const DetArgs& a);
+size_t detect_smem_bytes(int cs, int hw);
+
+void iir_design(double sigma, double a[3], double* scale, double M[9]);
+void iir_dev(double sigma, int K, int KR, IirDev* out);
+void iir_line_host(double* x, int n, double sigma, double iminus, double iplus);
+
+int pick_K(int H);  // per-lane chunk of the dim-1 kernel; 0 if unsupported
+constexpr int KR = 40;  // per-thread chunk of the dim-2 kernel
+
+}  // namespace sk

@@ -1,0 +1,481 @@
+// Pyramid construction kernels (sm_100a): input conversion, Young-van Vliet recursive Gaussian with
+// Triggs-Sdika boundaries along both dimensions, Scharr gradients + gradient products, bilinear decimation.
+//
+// Reference behaviour: pyramid.jl:40-137 (LKPyramid ctor, update!, gaussian_pyramid!, imgradients_yx!),
+// lucas_kanade.jl:102-129 (compute_partial_derivatives!).  The integral images of lucas_kanade.jl:131-138 are
+// NOT materialised: the LK kernel sums the 19x19 window of the smoothed planes directly.
+//
+// Layout: every plane is fp32, y contiguous (Julia column-major), pitch = roundup4(H) floats.
+//
+// The recursion u[i] = x[i] + a1 u[i-1] + a2 u[i-2] + a3 u[i-3] is sequential along a line.  Both kernels
+// cut each line into chunks, run every chunk from a zero state to obtain its outgoing state, combine the
+// chunk states with powers of the companion matrix A (exact by linearity), and re-run every chunk from its
+// true incoming state.  Along y (contiguous, short lines) one warp owns a whole column in registers and the
+// carries travel through a Kogge-Stone scan on shuffles; along x (strided, long lines) a CTA owns a strip of
+// rows, chunks are spread over warps and the carries travel through shared memory.
+#include "common.cuh"
+
+namespace sk {
+
+// ----------------------------------------------------------------------------------------------
+// input conversion: host layout (dtype, ld) -> level-0 layer (fp32, pitch) [+ optional f64 copy for detect]
+// ----------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ double to_unit(T v);
+template <> __device__ __forceinline__ double to_unit<double>(double v) { return v; }
+template <> __device__ __forceinline__ double to_unit<float>(float v) { return (double)v; }
+template <> __device__ __forceinline__ double to_unit<uint8_t>(uint8_t v) { return (double)v / 255.0; }
+
+template <typename T>
+__global__ void k_convert(const T* __restrict__ src, int ld, size_t src_stride, FrameSet dst, int dst_f0, size_t off_I, int H, int W,
+                          int pitch, double* __restrict__ dst64) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.y;
+    const T* s = src + (size_t)f * src_stride + (size_t)x * ld;
+    float* d = dst.frame(dst_f0 + f) + off_I + (size_t)x * pitch;
+    double* d64 = dst64 ? dst64 + ((size_t)f * W + x) * H : nullptr;
+    for (int y = blockIdx.x * blockDim.x + threadIdx.x; y < H; y += gridDim.x * blockDim.x) {
+        double v = to_unit<T>(s[y]);
+        d[y] = (float)v;
+        if (d64) d64[y] = v;
+    }
+}
+
+int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t src_stride, FrameSet dst, int dst_f0, int n_frames,
+                   const PyrGeom& g, double* dst64) {
+    const LevelGeom& l0 = g.lv[0];
+    dim3 grid((l0.H + 127) / 128, l0.W, n_frames), block(128);
+    size_t off = plane_off(l0, DP_I);
+    if (dtype == SLAMKLT_F64)
+        k_convert<double><<<grid, block, 0, s>>>((const double*)src, ld, src_stride, dst, dst_f0, off, l0.H, l0.W, l0.pitch, dst64);
+    else if (dtype == SLAMKLT_F32)
+        k_convert<float><<<grid, block, 0, s>>>((const float*)src, ld, src_stride, dst, dst_f0, off, l0.H, l0.W, l0.pitch, dst64);
+    else
+        k_convert<uint8_t><<<grid, block, 0, s>>>((const uint8_t*)src, ld, src_stride, dst, dst_f0, off, l0.H, l0.W, l0.pitch, dst64);
+    return 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// warp-wide recursive filter of one line held in registers: lane l owns elements [l*K, l*K+K)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, float r1, float r2, float& q0, float& q1, float& q2) {
+    q0 = fmaf(P[0], r0, fmaf(P[1], r1, fmaf(P[2], r2, q0)));
+    q1 = fmaf(P[3], r0, fmaf(P[4], r1, fmaf(P[5], r2, q1)));
+    q2 = fmaf(P[6], r0, fmaf(P[7], r1, fmaf(P[8], r2, q2)));
+}
+
+template <int K>
+__device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const int lane, const IirDev& c, const bool zero_border) {
+    const int y0 = lane * K;
+    const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
+    const int ln = (n - 1) / K, jn = (n - 1) - ln * K;
+    float first = __shfl_sync(FULL, x[0], 0);
+    float lastv = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (j == jn) lastv = x[j];
+    lastv = __shfl_sync(FULL, lastv, ln);
+    const float iminus = zero_border ? 0.f : first, iplus = zero_border ? 0.f : lastv;
+    const float um = iminus * c.inv1ma;
+
+    // forward, phase 1: chunk-local pass (lane 0 starts from the true left boundary state)
+    float s0 = lane == 0 ? um : 0.f, s1 = s0, s2 = s0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (y0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+    // phase 2: inclusive scan of the chunk states, q_l += A^(K d) q_{l-d}
+    float q0 = s0, q1 = s1, q2 = s2;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int d = 1 << j;
+        float r0 = __shfl_up_sync(FULL, q0, d), r1 = __shfl_up_sync(FULL, q1, d), r2 = __shfl_up_sync(FULL, q2, d);
+        if (lane >= d) mat3_acc(c.P[j], r0, r1, r2, q0, q1, q2);
+    }
+    s0 = __shfl_up_sync(FULL, q0, 1); s1 = __shfl_up_sync(FULL, q1, 1); s2 = __shfl_up_sync(FULL, q2, 1);
+    if (lane == 0) { s0 = um; s1 = um; s2 = um; }
+    // phase 3: true pass
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (y0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            x[j] = u;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+    // right boundary (Triggs & Sdika eq. 14): lane ln holds (u[n], u[n-1], u[n-2])
+    const float e0 = __shfl_sync(FULL, s0, ln), e1 = __shfl_sync(FULL, s1, ln), e2 = __shfl_sync(FULL, s2, ln);
+    const float up = iplus * c.inv1ma, vp = up * c.inv1ma;
+    const float d0 = e0 - up, d1 = e1 - up, d2 = e2 - up;
+    const float vr0 = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
+    const float vr1 = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
+    const float vr2 = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
+
+    // backward, phase 1
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {
+        const int idx = y0 + j;
+        if (idx < n) {
+            if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
+            else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+        }
+    }
+    q0 = t0; q1 = t1; q2 = t2;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int d = 1 << j;
+        float r0 = __shfl_down_sync(FULL, q0, d), r1 = __shfl_down_sync(FULL, q1, d), r2 = __shfl_down_sync(FULL, q2, d);
+        if (lane + d < 32) mat3_acc(c.P[j], r0, r1, r2, q0, q1, q2);
+    }
+    t0 = __shfl_down_sync(FULL, q0, 1); t1 = __shfl_down_sync(FULL, q1, 1); t2 = __shfl_down_sync(FULL, q2, 1);
+    if (lane == 31) { t0 = 0.f; t1 = 0.f; t2 = 0.f; }
+    const float sc = c.scale;
+#pragma unroll
+    for (int j = K - 1; j >= 0; --j) {
+        const int idx = y0 + j;
+        if (idx < n) {
+            float v;
+            if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
+            else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+            x[j] = v * sc;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// dim-1 kernels (along y).  One warp per (frame, column).
+// ----------------------------------------------------------------------------------------------
+struct ColArgs {
+    FrameSet fs;
+    int f0, n_frames;
+    int H, W, pitch;
+    int zero_border;       // blur: NA mode; grad: Fill(0) Scharr border
+    size_t o_in;           // layer
+    size_t o_out0;         // blur: T0;   grad: T0,T1,T2 consecutive
+    size_t o_iy, o_ix;     // grad only
+    size_t plane_elems;
+    const float* inv_n;    // blur NA mode: 1/ny[y]
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = a.n_frames * a.W;
+    const int y0 = lane * K;
+    for (int w = warp; w < total; w += nwarps) {
+        const int f = w / a.W, xcol = w - f * a.W;
+        float* fb = a.fs.frame(a.f0 + f);
+        const float* in = fb + a.o_in + (size_t)xcol * a.pitch;
+        float* out = fb + a.o_out0 + (size_t)xcol * a.pitch;
+        float x[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? in[y0 + j] : 0.f;
+        warp_iir_line<K>(x, a.H, lane, c, a.zero_border != 0);
+        if (a.inv_n) {
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (y0 + j < a.H) x[j] *= a.inv_n[y0 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (y0 + j < a.H) out[y0 + j] = x[j];
+    }
+}
+
+// Scharr gradients (pyramid.jl:59,75,98-103), gradient products and the y pass of their sigma=4 smoothing
+// (lucas_kanade.jl:116-126).  Writes Iy, Ix and the three y-filtered product planes T0 (yy), T1 (xx), T2 (yx).
+template <int K>
+__global__ void __launch_bounds__(256) k_cols_grad(ColArgs a, IirDev c) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = a.n_frames * a.W;
+    const int y0 = lane * K;
+    const int H = a.H, W = a.W;
+    const bool zb = a.zero_border != 0;
+    for (int w = warp; w < total; w += nwarps) {
+        const int f = w / W, xcol = w - f * W;
+        float* fb = a.fs.frame(a.f0 + f);
+        const float* I = fb + a.o_in;
+        // three columns x-1, x, x+1, rows y0-1 .. y0+K
+        float cm[K + 2], cc[K + 2], cp[K + 2];
+        const int xm = xcol - 1, xp = xcol + 1;
+        const bool okm = xm >= 0, okp = xp < W;
+        const float* colm = I + (size_t)(okm ? xm : 0) * a.pitch;
+        const float* colc = I + (size_t)xcol * a.pitch;
+        const float* colp = I + (size_t)(okp ? xp : W - 1) * a.pitch;
+#pragma unroll
+        for (int j = 0; j < K + 2; ++j) {
+            int y = y0 - 1 + j;
+            bool oky = (y >= 0) && (y < H);
+            int yc = y < 0 ? 0 : (y >= H ? H - 1 : y);
+            float vm = colm[yc], vc = colc[yc], vp = colp[yc];
+            if (zb) {
+                if (!oky) { vm = 0.f; vc = 0.f; vp = 0.f; }
+                if (!okm) vm = 0.f;
+                if (!okp) vp = 0.f;
+            }
+            cm[j] = vm; cc[j] = vc; cp[j] = vp;
+        }
+        float pyy[K], pxx[K], pyx[K];
+        float* oIy = fb + a.o_iy + (size_t)xcol * a.pitch;
+        float* oIx = fb + a.o_ix + (size_t)xcol * a.pitch;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            // centre row index in the local arrays is j+1
+            const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
+            float gy = s0 * (0.5f * (cm[j + 2] - cm[j])) + s1 * (0.5f * (cc[j + 2] - cc[j])) + s0 * (0.5f * (cp[j + 2] - cp[j]));
+            float gx = s0 * (0.5f * (cp[j] - cm[j])) + s1 * (0.5f * (cp[j + 1] - cm[j + 1])) + s0 * (0.5f * (cp[j + 2] - cm[j + 2]));
+            if (y0 + j < H) { oIy[y0 + j] = gy; oIx[y0 + j] = gx; }
+            pyy[j] = gy * gy; pxx[j] = gx * gx; pyx[j] = gy * gx;
+        }
+        warp_iir_line<K>(pyy, H, lane, c, false);
+        warp_iir_line<K>(pxx, H, lane, c, false);
+        warp_iir_line<K>(pyx, H, lane, c, false);
+        float* o0 = fb + a.o_out0 + (size_t)xcol * a.pitch;
+        float* o1 = o0 + a.plane_elems;
+        float* o2 = o1 + a.plane_elems;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (y0 + j < H) { o0[y0 + j] = pyy[j]; o1[y0 + j] = pxx[j]; o2[y0 + j] = pyx[j]; }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// dim-2 kernel (along x).  CTA = LR rows x NC chunks of KRt elements; thread (row, chunk) keeps its chunk in registers.
+// ----------------------------------------------------------------------------------------------
+struct RowArgs {
+    FrameSet fs;
+    int f0, n_frames;
+    int H, W, pitch, nplanes;
+    int zero_border;
+    size_t o_in0, o_out0, plane_elems;  // nplanes consecutive input planes -> nplanes consecutive output planes
+    const float* inv_n;                 // NA mode: 1/nx[x]
+};
+
+template <int KRt, int LR>
+__global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
+    constexpr int NCMAX = 32;
+    __shared__ float sF[NCMAX][3][LR];
+    __shared__ float sB[NCMAX][3][LR];
+    const int rl = threadIdx.x % LR;
+    const int ch = threadIdx.x / LR;
+    const int NC = (a.W + KRt - 1) / KRt;
+    const int r = blockIdx.x * LR + rl;
+    const int plane = blockIdx.y;
+    const int f = blockIdx.z;
+    const bool rowok = r < a.H;
+    const bool act = rowok && ch < NC;
+    float* fb = a.fs.frame(a.f0 + f);
+    const float* in = fb + a.o_in0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
+    float* out = fb + a.o_out0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
+    const int x0 = ch * KRt;
+    const int n = a.W;
+    const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
+
+    float x[KRt];
+#pragma unroll
+    for (int j = 0; j < KRt; ++j) x[j] = (act && x0 + j < n) ? __ldg(in + (size_t)(x0 + j) * a.pitch) : 0.f;
+    const bool zb = a.zero_border != 0;
+    const float iminus = (zb || !rowok) ? 0.f : __ldg(in);
+    const float iplus = (zb || !rowok) ? 0.f : __ldg(in + (size_t)(n - 1) * a.pitch);
+    const float um = iminus * c.inv1ma;
+
+    // forward phase 1
+    float s0 = ch == 0 ? um : 0.f, s1 = s0, s2 = s0;
+#pragma unroll
+    for (int j = 0; j < KRt; ++j)
+        if (x0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+    if (ch < NC) { sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2; }
+    __syncthreads();
+    if (ch == 0) {  // sequential carries over the chunks of this row
+        float q0 = sF[0][0][rl], q1 = sF[0][1][rl], q2 = sF[0][2][rl];
+        for (int k = 1; k < NC; ++k) {
+            float l0 = sF[k][0][rl], l1 = sF[k][1][rl], l2 = sF[k][2][rl];
+            sF[k][0][rl] = q0; sF[k][1][rl] = q1; sF[k][2][rl] = q2;  // incoming state of chunk k
+            mat3_acc(c.PK, q0, q1, q2, l0, l1, l2);
+            q0 = l0; q1 = l1; q2 = l2;
+        }
+    }
+    __syncthreads();
+    if (ch == 0) { s0 = um; s1 = um; s2 = um; }
+    else if (ch < NC) { s0 = sF[ch][0][rl]; s1 = sF[ch][1][rl]; s2 = sF[ch][2][rl]; }
+#pragma unroll
+    for (int j = 0; j < KRt; ++j)
+        if (x0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            x[j] = u;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+    // right boundary: only the last chunk holds (u[n], u[n-1], u[n-2])
+    const float up = iplus * c.inv1ma, vp = up * c.inv1ma;
+    const float d0 = s0 - up, d1 = s1 - up, d2 = s2 - up;
+    const float vr0 = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
+    const float vr1 = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
+    const float vr2 = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
+
+    // backward phase 1
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        const int idx = x0 + j;
+        if (idx < n) {
+            if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
+            else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+        }
+    }
+    if (ch < NC) { sB[ch][0][rl] = t0; sB[ch][1][rl] = t1; sB[ch][2][rl] = t2; }
+    __syncthreads();
+    if (ch == 0) {
+        float q0 = sB[NC - 1][0][rl], q1 = sB[NC - 1][1][rl], q2 = sB[NC - 1][2][rl];
+        for (int k = NC - 2; k >= 0; --k) {
+            float l0 = sB[k][0][rl], l1 = sB[k][1][rl], l2 = sB[k][2][rl];
+            sB[k][0][rl] = q0; sB[k][1][rl] = q1; sB[k][2][rl] = q2;
+            mat3_acc(c.PK, q0, q1, q2, l0, l1, l2);
+            q0 = l0; q1 = l1; q2 = l2;
+        }
+    }
+    __syncthreads();
+    if (ch < NC - 1) { t0 = sB[ch][0][rl]; t1 = sB[ch][1][rl]; t2 = sB[ch][2][rl]; }
+    else { t0 = 0.f; t1 = 0.f; t2 = 0.f; }
+    const float sc = c.scale;
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        const int idx = x0 + j;
+        if (idx < n) {
+            float v;
+            if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
+            else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+            float o = v * sc;
+            if (a.inv_n) o *= __ldg(a.inv_n + idx);
+            if (act) out[(size_t)idx * a.pitch] = o;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// bilinear decimation to ceil(size/2)  (pyramid.jl:120-121,132-133; [3P] imresize!)
+// ----------------------------------------------------------------------------------------------
+__global__ void k_resize(FrameSet fs, int f0, size_t o_in, int Hi, int Wi, int pin, size_t o_out, int Ho, int Wo, int pout) {
+    const int f = blockIdx.z;
+    const int j = blockIdx.y;  // output column (0-based)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ho) return;
+    float* fb = fs.frame(f0 + f);
+    const float* in = fb + o_in;
+    float* out = fb + o_out;
+    // 1-based source coordinate sf*(i1 - 0.5) + 0.5 with i1 = i+1; computed in double like the reference
+    const double sy = (double)Hi / (double)Ho, sx = (double)Wi / (double)Wo;
+    const double ry = sy * ((double)i + 0.5) + 0.5, rx = sx * ((double)j + 0.5) + 0.5;
+    int iy = (int)floor(ry), ix = (int)floor(rx);
+    iy = min(max(iy, 1), Hi - 1);
+    ix = min(max(ix, 1), Wi - 1);
+    const float wy = (float)(ry - iy), wx = (float)(rx - ix);
+    const float* p = in + (iy - 1) + (size_t)(ix - 1) * pin;
+    const float c0 = (1.f - wy) * p[0] + wy * p[1];
+    const float c1 = (1.f - wy) * p[pin] + wy * p[pin + 1];
+    out[i + (size_t)j * pout] = (1.f - wx) * c0 + wx * c1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+int pick_K(int H) {
+    const int need = (H + 31) / 32;
+    const int ks[] = {2, 4, 6, 8, 12, 16, 24, 34};
+    for (int k : ks)
+        if (k >= need) return k;
+    return 0;
+}
+
+template <int K>
+static void launch_cols(cudaStream_t s, bool grad, const ColArgs& a, const IirDev& c) {
+    const int total_warps = a.n_frames * a.W;
+    const int wpb = 8;
+    int blocks = (total_warps + wpb - 1) / wpb;
+    const int maxb = 148 * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (grad) k_cols_grad<K><<<blocks, wpb * 32, 0, s>>>(a, c);
+    else      k_cols_blur<K><<<blocks, wpb * 32, 0, s>>>(a, c);
+}
+
+static void dispatch_cols(cudaStream_t s, int K, bool grad, const ColArgs& a, const IirDev& c) {
+    switch (K) {
+        case 2: launch_cols<2>(s, grad, a, c); break;
+        case 4: launch_cols<4>(s, grad, a, c); break;
+        case 6: launch_cols<6>(s, grad, a, c); break;
+        case 8: launch_cols<8>(s, grad, a, c); break;
+        case 12: launch_cols<12>(s, grad, a, c); break;
+        case 16: launch_cols<16>(s, grad, a, c); break;
+        case 24: launch_cols<24>(s, grad, a, c); break;
+        case 34: launch_cols<34>(s, grad, a, c); break;
+    }
+}
+
+static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c) {
+    if (a.W <= 32 * 40) {
+        dim3 grid((a.H + 31) / 32, a.nplanes, a.n_frames);
+        const int NC = (a.W + 39) / 40;
+        k_rows<40, 32><<<grid, 32 * NC, 0, s>>>(a, c);
+    } else {
+        dim3 grid((a.H + 15) / 16, a.nplanes, a.n_frames);
+        const int NC = (a.W + 63) / 64;
+        k_rows<64, 16><<<grid, 16 * NC, 0, s>>>(a, c);
+    }
+}
+
+int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
+                   const float* const* inv_ny, const float* const* inv_nx) {
+    int launches = 0;
+    const bool ctor = mode == SLAMKLT_MODE_CTOR;
+    // 1. Gaussian pyramid (sigma chain): layer l -> blur l -> layer l+1
+    for (int l = 0; l + 1 < g.nl; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const LevelGeom& N = g.lv[l + 1];
+        const int K = pick_K(L.H);
+        const int krow = (L.W <= 32 * 40) ? 40 : 64;
+        IirDev c;
+        iir_dev(sigma, K, krow, &c);
+        ColArgs ca{};
+        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
+        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
+        ca.plane_elems = L.plane_elems; ca.inv_n = ctor ? inv_ny[l] : nullptr;
+        dispatch_cols(s, K, false, ca, c);
+        RowArgs ra{};
+        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
+        ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
+        ra.inv_n = ctor ? inv_nx[l] : nullptr;
+        dispatch_rows(s, ra, c);
+        dim3 grid((N.H + 127) / 128, N.W, n_frames);
+        k_resize<<<grid, 128, 0, s>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
+        launches += 3;
+    }
+    // 2. gradients + smoothed structure-tensor planes, every level
+    for (int l = 0; l < g.nl; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const int K = pick_K(L.H);
+        const int krow = (L.W <= 32 * 40) ? 40 : 64;
+        IirDev c;
+        iir_dev(4.0, K, krow, &c);  // lucas_kanade.jl:112
+        ColArgs ca{};
+        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
+        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
+        ca.o_iy = plane_off(L, DP_IY); ca.o_ix = plane_off(L, DP_IX); ca.plane_elems = L.plane_elems; ca.inv_n = nullptr;
+        dispatch_cols(s, K, true, ca, c);
+        RowArgs ra{};
+        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
+        ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_SYY); ra.plane_elems = L.plane_elems;
+        ra.inv_n = nullptr;
+        dispatch_rows(s, ra, c);
+        launches += 2;
+    }
+    return launches;
+}
+
+}  // namespace sk

@@ -1,0 +1,139 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the Float64 CPU oracle on the same seeded
+inputs.  Tolerances are the ones BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+import slamklt
+from slamklt import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PYR_RTOL = 1e-5      # "pyramid levels must agree within 1e-5 relative"
+POS_TOL = 0.01       # "tracked keypoint positions must agree within 0.01 px"
+FLAG_AGREE = 0.999   # "status flags must agree on at least 99.9% of points"
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def seq():
+    fr, aff = synth.make_sequence(2001, 3)
+    return synth.to_f64(fr), fr, aff
+
+
+@pytest.mark.parametrize("mode", ["ctor", "update"])
+@pytest.mark.parametrize("shape", [(376, 1241), (97, 131), (64, 40)])
+def test_pyramid_planes(ctx, seq, mode, shape):
+    H, W = shape
+    img = seq[0][0][:H, :W]
+    levels = 3
+    op = O.LKPyramid(img, levels, mode="ctor")
+    gp = slamklt.LKPyramid(ctx, img, levels)
+    if mode == "update":
+        img2 = seq[0][1][:H, :W]
+        op.update(img2)
+        gp.update(img2)
+    for l in range(levels + 1):
+        for name in ("layer", "Iy", "Ix", "Syy", "Sxx", "Syx"):
+            a, b = gp.plane(l, name), op.plane(l, name)
+            assert a.shape == b.shape
+            assert rel_err(a, b) < PYR_RTOL, (l, name, rel_err(a, b))
+        if l < levels:
+            assert rel_err(gp.plane(l, "blur"), op.plane(l, "blur")) < PYR_RTOL
+        # integral images: rebuilt in Float64 from fp32 planes, so the bound is on the window sums they serve
+        a, b = gp.plane(l, "Iyy"), op.plane(l, "Iyy")
+        assert rel_err(a, b) < 1e-5
+
+
+def _track_both(ctx, f0, f1, pts, levels=3, window=9, max_distance=1.0, disp=None, mode="ctor"):
+    o0, o1 = O.LKPyramid(f0, max(levels, 3), mode="ctor"), O.LKPyramid(f1, max(levels, 3), mode="ctor")
+    g0, g1 = slamklt.LKPyramid(ctx, f0, max(levels, 3)), slamklt.LKPyramid(ctx, f1, max(levels, 3))
+    if mode == "update":
+        o0.update(f0); o1.update(f1); g0.update(f0); g1.update(f1)
+    ro = O.fb_tracking(o0, o1, pts, displacement=disp, window_size=window, pyramid_levels=levels, max_distance=max_distance)
+    rg = slamklt.fb_tracking(g0, g1, pts, displacement=disp, window_size=window, pyramid_levels=levels, max_distance=max_distance)
+    return ro, rg
+
+
+def _check_tracks(ro, rg, min_n=1):
+    (po, so, fo), (pg, sg, fg) = ro, rg
+    n = len(so)
+    assert np.mean(so == sg) >= FLAG_AGREE or np.sum(so != sg) <= 1, np.mean(so == sg)
+    assert np.mean(fo == fg) >= FLAG_AGREE or np.sum(fo != fg) <= 1, np.mean(fo == fg)
+    both = so & sg
+    assert both.sum() >= min_n
+    d = np.abs(po[both] - pg[both]).max(axis=1)
+    assert np.mean(d < POS_TOL) >= FLAG_AGREE, (np.mean(d < POS_TOL), d.max())
+    return d
+
+
+def test_fb_tracking_kitti(ctx, seq):
+    f = seq[0]
+    e = O.Extractor(1000, 17, (11, 36), 35)
+    pts = O.detect(e, f[0], np.zeros((0, 2))).astype(np.float64)
+    pts += np.random.default_rng(5).uniform(-0.5, 0.5, pts.shape)  # tracked keypoints are sub-pixel in steady state
+    ro, rg = _track_both(ctx, f[0], f[1], pts)
+    d = _check_tracks(ro, rg, min_n=500)
+    assert np.median(d) < 1e-3
+    # and the tracks are right: against the known warp
+    gt = synth.true_flow(seq[2], 0, 1, pts)
+    ok = rg[1]
+    assert np.median(np.linalg.norm(rg[0][ok] - gt[ok], axis=1)) < 0.15
+
+
+def test_fb_tracking_update_mode_and_prior(ctx, seq):
+    f = seq[0]
+    pts = synth.random_keypoints(11, 700, 376, 1241, border=3.0)  # includes near-border points (clipped windows)
+    gt = synth.true_flow(seq[2], 0, 1, pts)
+    prior = 0.5 * (gt - pts) + np.random.default_rng(2).normal(0, 0.3, pts.shape)  # map_manager.jl:494: scale 1/2^1
+    ro, rg = _track_both(ctx, f[0], f[1], pts, levels=1, disp=prior, mode="update")
+    _check_tracks(ro, rg, min_n=100)
+
+
+def test_optflow_matches_oracle(ctx, seq):
+    f = seq[0]
+    pts = synth.random_keypoints(3, 400, 376, 1241, border=1.0)
+    o0, o1 = O.LKPyramid(f[1], 3), O.LKPyramid(f[2], 3)
+    g0, g1 = slamklt.LKPyramid(ctx, f[1], 3), slamklt.LKPyramid(ctx, f[2], 3)
+    alg_o, alg_g = O.LucasKanade(), slamklt.LucasKanade()
+    d0 = np.zeros_like(pts)
+    do, so, no = O.optflow(d0, o0, o1, pts, alg_o)
+    dg, sg, ng = slamklt.optflow(d0, g0, g1, pts, alg_g)
+    assert np.mean(so == sg) >= FLAG_AGREE or np.sum(so != sg) <= 1
+    both = so & sg
+    assert np.mean(np.abs(do[both] - dg[both]).max(axis=1) < POS_TOL) >= FLAG_AGREE
+    assert abs(no - ng) <= max(1, int(0.001 * len(pts)))
+
+
+def test_not_enough_layers(ctx, seq):
+    g0 = slamklt.LKPyramid(ctx, seq[0][0], 2)
+    with pytest.raises(slamklt.SlamKltError) as ei:
+        slamklt.optflow(np.zeros((1, 2)), g0, g0, np.array([[50.0, 50.0]]), slamklt.LucasKanade(pyramid_levels=3))
+    assert ei.value.code == slamklt.E_LAYERS
+    assert slamklt.fb_tracking(g0, g0, np.zeros((0, 2))) is None  # tracker.jl:24
+
+
+@pytest.mark.parametrize("n_cur", [0, 300])
+@pytest.mark.parametrize("dtype", ["f64", "u8"])
+def test_detect_identical(ctx, seq, n_cur, dtype):
+    f64, u8 = seq[0][0], seq[1][0]
+    e_o = O.Extractor(1000, 17, (11, 36), 35)
+    e_g = slamklt.Extractor(1000, 17, (11, 36), 35)
+    cur = synth.random_keypoints(21, n_cur, 376, 1241, border=0.0) if n_cur else np.zeros((0, 2))
+    ko = O.detect(e_o, f64, cur)
+    kg = slamklt.detect(ctx, e_g, f64 if dtype == "f64" else u8, cur)
+    assert ko.shape == kg.shape and np.array_equal(ko, kg)  # identical sets AND identical order
+    assert len(kg) > 300
+
+
+def test_detect_small_ragged(ctx, seq):
+    img = seq[0][0][:100, :150]  # ragged last cells: 100 = 2*35+30, 150 = 4*35+10
+    e_o = O.Extractor(200, 8, (3, 5), 35)
+    e_g = slamklt.Extractor(200, 8, (3, 5), 35)
+    cur = np.array([[10.5, 10.5], [50.0, 75.5], [99.6, 149.7], [1.0, 1.0]])
+    assert np.array_equal(O.detect(e_o, img, cur), slamklt.detect(ctx, e_g, img, cur))
+    full = np.zeros((200, 2)) + 5.0
+    assert len(slamklt.detect(ctx, e_g, img, full)) == 0  # extractor.jl:64
