@@ -108,6 +108,11 @@ int slamklt_get_stats(slamklt_ctx* ctx, slamklt_stats* out, int reset_lk_counter
 int slamklt_timer_start(slamklt_ctx* ctx);
 int slamklt_timer_stop(slamklt_ctx* ctx, float* elapsed_ms); /* records, synchronises, returns ms */
 
+/* per-kernel device timing (CUDA events around every launch on the context's stream).  Off by default; never
+ * enable it inside a region you time.  The report is text: one "kernel_name launches total_ms" line per kernel. */
+int slamklt_profile(slamklt_ctx* ctx, int enable);
+int slamklt_profile_report(slamklt_ctx* ctx, char* buf, size_t cap);
+
 /* ---- LKPyramid ------------------------------------------------------------------------- */
 /* allocation of LKPyramid(image, levels; reusable=true) -- pyramid.jl:40-72 */
 int slamklt_pyr_create(slamklt_ctx* ctx, int H, int W, int levels, slamklt_pyr** out);

@@ -76,7 +76,7 @@ _lib = None
 # every symbol include/slamklt.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "slamklt_last_error", "slamklt_version", "slamklt_device_count", "slamklt_ctx_create", "slamklt_ctx_destroy",
-    "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
+    "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_profile", "slamklt_profile_report", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
     "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
     "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
@@ -98,6 +98,8 @@ def lib():
         L.slamklt_ctx_destroy.argtypes = [vp]
         L.slamklt_ctx_sync.argtypes = [vp]
         L.slamklt_get_stats.argtypes = [vp, C.POINTER(Stats), C.c_int]
+        L.slamklt_profile.argtypes = [vp, C.c_int]
+        L.slamklt_profile_report.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.slamklt_timer_start.argtypes = [vp]
         L.slamklt_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.slamklt_pyr_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -172,6 +174,19 @@ class Context:
         s = Stats()
         _ck(lib().slamklt_get_stats(self._h, C.byref(s), 1 if reset else 0))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def profile(self, enable: bool):
+        _ck(lib().slamklt_profile(self._h, 1 if enable else 0))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total_ms)} accumulated since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _ck(lib().slamklt_profile_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
 
     def timer_start(self):
         _ck(lib().slamklt_timer_start(self._h))

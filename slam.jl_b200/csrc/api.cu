@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -175,7 +176,24 @@ struct slamklt_ctx {
     DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur;
     HostBuf h_out, h_status, h_misc;
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
+    // per-kernel profiling (off by default)
+    bool prof_on = false;
+    Hook hook{nullptr, nullptr};
+    std::vector<std::pair<std::string, cudaEvent_t>> prof_ev;
+    std::vector<cudaEvent_t> ev_pool;
+    std::map<std::string, std::pair<double, long long>> prof_acc;
+    const Hook* hk() const { return prof_on ? &hook : nullptr; }
 };
+
+static void prof_mark(void* user, const char* name) {
+    slamklt_ctx* c = (slamklt_ctx*)user;
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c->stream);
+    c->prof_ev.emplace_back(name, e);
+}
+static void prof_end(slamklt_ctx* c) { if (c->prof_on) prof_mark(c, "<end>"); }
 
 struct slamklt_pyr {
     PyrGeom g;
@@ -297,6 +315,8 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
+    for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_counters);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -322,6 +342,41 @@ int slamklt_get_stats(slamklt_ctx* c, slamklt_stats* out, int reset) {
     out->lk_window_iters = h[0]; out->lk_iters = h[1];
     out->h2d_bytes = c->h2d; out->d2h_bytes = c->d2h;
     if (reset) CK(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
+    return 0;
+}
+
+int slamklt_profile(slamklt_ctx* c, int enable) {
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->hook.fn = prof_mark; c->hook.user = c;
+    c->prof_on = enable != 0;
+    if (enable) { c->prof_acc.clear(); for (auto& pe : c->prof_ev) c->ev_pool.push_back(pe.second); c->prof_ev.clear(); }
+    return 0;
+}
+
+int slamklt_profile_report(slamklt_ctx* c, char* buf, size_t cap) {
+    if (!c || !buf || cap == 0) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->prof_ev.size(); ++i) {
+        if (c->prof_ev[i].first == "<end>") continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->prof_ev[i].second, c->prof_ev[i + 1].second) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto& acc = c->prof_acc[c->prof_ev[i].first];
+        acc.first += ms; acc.second += 1;
+    }
+    for (auto& pe : c->prof_ev) c->ev_pool.push_back(pe.second);
+    c->prof_ev.clear();
+    size_t off = 0;
+    buf[0] = 0;
+    for (auto& kv : c->prof_acc) {
+        int n = snprintf(buf + off, cap - off, "%s %lld %.6f\n", kv.first.c_str(), kv.second.second, kv.second.first);
+        if (n < 0 || (size_t)n >= cap - off) break;
+        off += (size_t)n;
+    }
     return 0;
 }
 
@@ -395,10 +450,11 @@ static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const
         int r = get_norms(c, g, sigma, ny, nx);
         if (r) return r;
     }
-    c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64);
+    c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64, c->hk());
     CKL();
-    c->launches += launch_pyramid(c->stream, fs, f0, n_frames, g, sigma, mode, ny, nx);
+    c->launches += launch_pyramid(c->stream, fs, f0, n_frames, g, sigma, mode, ny, nx, c->hk());
     CKL();
+    prof_end(c);
     return 0;
 }
 
@@ -559,8 +615,9 @@ static int run_lk_single(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters;
-    c->launches += launch_lk(c->stream, a);
+    c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
+    prof_end(c);
     return 0;
 }
 
@@ -653,8 +710,9 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_fra
     }
     a.cell_out = (int64_t*)c->cell_out.p; a.cell_cnt = (int*)c->cell_cnt.p;
     a.out = (int64_t*)c->det_out.p; a.n_out = (int*)c->det_n.p;
-    c->launches += launch_detect(c->stream, a);
+    c->launches += launch_detect(c->stream, a, c->hk());
     CKL();
+    prof_end(c);
     CK(cudaMemcpyAsync(n_out, c->det_n.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int f = 0; f < n_frames; ++f) {
@@ -691,7 +749,7 @@ int slamklt_detect(slamklt_ctx* c, const void* img, int dtype, int H, int W, int
         DevBuf& scratch = c->outp;  // any buffer large enough for one level-0 frame
         if ((r = scratch.ensure(g.frame_elems * sizeof(float)))) return r;
         FrameSet fs{(float*)scratch.p, g.frame_elems, 1, 0};
-        c->launches += launch_convert(c->stream, c->staging.p, dtype, H, (size_t)H * W, fs, 0, 1, g, (double*)c->img64.p);
+        c->launches += launch_convert(c->stream, c->staging.p, dtype, H, (size_t)H * W, fs, 0, 1, g, (double*)c->img64.p, c->hk());
         CKL();
         d_img = (const double*)c->img64.p;
     }
@@ -797,8 +855,9 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters;
-    c->launches += launch_lk(c->stream, a);
+    c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
+    prof_end(c);
     return 0;
 }
 
@@ -861,7 +920,7 @@ int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, in
     if (b->up_dtype == SLAMKLT_F64) d_img = (const double*)b->staging.p;
     else {
         if ((r = b->img64.ensure((size_t)b->n_frames * b->g.H0 * b->g.W0 * 8))) return r;
-        c->launches += launch_convert(c->stream, b->staging.p, b->up_dtype, b->g.H0, (size_t)b->g.H0 * b->g.W0, fs_of(b), 1, b->n_frames, b->g, (double*)b->img64.p);
+        c->launches += launch_convert(c->stream, b->staging.p, b->up_dtype, b->g.H0, (size_t)b->g.H0 * b->g.W0, fs_of(b), 1, b->n_frames, b->g, (double*)b->img64.p, c->hk());
         CKL();
         d_img = (const double*)b->img64.p;
     }

@@ -93,13 +93,17 @@ struct DetArgs {
     int cap;
 };
 
+// optional per-kernel profiling hook: called with the kernel's name right before each launch
+struct Hook { void (*fn)(void* user, const char* name); void* user; };
+inline void mark(const Hook* h, const char* name) { if (h && h->fn) h->fn(h->user, name); }
+
 // launchers (each returns the number of kernels it launched; errors are picked up by cudaGetLastError in api.cu)
 int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t src_frame_stride_elems, FrameSet dst, int dst_f0,
-                   int n_frames, const PyrGeom& g, double* dst64 /*nullable: also keep f64 copy, frame stride H*W*/);
+                   int n_frames, const PyrGeom& g, double* dst64 /*nullable: also keep f64 copy, frame stride H*W*/, const Hook* hk);
 int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
-                   const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */);
-int launch_lk(cudaStream_t s, const LKArgs& a);
-int launch_detect(cudaStream_t s, const DetArgs& a);
+                   const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */, const Hook* hk);
+int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
+int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);
 
 void iir_design(double sigma, double a[3], double* scale, double M[9]);

@@ -245,12 +245,14 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_compact(DetArgs a, int n
     if (threadIdx.x == 0) a.n_out[f] = s_base;
 }
 
-int launch_detect(cudaStream_t s, const DetArgs& a) {
+int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk) {
     const int n_cells = a.grid_h * a.grid_w;
     const size_t smem = detect_smem_bytes(a.cs, a.hw);
     cudaFuncSetAttribute(k_detect_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(n_cells, a.n_frames);
+    mark(hk, "k_detect_cells");
     k_detect_cells<<<grid, DET_THREADS, smem, s>>>(a);
+    mark(hk, "k_detect_compact");
     k_detect_compact<<<a.n_frames, DET_THREADS, 0, s>>>(a, n_cells);
     return 2;
 }

@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(128) k_lk(LKArgs a) {
     }
 }
 
-int launch_lk(cudaStream_t s, const LKArgs& a) {
+int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     const int total = a.n_frames * a.n_per_frame;
     if (total <= 0) return 0;
+    mark(hk, a.mode ? "k_lk_fb" : "k_lk_optflow");
     const int wpb = 4;
     const int blocks = (total + wpb - 1) / wpb;
     const int w2 = 2 * a.window + 1;

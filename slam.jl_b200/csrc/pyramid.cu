@@ -13,6 +13,8 @@
 // true incoming state.  Along y (contiguous, short lines) one warp owns a whole column in registers and the
 // carries travel through a Kogge-Stone scan on shuffles; along x (strided, long lines) a CTA owns a strip of
 // rows, chunks are spread over warps and the carries travel through shared memory.
+#include <cstdio>
+
 #include "common.cuh"
 
 namespace sk {
@@ -41,8 +43,9 @@ __global__ void k_convert(const T* __restrict__ src, int ld, size_t src_stride, 
 }
 
 int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t src_stride, FrameSet dst, int dst_f0, int n_frames,
-                   const PyrGeom& g, double* dst64) {
+                   const PyrGeom& g, double* dst64, const Hook* hk) {
     const LevelGeom& l0 = g.lv[0];
+    mark(hk, "k_convert");
     dim3 grid((l0.H + 127) / 128, l0.W, n_frames), block(128);
     size_t off = plane_off(l0, DP_I);
     if (dtype == SLAMKLT_F64)
@@ -431,8 +434,9 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c) {
 }
 
 int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
-                   const float* const* inv_ny, const float* const* inv_nx) {
+                   const float* const* inv_ny, const float* const* inv_nx, const Hook* hk) {
     int launches = 0;
+    char nm[48];
     const bool ctor = mode == SLAMKLT_MODE_CTOR;
     // 1. Gaussian pyramid (sigma chain): layer l -> blur l -> layer l+1
     for (int l = 0; l + 1 < g.nl; ++l) {
@@ -446,12 +450,15 @@ int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrG
         ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
         ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
         ca.plane_elems = L.plane_elems; ca.inv_n = ctor ? inv_ny[l] : nullptr;
+        snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
         dispatch_cols(s, K, false, ca, c);
         RowArgs ra{};
         ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
         ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
         ra.inv_n = ctor ? inv_nx[l] : nullptr;
+        snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
         dispatch_rows(s, ra, c);
+        snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
         dim3 grid((N.H + 127) / 128, N.W, n_frames);
         k_resize<<<grid, 128, 0, s>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
         launches += 3;
@@ -467,11 +474,13 @@ int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrG
         ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
         ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
         ca.o_iy = plane_off(L, DP_IY); ca.o_ix = plane_off(L, DP_IX); ca.plane_elems = L.plane_elems; ca.inv_n = nullptr;
+        snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
         dispatch_cols(s, K, true, ca, c);
         RowArgs ra{};
         ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
         ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_SYY); ra.plane_elems = L.plane_elems;
         ra.inv_n = nullptr;
+        snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
         dispatch_rows(s, ra, c);
         launches += 2;
     }
