@@ -227,8 +227,9 @@ static int make_geom(int H, int W, int levels, PyrGeom* g) {
         if (pick_K(h) == 0) return fail(SLAMKLT_E_INVALID, "image height %d exceeds the supported 1088", h);
         if (w > 2048) return fail(SLAMKLT_E_INVALID, "image width %d exceeds the supported 2048", w);
         LevelGeom& L = g->lv[l];
-        L.H = h; L.W = w; L.pitch = (h + 3) & ~3;
-        L.plane_elems = (((size_t)L.pitch * w) + 31) & ~(size_t)31;
+        // one guard row and one guard column (kept zero) so that LK's weight-0 bilinear tap at H+1 / W+1 stays in bounds
+        L.H = h; L.W = w; L.pitch = (h + 1 + 3) & ~3;
+        L.plane_elems = (((size_t)L.pitch * (w + 1)) + 31) & ~(size_t)31;
         L.off = off;
         off += L.plane_elems * DP_COUNT;
         h = (h + 1) / 2; w = (w + 1) / 2;  // ceil(s/2), [3P] Images.gaussian_pyramid
