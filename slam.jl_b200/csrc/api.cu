@@ -215,6 +215,9 @@ struct slamklt_batch {
     bool primed = false;
 };
 
+// LK reads up to 32 window columns without predicates; the last plane of an allocation needs that much slack
+static const size_t ALLOC_SLACK = 34 * 1100;
+
 static int make_geom(int H, int W, int levels, PyrGeom* g) {
     if (H < 4 || W < 4) return fail(SLAMKLT_E_INVALID, "image %dx%d too small", H, W);
     if (levels < 0 || levels + 1 > MAX_LAYERS) return fail(SLAMKLT_E_INVALID, "pyramid_levels %d out of range [0,%d]", levels, MAX_LAYERS - 1);
@@ -235,6 +238,7 @@ static int make_geom(int H, int W, int levels, PyrGeom* g) {
         h = (h + 1) / 2; w = (w + 1) / 2;  // ceil(s/2), [3P] Images.gaussian_pyramid
     }
     g->frame_elems = off;
+    g->pad_ = 0;
     return 0;
 }
 
@@ -407,9 +411,9 @@ int slamklt_pyr_create(slamklt_ctx* c, int H, int W, int levels, slamklt_pyr** o
     if (r) return r;
     slamklt_pyr* p = new slamklt_pyr();
     p->g = g;
-    cudaError_t e = cudaMalloc(&p->base, g.frame_elems * sizeof(float));
+    cudaError_t e = cudaMalloc(&p->base, (g.frame_elems + ALLOC_SLACK) * sizeof(float));
     if (e != cudaSuccess) { delete p; return fail(SLAMKLT_E_CUDA, "cudaMalloc pyramid failed: %s", cudaGetErrorString(e)); }
-    cudaMemsetAsync(p->base, 0, g.frame_elems * sizeof(float), c->stream);
+    cudaMemsetAsync(p->base, 0, (g.frame_elems + ALLOC_SLACK) * sizeof(float), c->stream);
     p->owns = true;
     *out = p;
     return 0;
@@ -530,31 +534,41 @@ int slamklt_pyr_level_dims(const slamklt_pyr* p, int level, int* H, int* W) {
 int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int plane, double* out) {
     if (!c || !p || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
     if (level < 0 || level >= p->g.nl) return fail(SLAMKLT_E_INVALID, "level %d out of range", level);
-    int dp;
+    int dp = DP_I, which = -1, comp = -1;  // which: smoothed product plane to recompute; comp: component of the gradient plane
     bool sat = false;
     switch (plane) {
         case SLAMKLT_PLANE_LAYER: dp = DP_I; break;
-        case SLAMKLT_PLANE_IY: dp = DP_IY; break;
-        case SLAMKLT_PLANE_IX: dp = DP_IX; break;
-        case SLAMKLT_PLANE_IYY: dp = DP_SYY; sat = true; break;
-        case SLAMKLT_PLANE_IXX: dp = DP_SXX; sat = true; break;
-        case SLAMKLT_PLANE_IYX: dp = DP_SYX; sat = true; break;
-        case SLAMKLT_PLANE_SYY: dp = DP_SYY; break;
-        case SLAMKLT_PLANE_SXX: dp = DP_SXX; break;
-        case SLAMKLT_PLANE_SYX: dp = DP_SYX; break;
+        case SLAMKLT_PLANE_IY: dp = DP_GRAD; comp = 0; break;
+        case SLAMKLT_PLANE_IX: dp = DP_GRAD; comp = 1; break;
+        case SLAMKLT_PLANE_IYY: which = 0; sat = true; break;
+        case SLAMKLT_PLANE_IXX: which = 1; sat = true; break;
+        case SLAMKLT_PLANE_IYX: which = 2; sat = true; break;
+        case SLAMKLT_PLANE_SYY: which = 0; break;
+        case SLAMKLT_PLANE_SXX: which = 1; break;
+        case SLAMKLT_PLANE_SYX: which = 2; break;
         case SLAMKLT_PLANE_BLUR: dp = DP_BLUR; break;
         default: return fail(SLAMKLT_E_INVALID, "unknown plane %d", plane);
     }
+    if ((which >= 0 || comp >= 0) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     const LevelGeom& L = p->g.lv[level];
-    std::vector<float> tmp((size_t)L.H * L.W);
+    std::vector<float> tmp((size_t)L.H * L.W * (comp >= 0 ? 2 : 1));
+    if (which >= 0) {
+        // the pyramid keeps only the row-prefix form of the smoothed planes; rebuild the plain plane from the y-filtered scratch
+        c->launches += launch_smoothed_plane(c->stream, fs_of(p), 0, p->g, level, which, c->hk());
+        CKL();
+        prof_end(c);
+        dp = DP_TMP;
+    }
     const float* src = pyr_frame_base(p) + plane_off(L, dp);
-    CK(cudaMemcpy2DAsync(tmp.data(), (size_t)L.H * sizeof(float), src, (size_t)L.pitch * sizeof(float), (size_t)L.H * sizeof(float), L.W,
-                         cudaMemcpyDeviceToHost, c->stream));
+    const size_t rowb = (size_t)L.H * sizeof(float) * (comp >= 0 ? 2 : 1), pitchb = (size_t)L.pitch * sizeof(float) * (comp >= 0 ? 2 : 1);
+    CK(cudaMemcpy2DAsync(tmp.data(), rowb, src, pitchb, rowb, L.W, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->d2h += tmp.size() * sizeof(float);
-    for (size_t i = 0; i < tmp.size(); ++i) out[i] = (double)tmp[i];
+    const size_t npx = (size_t)L.H * L.W;
+    if (comp >= 0) for (size_t i = 0; i < npx; ++i) out[i] = (double)tmp[2 * i + comp];
+    else for (size_t i = 0; i < npx; ++i) out[i] = (double)tmp[i];
     if (sat) {  // integral_image!, lucas_kanade.jl:131-138, in Float64 on the host (parity access only)
         for (int x = 0; x < L.W; ++x) {
             double acc = 0;
@@ -573,8 +587,8 @@ static int fill_lk_levels(const PyrGeom& g, LKArgs* a) {
         const LevelGeom& L = g.lv[l];
         LKLevel& d = a->lv[l];
         d.H = L.H; d.W = L.W; d.pitch = L.pitch;
-        d.oI = plane_off(L, DP_I); d.oIy = plane_off(L, DP_IY); d.oIx = plane_off(L, DP_IX);
-        d.oSyy = plane_off(L, DP_SYY); d.oSxx = plane_off(L, DP_SXX); d.oSyx = plane_off(L, DP_SYX);
+        d.oI = plane_off(L, DP_I); d.oG = plane_off(L, DP_GRAD);
+        d.oRyy = plane_off(L, DP_RYY); d.oRxx = plane_off(L, DP_RXX); d.oRyx = plane_off(L, DP_RYX);
     }
     return 0;
 }
@@ -771,9 +785,9 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     if (r) return r;
     slamklt_batch* b = new slamklt_batch();
     b->g = g; b->n_frames = n_frames; b->n_slots = n_frames + 1; b->slot0 = 0; b->max_pts = max_pts;
-    cudaError_t e = cudaMalloc(&b->base, g.frame_elems * sizeof(float) * b->n_slots);
+    cudaError_t e = cudaMalloc(&b->base, (g.frame_elems * b->n_slots + ALLOC_SLACK) * sizeof(float));
     if (e != cudaSuccess) { delete b; return fail(SLAMKLT_E_CUDA, "cudaMalloc batch (%zu bytes) failed: %s", g.frame_elems * sizeof(float) * b->n_slots, cudaGetErrorString(e)); }
-    cudaMemsetAsync(b->base, 0, g.frame_elems * sizeof(float) * b->n_slots, c->stream);
+    cudaMemsetAsync(b->base, 0, (g.frame_elems * b->n_slots + ALLOC_SLACK) * sizeof(float), c->stream);
     if ((r = b->pts.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
     if ((r = b->outp.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
     if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;

@@ -11,11 +11,14 @@ namespace sk {
 constexpr int MAX_LAYERS = 8;   // pyramid_levels + 1 <= 8
 constexpr unsigned FULL = 0xffffffffu;
 
-// device planes kept per level (fp32, y contiguous, pitch = roundup4(H))
+// device planes kept per level (fp32, y contiguous, pitch = roundup4(H+1), W+1 columns, guards kept at zero)
 enum DevPlane {
-    DP_I = 0, DP_IY, DP_IX, DP_SYY, DP_SXX, DP_SYX,  // the pyramid proper (LKPyramid fields)
-    DP_T0, DP_T1, DP_T2,                              // scratch: planes after the dim-1 recursive pass
-    DP_BLUR,                                          // LKCache.gaussian_filtered
+    DP_I = 0,              // layer
+    DP_GRAD = 1,           // interleaved (Iy, Ix): float2 per pixel, occupies two plane slots
+    DP_RYY = 3, DP_RXX, DP_RYX,  // exclusive prefix sums along x of the smoothed Iy*Iy, Ix*Ix, Iy*Ix (W+1 columns)
+    DP_T0, DP_T1, DP_T2,   // scratch: planes after the dim-1 recursive pass
+    DP_BLUR,               // LKCache.gaussian_filtered
+    DP_TMP,                // scratch for parity downloads
     DP_COUNT
 };
 
@@ -59,7 +62,7 @@ struct IirDev {
 
 struct LKLevel {
     int H, W, pitch, pad_;
-    size_t oI, oIy, oIx, oSyy, oSxx, oSyx;
+    size_t oI, oG, oRyy, oRxx, oRyx;
 };
 
 struct LKArgs {
@@ -102,6 +105,7 @@ int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t sr
                    int n_frames, const PyrGeom& g, double* dst64 /*nullable: also keep f64 copy, frame stride H*W*/, const Hook* hk);
 int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */, const Hook* hk);
+int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);

@@ -19,6 +19,12 @@
 
 namespace sk {
 
+template <typename T>
+__device__ __forceinline__ const T* col_ptr(const T* base, int stride_bytes, int k) {
+    // base + k columns: one IMAD.WIDE instead of a 64-bit multiply-shift-add chain
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (long long)stride_bytes * k);
+}
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
         }
         const double eps = back ? 1e-2 : a.eps;  // tracker.jl:51-54 does not forward epsilon to the backward pass
         const LKLevel& L = a.lv[lvl];
-        const int H = L.H, W = L.W, pitch = L.pitch;
+        const int H = L.H, W = L.W, pitch = L.pitch, pitch4 = L.pitch * 4;
         const double inv = 1.0 / (double)(1 << lvl);
         const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);  // get_pyramid_coordinate, lucas_kanade.jl:197
         // get_offsets(point, point), lucas_kanade.jl:199-208, in integer arithmetic
@@ -75,21 +81,33 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
                 // ---- compute_spatial_gradient (lucas_kanade.jl:140-157): window sums of the smoothed planes
                 const int r0 = py - up, c0 = px - left;
                 if (nrows < 1 || ncols < 1 || r0 < 1 || c0 < 1 || py + down > H || px + right > W) { ok = false; break; }
-                const size_t base = (size_t)(r0 - 1 + min(lane, nrows - 1)) + (size_t)(c0 - 1) * pitch;
                 const bool rowact = lane < nrows;
-                float syy = 0.f, sxx = 0.f, syx = 0.f;
+                const int row = r0 - 1 + min(lane, nrows - 1);  // 0-based
+                const float* colA = fbA + (size_t)row;
+                // window sums from the exclusive row prefix planes: R[., c1] - R[., c0-1]  (0-based prefix columns)
+                float syy, sxx, syx;
                 {
-                    const float* p0 = fbA + L.oSyy + base;
-                    const float* p1 = fbA + L.oSxx + base;
-                    const float* p2 = fbA + L.oSyx + base;
-#pragma unroll
-                    for (int k = 0; k < W2; ++k)
-                        if (k < ncols) {
-                            syy += __ldg(p0 + (size_t)k * pitch);
-                            sxx += __ldg(p1 + (size_t)k * pitch);
-                            syx += __ldg(p2 + (size_t)k * pitch);
-                        }
+                    const size_t lo = (size_t)(c0 - 1) * pitch, hi = (size_t)(px + right) * pitch;
+                    syy = __ldg(colA + L.oRyy + hi) - __ldg(colA + L.oRyy + lo);
+                    sxx = __ldg(colA + L.oRxx + hi) - __ldg(colA + L.oRxx + lo);
+                    syx = __ldg(colA + L.oRyx + hi) - __ldg(colA + L.oRyx + lo);
                     if (!rowact) { syy = 0.f; sxx = 0.f; syx = 0.f; }
+                }
+                // ---- template rows into registers (issued before the reduction so the loads overlap it)
+                {
+                    const float* pI = colA + L.oI + (size_t)(c0 - 1) * pitch;
+                    const float2* pG = reinterpret_cast<const float2*>(fbA + L.oG) + (size_t)row + (size_t)(c0 - 1) * pitch;
+#pragma unroll
+                    for (int k = 0; k < W2; ++k) {
+                        const bool okk = rowact && k < ncols;
+                        float2 g2 = make_float2(0.f, 0.f);
+                        float iv = 0.f;
+                        if (okk) {
+                            iv = __ldg(col_ptr(pI, pitch4, k));
+                            g2 = __ldg(col_ptr(pG, 2 * pitch4, k));
+                        }
+                        tI[k] = iv; tIy[k] = g2.x; tIx[k] = g2.y;
+                    }
                 }
                 const double ga = (double)warp_sum_f(syy), gc = (double)warp_sum_f(sxx), gb = (double)warp_sum_f(syx);
                 // singular values of the symmetric G = [a b; b c] (utils.jl:5-27 with H = 0): Q +- R
@@ -114,17 +132,6 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
                         g00 = vx * vx * nn; g01 = vx * vy * nn; g11 = vy * vy * nn;
                     }
                 }
-                // ---- template rows into registers
-                const float* pI = fbA + L.oI + base;
-                const float* pIy = fbA + L.oIy + base;
-                const float* pIx = fbA + L.oIx + base;
-#pragma unroll
-                for (int k = 0; k < W2; ++k) {
-                    const bool okk = rowact && k < ncols;
-                    tI[k] = okk ? __ldg(pI + (size_t)k * pitch) : 0.f;
-                    tIy[k] = okk ? __ldg(pIy + (size_t)k * pitch) : 0.f;
-                    tIx[k] = okk ? __ldg(pIx + (size_t)k * pitch) : 0.f;
-                }
                 setup = false;
             }
             if (it >= a.iterations) break;
@@ -145,8 +152,10 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
             const float wy = (float)(pcy - (double)fy), wx = (float)(pcx - (double)fx);
             const float* tp = fbB + L.oI + (size_t)(fy - up - 1 + min(lane, nrows)) + (size_t)(fx - left - 1) * pitch;
             float tv[W2 + 1];
+            // unpredicated: columns past the window are finite junk (guard column, next plane or allocation slack) and
+            // meet zero template gradients below
 #pragma unroll
-            for (int k = 0; k <= W2; ++k) tv[k] = (k <= ncols) ? __ldg(tp + (size_t)k * pitch) : 0.f;
+            for (int k = 0; k <= W2; ++k) tv[k] = __ldg(col_ptr(tp, pitch4, k));
             float by = 0.f, bx = 0.f;
             float tn = __shfl_down_sync(FULL, tv[0], 1);
             float prev = fmaf(wy, tn - tv[0], tv[0]);

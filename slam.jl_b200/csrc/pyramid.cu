@@ -2,17 +2,22 @@
 // Triggs-Sdika boundaries along both dimensions, Scharr gradients + gradient products, bilinear decimation.
 //
 // Reference behaviour: pyramid.jl:40-137 (LKPyramid ctor, update!, gaussian_pyramid!, imgradients_yx!),
-// lucas_kanade.jl:102-129 (compute_partial_derivatives!).  The integral images of lucas_kanade.jl:131-138 are
-// NOT materialised: the LK kernel sums the 19x19 window of the smoothed planes directly.
+// lucas_kanade.jl:102-129 (compute_partial_derivatives!).  The 2-D integral images of lucas_kanade.jl:131-138 are
+// replaced by 1-D exclusive prefix sums along x of the smoothed planes (accumulated in Float64, stored fp32): the
+// LK kernel gets a window sum from two coalesced loads per row and plane, and fp32 keeps enough digits because a
+// row prefix is ~65x a window sum, not ~10^5x like a 2-D integral image.
 //
-// Layout: every plane is fp32, y contiguous (Julia column-major), pitch = roundup4(H) floats.
+// Layout: every plane is fp32, y contiguous (Julia column-major), pitch = roundup4(H+1) floats, W+1 columns; the guard
+// row(s) y >= H and the guard column x = W are kept at zero by every kernel here.  Iy and Ix are interleaved
+// (float2 per pixel) so that the LK template costs one 8-byte load per pixel.
 //
 // The recursion u[i] = x[i] + a1 u[i-1] + a2 u[i-2] + a3 u[i-3] is sequential along a line.  Both kernels
 // cut each line into chunks, run every chunk from a zero state to obtain its outgoing state, combine the
 // chunk states with powers of the companion matrix A (exact by linearity), and re-run every chunk from its
-// true incoming state.  Along y (contiguous, short lines) one warp owns a whole column in registers and the
-// carries travel through a Kogge-Stone scan on shuffles; along x (strided, long lines) a CTA owns a strip of
-// rows, chunks are spread over warps and the carries travel through shared memory.
+// true incoming state.  Along y (contiguous, short lines) one warp owns a whole column in registers (vector
+// loads, lane l owns rows [l*K, l*K+K)) and the carries travel through a Kogge-Stone scan on shuffles; along x
+// (strided, long lines) a CTA owns a strip of rows, chunks are spread over warps and the carries travel through
+// shared memory.
 #include <cstdio>
 
 #include "common.cuh"
@@ -58,6 +63,55 @@ int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t sr
 }
 
 // ----------------------------------------------------------------------------------------------
+// column I/O: lane l owns rows [l*K, l*K+K) of a column; K is even, so 8- or 16-byte vectors are always aligned
+// ----------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void load_col(const float* __restrict__ col, int y0, int pitch, float (&x)[K]) {
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int v = 0; v < K / 4; ++v) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y0 + 4 * v < pitch) t = __ldg(reinterpret_cast<const float4*>(col + y0 + 4 * v));
+            x[4 * v] = t.x; x[4 * v + 1] = t.y; x[4 * v + 2] = t.z; x[4 * v + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < K / 2; ++v) {
+            float2 t = make_float2(0.f, 0.f);
+            if (y0 + 2 * v < pitch) t = __ldg(reinterpret_cast<const float2*>(col + y0 + 2 * v));
+            x[2 * v] = t.x; x[2 * v + 1] = t.y;
+        }
+    }
+}
+
+// rows >= H (guard rows) are written as zero
+template <int K>
+__device__ __forceinline__ void store_col(float* __restrict__ col, int y0, int pitch, int H, const float (&x)[K]) {
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int v = 0; v < K / 4; ++v) {
+            const int y = y0 + 4 * v;
+            if (y < pitch) {
+                float4 t;
+                t.x = y < H ? x[4 * v] : 0.f; t.y = y + 1 < H ? x[4 * v + 1] : 0.f;
+                t.z = y + 2 < H ? x[4 * v + 2] : 0.f; t.w = y + 3 < H ? x[4 * v + 3] : 0.f;
+                *reinterpret_cast<float4*>(col + y) = t;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < K / 2; ++v) {
+            const int y = y0 + 2 * v;
+            if (y < pitch) {
+                float2 t;
+                t.x = y < H ? x[2 * v] : 0.f; t.y = y + 1 < H ? x[2 * v + 1] : 0.f;
+                *reinterpret_cast<float2*>(col + y) = t;
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // warp-wide recursive filter of one line held in registers: lane l owns elements [l*K, l*K+K)
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, float r1, float r2, float& q0, float& q1, float& q2) {
@@ -69,13 +123,15 @@ __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, 
 template <int K>
 __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const int lane, const IirDev& c, const bool zero_border) {
     const int y0 = lane * K;
+    const int nv = min(max(n - y0, 0), K);  // valid elements of this lane
+    const int jl = n - 1 - y0;              // slot of the last element of the line, if it lives in this lane
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
-    const int ln = (n - 1) / K, jn = (n - 1) - ln * K;
+    const int ln = (n - 1) / K;
     float first = __shfl_sync(FULL, x[0], 0);
     float lastv = 0.f;
 #pragma unroll
     for (int j = 0; j < K; ++j)
-        if (j == jn) lastv = x[j];
+        if (j == jl) lastv = x[j];
     lastv = __shfl_sync(FULL, lastv, ln);
     const float iminus = zero_border ? 0.f : first, iplus = zero_border ? 0.f : lastv;
     const float um = iminus * c.inv1ma;
@@ -84,7 +140,7 @@ __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const 
     float s0 = lane == 0 ? um : 0.f, s1 = s0, s2 = s0;
 #pragma unroll
     for (int j = 0; j < K; ++j)
-        if (y0 + j < n) {
+        if (j < nv) {
             float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
             s2 = s1; s1 = s0; s0 = u;
         }
@@ -101,7 +157,7 @@ __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const 
     // phase 3: true pass
 #pragma unroll
     for (int j = 0; j < K; ++j)
-        if (y0 + j < n) {
+        if (j < nv) {
             float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
             x[j] = u;
             s2 = s1; s1 = s0; s0 = u;
@@ -118,9 +174,8 @@ __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const 
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
-        const int idx = y0 + j;
-        if (idx < n) {
-            if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
+        if (j < nv) {
+            if (j == jl) { t0 = vr0; t1 = vr1; t2 = vr2; }
             else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
         }
     }
@@ -136,10 +191,9 @@ __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const 
     const float sc = c.scale;
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
-        const int idx = y0 + j;
-        if (idx < n) {
+        if (j < nv) {
             float v;
-            if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
+            if (j == jl) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
             else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
             x[j] = v * sc;
         }
@@ -147,7 +201,7 @@ __device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const 
 }
 
 // ----------------------------------------------------------------------------------------------
-// dim-1 kernels (along y).  One warp per (frame, column).
+// dim-1 kernels (along y)
 // ----------------------------------------------------------------------------------------------
 struct ColArgs {
     FrameSet fs;
@@ -156,11 +210,12 @@ struct ColArgs {
     int zero_border;       // blur: NA mode; grad: Fill(0) Scharr border
     size_t o_in;           // layer
     size_t o_out0;         // blur: T0;   grad: T0,T1,T2 consecutive
-    size_t o_iy, o_ix;     // grad only
+    size_t o_grad;         // grad only: interleaved (Iy, Ix)
     size_t plane_elems;
     const float* inv_n;    // blur NA mode: 1/ny[y]
 };
 
+// One warp per (frame, column).
 template <int K>
 __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
     const int lane = threadIdx.x & 31;
@@ -174,81 +229,114 @@ __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
         const float* in = fb + a.o_in + (size_t)xcol * a.pitch;
         float* out = fb + a.o_out0 + (size_t)xcol * a.pitch;
         float x[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? in[y0 + j] : 0.f;
+        load_col<K>(in, y0, a.pitch, x);
         warp_iir_line<K>(x, a.H, lane, c, a.zero_border != 0);
         if (a.inv_n) {
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                if (y0 + j < a.H) x[j] *= a.inv_n[y0 + j];
+                if (y0 + j < a.H) x[j] *= __ldg(a.inv_n + y0 + j);
         }
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (y0 + j < a.H) out[y0 + j] = x[j];
+        store_col<K>(out, y0, a.pitch, a.H, x);
     }
 }
 
 // Scharr gradients (pyramid.jl:59,75,98-103), gradient products and the y pass of their sigma=4 smoothing
-// (lucas_kanade.jl:116-126).  Writes Iy, Ix and the three y-filtered product planes T0 (yy), T1 (xx), T2 (yx).
+// (lucas_kanade.jl:116-126).  A warp walks a strip of CS consecutive columns with a 3-column sliding window in
+// registers, so every layer column is loaded once per strip (+2 halo columns).  Writes the interleaved (Iy, Ix)
+// plane and the three y-filtered product planes T0 (yy), T1 (xx), T2 (yx).
+constexpr int GRAD_CS = 8;
+
 template <int K>
-__global__ void __launch_bounds__(256) k_cols_grad(ColArgs a, IirDev c) {
+__device__ __forceinline__ void load_col_halo(const float* __restrict__ I, int xcol, int W, int pitch, int H, int y0, int lane, bool zb,
+                                              float (&e)[K + 2]) {
+    // e[0] = row y0-1, e[1..K] = rows y0..y0+K-1, e[K+1] = row y0+K; border rule along x and y applied here
+    float x[K];
+    const bool inside = xcol >= 0 && xcol < W;
+    if (inside || !zb) {
+        const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
+        load_col<K>(I + (size_t)xc * pitch, y0, pitch, x);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = 0.f;
+    }
+    float upv = __shfl_up_sync(FULL, x[K - 1], 1);
+    float dnv = __shfl_down_sync(FULL, x[0], 1);
+    if (lane == 0) upv = zb ? 0.f : x[0];
+    if (lane == 31) dnv = 0.f;
+    e[0] = upv;
+#pragma unroll
+    for (int j = 0; j < K; ++j) e[j + 1] = x[j];
+    e[K + 1] = dnv;
+    if (!zb) {
+        // replicate below the last row: the neighbour of row H-1 is row H-1 itself (rows >= H hold guard zeros)
+#pragma unroll
+        for (int j = 1; j <= K + 1; ++j)
+            if (y0 + j - 1 == H) e[j] = e[j - 1];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_cols_grad(ColArgs a, IirDev c) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = a.n_frames * a.W;
+    const int H = a.H, W = a.W, pitch = a.pitch;
+    const int strips = (W + GRAD_CS - 1) / GRAD_CS;
+    const int total = a.n_frames * strips;
     const int y0 = lane * K;
-    const int H = a.H, W = a.W;
     const bool zb = a.zero_border != 0;
     for (int w = warp; w < total; w += nwarps) {
-        const int f = w / W, xcol = w - f * W;
+        const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
         float* fb = a.fs.frame(a.f0 + f);
         const float* I = fb + a.o_in;
-        // three columns x-1, x, x+1, rows y0-1 .. y0+K
-        float cm[K + 2], cc[K + 2], cp[K + 2];
-        const int xm = xcol - 1, xp = xcol + 1;
-        const bool okm = xm >= 0, okp = xp < W;
-        const float* colm = I + (size_t)(okm ? xm : 0) * a.pitch;
-        const float* colc = I + (size_t)xcol * a.pitch;
-        const float* colp = I + (size_t)(okp ? xp : W - 1) * a.pitch;
+        float em[K + 2], ec[K + 2], ep[K + 2];
+        load_col_halo<K>(I, xb - 1, W, pitch, H, y0, lane, zb, em);
+        load_col_halo<K>(I, xb, W, pitch, H, y0, lane, zb, ec);
+        const int xe = min(xb + GRAD_CS, W);
+        for (int xcol = xb; xcol < xe; ++xcol) {
+            load_col_halo<K>(I, xcol + 1, W, pitch, H, y0, lane, zb, ep);
+            float pyy[K], pxx[K], pyx[K];
+            float gi[2 * K];
 #pragma unroll
-        for (int j = 0; j < K + 2; ++j) {
-            int y = y0 - 1 + j;
-            bool oky = (y >= 0) && (y < H);
-            int yc = y < 0 ? 0 : (y >= H ? H - 1 : y);
-            float vm = colm[yc], vc = colc[yc], vp = colp[yc];
-            if (zb) {
-                if (!oky) { vm = 0.f; vc = 0.f; vp = 0.f; }
-                if (!okm) vm = 0.f;
-                if (!okp) vp = 0.f;
+            for (int j = 0; j < K; ++j) {
+                // centre row index in the halo arrays is j+1
+                const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
+                float gy = s0 * (0.5f * (em[j + 2] - em[j])) + s1 * (0.5f * (ec[j + 2] - ec[j])) + s0 * (0.5f * (ep[j + 2] - ep[j]));
+                float gx = s0 * (0.5f * (ep[j] - em[j])) + s1 * (0.5f * (ep[j + 1] - em[j + 1])) + s0 * (0.5f * (ep[j + 2] - em[j + 2]));
+                gi[2 * j] = gy; gi[2 * j + 1] = gx;
+                pyy[j] = gy * gy; pxx[j] = gx * gx; pyx[j] = gy * gx;
             }
-            cm[j] = vm; cc[j] = vc; cp[j] = vp;
-        }
-        float pyy[K], pxx[K], pyx[K];
-        float* oIy = fb + a.o_iy + (size_t)xcol * a.pitch;
-        float* oIx = fb + a.o_ix + (size_t)xcol * a.pitch;
+            // interleaved gradients: lane owns 2K consecutive floats starting at 2*y0
+            {
+                float* og = fb + a.o_grad + (size_t)xcol * (2 * pitch);
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            // centre row index in the local arrays is j+1
-            const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
-            float gy = s0 * (0.5f * (cm[j + 2] - cm[j])) + s1 * (0.5f * (cc[j + 2] - cc[j])) + s0 * (0.5f * (cp[j + 2] - cp[j]));
-            float gx = s0 * (0.5f * (cp[j] - cm[j])) + s1 * (0.5f * (cp[j + 1] - cm[j + 1])) + s0 * (0.5f * (cp[j + 2] - cm[j + 2]));
-            if (y0 + j < H) { oIy[y0 + j] = gy; oIx[y0 + j] = gx; }
-            pyy[j] = gy * gy; pxx[j] = gx * gx; pyx[j] = gy * gx;
-        }
-        warp_iir_line<K>(pyy, H, lane, c, false);
-        warp_iir_line<K>(pxx, H, lane, c, false);
-        warp_iir_line<K>(pyx, H, lane, c, false);
-        float* o0 = fb + a.o_out0 + (size_t)xcol * a.pitch;
-        float* o1 = o0 + a.plane_elems;
-        float* o2 = o1 + a.plane_elems;
+                for (int v = 0; v < K / 2; ++v) {
+                    const int y = y0 + 2 * v;
+                    if (y < pitch) {
+                        float4 t;
+                        t.x = y < H ? gi[4 * v] : 0.f; t.y = y < H ? gi[4 * v + 1] : 0.f;
+                        t.z = y + 1 < H ? gi[4 * v + 2] : 0.f; t.w = y + 1 < H ? gi[4 * v + 3] : 0.f;
+                        *reinterpret_cast<float4*>(og + 2 * y) = t;
+                    }
+                }
+            }
+            warp_iir_line<K>(pyy, H, lane, c, false);
+            warp_iir_line<K>(pxx, H, lane, c, false);
+            warp_iir_line<K>(pyx, H, lane, c, false);
+            float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
+            store_col<K>(o0, y0, pitch, H, pyy);
+            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pxx);
+            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pyx);
 #pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (y0 + j < H) { o0[y0 + j] = pyy[j]; o1[y0 + j] = pxx[j]; o2[y0 + j] = pyx[j]; }
+            for (int j = 0; j < K + 2; ++j) { em[j] = ec[j]; ec[j] = ep[j]; }
+        }
     }
 }
 
 // ----------------------------------------------------------------------------------------------
 // dim-2 kernel (along x).  CTA = LR rows x NC chunks of KRt elements; thread (row, chunk) keeps its chunk in registers.
+// MODE 0: plain output (v * scale [* inv_n])       -- blur chain, and parity download of the smoothed planes
+// MODE 1: exclusive prefix sum along x of v * scale, accumulated in Float64, W+1 columns (column 0 stays 0)
 // ----------------------------------------------------------------------------------------------
 struct RowArgs {
     FrameSet fs;
@@ -259,11 +347,72 @@ struct RowArgs {
     const float* inv_n;                 // NA mode: 1/nx[x]
 };
 
-template <int KRt, int LR>
+__device__ __forceinline__ const float* row_ptr(const float* base, int pitch4, int k) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (long long)pitch4 * k);
+}
+__device__ __forceinline__ float* row_ptr(float* base, int pitch4, int k) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + (long long)pitch4 * k);
+}
+
+// FULLC: the chunk is complete and does not hold the last element of the line => no per-element predicates
+template <int KRt, bool FULLC>
+__device__ __forceinline__ void rows_fwd_local(const float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float& s0, float& s1, float& s2) {
+#pragma unroll
+    for (int j = 0; j < KRt; ++j)
+        if (FULLC || x0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+}
+template <int KRt, bool FULLC>
+__device__ __forceinline__ void rows_fwd_true(float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float& s0, float& s1, float& s2) {
+#pragma unroll
+    for (int j = 0; j < KRt; ++j)
+        if (FULLC || x0 + j < n) {
+            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+            x[j] = u;
+            s2 = s1; s1 = s0; s0 = u;
+        }
+}
+template <int KRt, bool FULLC>
+__device__ __forceinline__ void rows_bwd_local(const float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float vr0, float vr1, float vr2,
+                                               float& t0, float& t1, float& t2) {
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        if (FULLC) { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+        else {
+            const int idx = x0 + j;
+            if (idx < n) {
+                if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
+                else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+            }
+        }
+    }
+}
+template <int KRt, bool FULLC>
+__device__ __forceinline__ void rows_bwd_true(float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float sc, float vr0, float vr1, float vr2,
+                                              float t0, float t1, float t2) {
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        if (FULLC) { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; x[j] = v * sc; }
+        else {
+            const int idx = x0 + j;
+            if (idx < n) {
+                float v;
+                if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
+                else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+                x[j] = v * sc;
+            } else x[j] = 0.f;
+        }
+    }
+}
+
+template <int KRt, int LR, int MODE>
 __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     constexpr int NCMAX = 32;
     __shared__ float sF[NCMAX][3][LR];
     __shared__ float sB[NCMAX][3][LR];
+    __shared__ double sP[MODE == 1 ? NCMAX : 1][LR];
     const int rl = threadIdx.x % LR;
     const int ch = threadIdx.x / LR;
     const int NC = (a.W + KRt - 1) / KRt;
@@ -271,31 +420,40 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     const int plane = blockIdx.y;
     const int f = blockIdx.z;
     const bool rowok = r < a.H;
-    const bool act = rowok && ch < NC;
     float* fb = a.fs.frame(a.f0 + f);
     const float* in = fb + a.o_in0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     float* out = fb + a.o_out0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     const int x0 = ch * KRt;
     const int n = a.W;
+    const int pitch4 = a.pitch * 4;
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
+    const bool fullc = x0 + KRt < n;  // uniform per warp when LR == 32 (and per half-warp when LR == 16)
 
     float x[KRt];
+    {
+        const float* p = row_ptr(in, pitch4, x0);
+        if (fullc) {
 #pragma unroll
-    for (int j = 0; j < KRt; ++j) x[j] = (act && x0 + j < n) ? __ldg(in + (size_t)(x0 + j) * a.pitch) : 0.f;
+            for (int j = 0; j < KRt; ++j) x[j] = __ldg(row_ptr(p, pitch4, j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < KRt; ++j) x[j] = (x0 + j < n) ? __ldg(row_ptr(p, pitch4, j)) : 0.f;
+        }
+        if (!rowok) {
+#pragma unroll
+            for (int j = 0; j < KRt; ++j) x[j] = 0.f;
+        }
+    }
     const bool zb = a.zero_border != 0;
     const float iminus = (zb || !rowok) ? 0.f : __ldg(in);
-    const float iplus = (zb || !rowok) ? 0.f : __ldg(in + (size_t)(n - 1) * a.pitch);
+    const float iplus = (zb || !rowok) ? 0.f : __ldg(row_ptr(in, pitch4, n - 1));
     const float um = iminus * c.inv1ma;
 
     // forward phase 1
     float s0 = ch == 0 ? um : 0.f, s1 = s0, s2 = s0;
-#pragma unroll
-    for (int j = 0; j < KRt; ++j)
-        if (x0 + j < n) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            s2 = s1; s1 = s0; s0 = u;
-        }
-    if (ch < NC) { sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2; }
+    if (fullc) rows_fwd_local<KRt, true>(x, x0, n, a1, a2, a3, s0, s1, s2);
+    else rows_fwd_local<KRt, false>(x, x0, n, a1, a2, a3, s0, s1, s2);
+    sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2;
     __syncthreads();
     if (ch == 0) {  // sequential carries over the chunks of this row
         float q0 = sF[0][0][rl], q1 = sF[0][1][rl], q2 = sF[0][2][rl];
@@ -308,14 +466,9 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     }
     __syncthreads();
     if (ch == 0) { s0 = um; s1 = um; s2 = um; }
-    else if (ch < NC) { s0 = sF[ch][0][rl]; s1 = sF[ch][1][rl]; s2 = sF[ch][2][rl]; }
-#pragma unroll
-    for (int j = 0; j < KRt; ++j)
-        if (x0 + j < n) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            x[j] = u;
-            s2 = s1; s1 = s0; s0 = u;
-        }
+    else { s0 = sF[ch][0][rl]; s1 = sF[ch][1][rl]; s2 = sF[ch][2][rl]; }
+    if (fullc) rows_fwd_true<KRt, true>(x, x0, n, a1, a2, a3, s0, s1, s2);
+    else rows_fwd_true<KRt, false>(x, x0, n, a1, a2, a3, s0, s1, s2);
     // right boundary: only the last chunk holds (u[n], u[n-1], u[n-2])
     const float up = iplus * c.inv1ma, vp = up * c.inv1ma;
     const float d0 = s0 - up, d1 = s1 - up, d2 = s2 - up;
@@ -325,15 +478,9 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
 
     // backward phase 1
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-    for (int j = KRt - 1; j >= 0; --j) {
-        const int idx = x0 + j;
-        if (idx < n) {
-            if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
-            else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-        }
-    }
-    if (ch < NC) { sB[ch][0][rl] = t0; sB[ch][1][rl] = t1; sB[ch][2][rl] = t2; }
+    if (fullc) rows_bwd_local<KRt, true>(x, x0, n, a1, a2, a3, vr0, vr1, vr2, t0, t1, t2);
+    else rows_bwd_local<KRt, false>(x, x0, n, a1, a2, a3, vr0, vr1, vr2, t0, t1, t2);
+    sB[ch][0][rl] = t0; sB[ch][1][rl] = t1; sB[ch][2][rl] = t2;
     __syncthreads();
     if (ch == 0) {
         float q0 = sB[NC - 1][0][rl], q1 = sB[NC - 1][1][rl], q2 = sB[NC - 1][2][rl];
@@ -347,17 +494,41 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     __syncthreads();
     if (ch < NC - 1) { t0 = sB[ch][0][rl]; t1 = sB[ch][1][rl]; t2 = sB[ch][2][rl]; }
     else { t0 = 0.f; t1 = 0.f; t2 = 0.f; }
-    const float sc = c.scale;
+    if (fullc) rows_bwd_true<KRt, true>(x, x0, n, a1, a2, a3, c.scale, vr0, vr1, vr2, t0, t1, t2);
+    else rows_bwd_true<KRt, false>(x, x0, n, a1, a2, a3, c.scale, vr0, vr1, vr2, t0, t1, t2);
+
+    if (MODE == 0) {
+        float* q = row_ptr(out, pitch4, x0);
+        if (a.inv_n) {
 #pragma unroll
-    for (int j = KRt - 1; j >= 0; --j) {
-        const int idx = x0 + j;
-        if (idx < n) {
-            float v;
-            if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
-            else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-            float o = v * sc;
-            if (a.inv_n) o *= __ldg(a.inv_n + idx);
-            if (act) out[(size_t)idx * a.pitch] = o;
+            for (int j = 0; j < KRt; ++j)
+                if (fullc || x0 + j < n) x[j] *= __ldg(a.inv_n + x0 + j);
+        }
+        if (rowok) {
+#pragma unroll
+            for (int j = 0; j < KRt; ++j)
+                if (fullc || x0 + j < n) *row_ptr(q, pitch4, j) = x[j];
+        }
+    } else {
+        // exclusive prefix along x in Float64: out[., j+1] = sum_{x' <= j} v[x']
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < KRt; ++j) acc += (double)x[j];  // elements past the end of the line are 0
+        sP[ch][rl] = acc;
+        __syncthreads();
+        if (ch == 0) {
+            double run = 0.0;
+            for (int k = 0; k < NC; ++k) { double t = sP[k][rl]; sP[k][rl] = run; run += t; }
+        }
+        __syncthreads();
+        acc = sP[ch][rl];
+        if (rowok) {
+            float* q = row_ptr(out, pitch4, x0 + 1);
+#pragma unroll
+            for (int j = 0; j < KRt; ++j) {
+                acc += (double)x[j];
+                if (fullc || x0 + j < n) *row_ptr(q, pitch4, j) = (float)acc;
+            }
         }
     }
 }
@@ -399,13 +570,20 @@ int pick_K(int H) {
 
 template <int K>
 static void launch_cols(cudaStream_t s, bool grad, const ColArgs& a, const IirDev& c) {
-    const int total_warps = a.n_frames * a.W;
-    const int wpb = 8;
-    int blocks = (total_warps + wpb - 1) / wpb;
     const int maxb = 148 * 16;
-    if (blocks > maxb) blocks = maxb;
-    if (grad) k_cols_grad<K><<<blocks, wpb * 32, 0, s>>>(a, c);
-    else      k_cols_blur<K><<<blocks, wpb * 32, 0, s>>>(a, c);
+    if (grad) {
+        const int total_warps = a.n_frames * ((a.W + GRAD_CS - 1) / GRAD_CS);
+        const int wpb = 4;
+        int blocks = (total_warps + wpb - 1) / wpb;
+        if (blocks > maxb) blocks = maxb;
+        k_cols_grad<K><<<blocks, wpb * 32, 0, s>>>(a, c);
+    } else {
+        const int total_warps = a.n_frames * a.W;
+        const int wpb = 8;
+        int blocks = (total_warps + wpb - 1) / wpb;
+        if (blocks > maxb) blocks = maxb;
+        k_cols_blur<K><<<blocks, wpb * 32, 0, s>>>(a, c);
+    }
 }
 
 static void dispatch_cols(cudaStream_t s, int K, bool grad, const ColArgs& a, const IirDev& c) {
@@ -421,17 +599,21 @@ static void dispatch_cols(cudaStream_t s, int K, bool grad, const ColArgs& a, co
     }
 }
 
-static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c) {
+static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int mode) {
     if (a.W <= 32 * 40) {
         dim3 grid((a.H + 31) / 32, a.nplanes, a.n_frames);
         const int NC = (a.W + 39) / 40;
-        k_rows<40, 32><<<grid, 32 * NC, 0, s>>>(a, c);
+        if (mode == 0) k_rows<40, 32, 0><<<grid, 32 * NC, 0, s>>>(a, c);
+        else k_rows<40, 32, 1><<<grid, 32 * NC, 0, s>>>(a, c);
     } else {
         dim3 grid((a.H + 15) / 16, a.nplanes, a.n_frames);
         const int NC = (a.W + 63) / 64;
-        k_rows<64, 16><<<grid, 16 * NC, 0, s>>>(a, c);
+        if (mode == 0) k_rows<64, 16, 0><<<grid, 16 * NC, 0, s>>>(a, c);
+        else k_rows<64, 16, 1><<<grid, 16 * NC, 0, s>>>(a, c);
     }
 }
+
+static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
 
 int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx, const Hook* hk) {
@@ -443,9 +625,8 @@ int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrG
         const LevelGeom& L = g.lv[l];
         const LevelGeom& N = g.lv[l + 1];
         const int K = pick_K(L.H);
-        const int krow = (L.W <= 32 * 40) ? 40 : 64;
         IirDev c;
-        iir_dev(sigma, K, krow, &c);
+        iir_dev(sigma, K, krow_of(L.W), &c);
         ColArgs ca{};
         ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
         ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
@@ -457,34 +638,48 @@ int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrG
         ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
         ra.inv_n = ctor ? inv_nx[l] : nullptr;
         snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
-        dispatch_rows(s, ra, c);
+        dispatch_rows(s, ra, c, 0);
         snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
         dim3 grid((N.H + 127) / 128, N.W, n_frames);
         k_resize<<<grid, 128, 0, s>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
         launches += 3;
     }
-    // 2. gradients + smoothed structure-tensor planes, every level
+    // 2. gradients + smoothed structure-tensor planes (stored as row prefix sums), every level
     for (int l = 0; l < g.nl; ++l) {
         const LevelGeom& L = g.lv[l];
         const int K = pick_K(L.H);
-        const int krow = (L.W <= 32 * 40) ? 40 : 64;
         IirDev c;
-        iir_dev(4.0, K, krow, &c);  // lucas_kanade.jl:112
+        iir_dev(4.0, K, krow_of(L.W), &c);  // lucas_kanade.jl:112
         ColArgs ca{};
         ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
         ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
-        ca.o_iy = plane_off(L, DP_IY); ca.o_ix = plane_off(L, DP_IX); ca.plane_elems = L.plane_elems; ca.inv_n = nullptr;
+        ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems; ca.inv_n = nullptr;
         snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
         dispatch_cols(s, K, true, ca, c);
         RowArgs ra{};
         ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
-        ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_SYY); ra.plane_elems = L.plane_elems;
+        ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_RYY); ra.plane_elems = L.plane_elems;
         ra.inv_n = nullptr;
         snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
-        dispatch_rows(s, ra, c);
+        dispatch_rows(s, ra, c, 1);
         launches += 2;
     }
     return launches;
+}
+
+// parity access: smoothed product plane `which` (0 yy, 1 xx, 2 yx) of one level, recomputed from the y-filtered
+// scratch plane into DP_TMP (the pyramid itself only keeps the row-prefix form)
+int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk) {
+    const LevelGeom& L = g.lv[level];
+    IirDev c;
+    iir_dev(4.0, pick_K(L.H), krow_of(L.W), &c);
+    RowArgs ra{};
+    ra.fs = fs; ra.f0 = f0; ra.n_frames = 1; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
+    ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0 + which); ra.o_out0 = plane_off(L, DP_TMP); ra.plane_elems = L.plane_elems;
+    ra.inv_n = nullptr;
+    mark(hk, "k_rows_plain");
+    dispatch_rows(s, ra, c, 0);
+    return 1;
 }
 
 }  // namespace sk
