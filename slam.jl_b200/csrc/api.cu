@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -169,6 +170,9 @@ struct HostBuf {
 struct slamklt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the pipelined batch step
+    cudaStream_t d2h_stream = nullptr;   // D2H of the pipelined batch step
+    std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     unsigned long long* d_counters = nullptr;
@@ -304,6 +308,8 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     slamklt_ctx* c = new slamklt_ctx();
     c->device = device;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
@@ -324,6 +330,9 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_counters);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (auto e : c->pipe_ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->d2h_stream);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -897,13 +906,90 @@ int slamklt_batch_rotate(slamklt_ctx* c, slamklt_batch* b) {
     return 0;
 }
 
+// Whole step through host buffers.  The batch is cut into chunks of frames; the H2D copy of chunk k+1 (copy stream)
+// overlaps the pyramid build + tracking of chunk k (compute stream), and the D2H of chunk k's results overlaps chunk k+1.
 int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
                        const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
-    int r;
-    if ((r = slamklt_batch_upload(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts))) return r;
-    if ((r = slamklt_batch_build(c, b, sigma, mode))) return r;
-    if ((r = slamklt_batch_track(c, b, p))) return r;
-    if ((r = slamklt_batch_download(c, b, out_pts, status))) return r;
+    if (!c || !b || !imgs) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (ld < b->g.H0) return fail(SLAMKLT_E_INVALID, "ld < H");
+    if (n_pts < 0 || n_pts > b->max_pts) return fail(SLAMKLT_E_INVALID, "n_pts %d outside [0,%d]", n_pts, b->max_pts);
+    if (n_pts > 0 && (!pts || !out_pts || !status)) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
+    int r = check_lk(p, b->g.nl, b->g.nl);
+    if (r) return r;
+    if (!b->primed) return fail(SLAMKLT_E_INVALID, "batch slot 0 was never built (call slamklt_batch_prime)");
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
+        const size_t es = dtype_size(dtype), fbytes = (size_t)H * W * es;
+        if ((r = b->staging.ensure((size_t)nf * fbytes))) return r;
+        // more chunks hide more of the copy but run the kernels on smaller grids: 8 for 8-byte pixels, fewer for light copies
+        const int want = dtype == SLAMKLT_F64 ? 8 : (dtype == SLAMKLT_F32 ? 4 : 2);
+        const int chunk = nf >= 2 * want ? (nf + want - 1) / want : nf;
+        const int nchunks = (nf + chunk - 1) / chunk;
+        while ((int)c->pipe_ev.size() < 2 * nchunks + 1) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->pipe_ev.push_back(e);
+        }
+        // order the copy stream after everything already queued on the compute stream (staging reuse)
+        CK(cudaEventRecord(c->pipe_ev[2 * nchunks], c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[2 * nchunks], 0));
+        if (n_pts > 0) {
+            CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)nf * n_pts * 16, cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d += (uint64_t)nf * n_pts * 16;
+        }
+        b->n_pts = n_pts; b->up_dtype = dtype; b->up_ld = ld;
+        const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
+        LKArgs a{};
+        a.A = fs_of(b); a.B = fs_of(b);
+        fill_lk_levels(b->g, &a);
+        a.mode = 1;
+        a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+        a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+        a.counters = c->d_counters;
+        a.n_per_frame = n_pts;
+        // 1. queue every H2D chunk on the copy stream
+        for (int k = 0; k < nchunks; ++k) {
+            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+            char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
+            if (contiguous) {
+                CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
+            } else {
+                for (int f = f0; f < f1; ++f)
+                    CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
+                                         (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            c->h2d += (uint64_t)n * fbytes;
+            CK(cudaEventRecord(c->pipe_ev[2 * k], c->copy_stream));
+        }
+        // 2. compute chunk k as soon as its frames have landed; results leave on a third stream
+        for (int k = 0; k < nchunks; ++k) {
+            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+            const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
+            CK(cudaStreamWaitEvent(c->stream, c->pipe_ev[2 * k], 0));
+            if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr))) return r;
+            if (n_pts > 0) {
+                a.offA = f0; a.offB = f0 + 1; a.n_frames = n;
+                a.pts = (const double*)b->pts.p + (size_t)f0 * n_pts * 2;
+                a.out_pts = (double*)b->outp.p + (size_t)f0 * n_pts * 2;
+                a.status = (uint8_t*)b->status.p + (size_t)f0 * n_pts;
+                c->launches += launch_lk(c->stream, a, c->hk());
+                CKL();
+                prof_end(c);
+                CK(cudaEventRecord(c->pipe_ev[2 * k + 1], c->stream));
+                CK(cudaStreamWaitEvent(c->d2h_stream, c->pipe_ev[2 * k + 1], 0));
+                CK(cudaMemcpyAsync(out_pts + (size_t)f0 * n_pts * 2, a.out_pts, (size_t)n * n_pts * 16, cudaMemcpyDeviceToHost, c->d2h_stream));
+                CK(cudaMemcpyAsync(status + (size_t)f0 * n_pts, a.status, (size_t)n * n_pts, cudaMemcpyDeviceToHost, c->d2h_stream));
+                c->d2h += (uint64_t)n * n_pts * 17;
+            }
+        }
+        CK(cudaStreamSynchronize(c->d2h_stream));
+        CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
     return slamklt_batch_rotate(c, b);
 }
 

@@ -1,0 +1,101 @@
+"""GPU tests of the batched stream API (configs 2/4/5): the batch path must give exactly what the single-pair entry
+points give (same kernels), which in turn are parity-checked against the oracle in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import slamklt
+from slamklt import synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_seq():
+    fr, aff = synth.make_sequence(909, 9, H=120, W=200)
+    return fr, synth.to_f64(fr), aff
+
+
+@pytest.mark.parametrize("dtype", ["f64", "u8"])
+def test_batch_step_matches_single_calls_and_oracle(ctx, small_seq, dtype):
+    fr, f64, aff = small_seq
+    H, W, L, NF, NP = 120, 200, 2, 4, 150
+    alg = slamklt.LucasKanade(pyramid_levels=L, window_size=9)
+    batch = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+    src = f64 if dtype == "f64" else fr
+    batch.prime(src[0], mode=slamklt.MODE_UPDATE)
+    pts = np.stack([synth.random_keypoints(50 + i, NP, H, W, border=2.0) for i in range(8)])
+    singles = [slamklt.LKPyramid(ctx, f64[0], L)]
+    singles[0].update(f64[0])
+    for step in range(2):  # two consecutive steps: the second relies on slamklt_batch_rotate carrying the last frame
+        frames = src[1 + step * NF: 1 + (step + 1) * NF]
+        p = pts[step * NF:(step + 1) * NF]
+        out, st = batch.step(slamklt.StreamBatch.pack_frames(frames), p, alg, max_distance=1.0)
+        for i in range(NF):
+            t = step * NF + i
+            cur = slamklt.LKPyramid(ctx, f64[t + 1], L)
+            cur.update(f64[t + 1])
+            singles.append(cur)
+            ref_pts, ref_st, ref_fst = slamklt.fb_tracking(singles[t], cur, p[i], window_size=9, pyramid_levels=L, max_distance=1.0)
+            assert np.array_equal(st[i] & 1, ref_st.astype(np.uint8))
+            assert np.array_equal((st[i] >> 1) & 1, ref_fst.astype(np.uint8))
+            assert np.array_equal(out[i][ref_fst], ref_pts[ref_fst])  # same kernels => bit-identical
+            assert np.all(np.isnan(out[i][~ref_fst]))
+        # slot planes equal the single pyramids (slot 0 now holds the last frame of this step)
+        a = batch.slot(0).plane(1, "layer")
+        assert np.array_equal(a, singles[(step + 1) * NF].plane(1, "layer"))
+    # and against the oracle for the very last pair
+    o0 = O.LKPyramid(f64[7], L); o0.update(f64[7]); o1 = O.LKPyramid(f64[8], L); o1.update(f64[8])
+    po, so, fo = O.fb_tracking(o0, o1, pts[7], window_size=9, pyramid_levels=L, max_distance=1.0)
+    assert np.mean(so == (st[3] & 1).astype(bool)) >= 0.99
+    both = so & (st[3] & 1).astype(bool)
+    assert np.mean(np.abs(po[both] - out[3][both]).max(axis=1) < 0.01) >= 0.99
+    batch.close()
+
+
+def test_batch_phases_equal_step(ctx, small_seq):
+    fr, f64, aff = small_seq
+    H, W, L, NF, NP = 120, 200, 2, 4, 100
+    alg = slamklt.LucasKanade(pyramid_levels=L)
+    pts = np.stack([synth.random_keypoints(80 + i, NP, H, W, border=4.0) for i in range(NF)])
+    packed = slamklt.StreamBatch.pack_frames(f64[1:1 + NF])
+    b1 = slamklt.StreamBatch(ctx, H, W, L, NF, NP); b1.prime(f64[0])
+    b2 = slamklt.StreamBatch(ctx, H, W, L, NF, NP); b2.prime(f64[0])
+    o1, s1 = b1.step(packed, pts, alg)
+    b2.upload(packed, pts); b2.build(); b2.track(alg, 1.0)
+    o2, s2 = b2.download()
+    assert np.array_equal(s1, s2) and np.array_equal(np.nan_to_num(o1), np.nan_to_num(o2))
+    assert ctx.stats()["kernel_launches"] > 0
+    b1.close(); b2.close()
+
+
+def test_batch_detect_matches_single(ctx, small_seq):
+    fr, f64, aff = small_seq
+    H, W, NF = 120, 200, 4
+    e = slamklt.Extractor(300, 8, (4, 6), 35)
+    batch = slamklt.StreamBatch(ctx, H, W, 2, NF, 10)
+    cur = np.stack([synth.random_keypoints(5 + i, 20, H, W) for i in range(NF)])
+    for src in (f64, fr):
+        batch.upload(slamklt.StreamBatch.pack_frames(src[:NF]), np.zeros((NF, 1, 2)) + 5)
+        got = batch.detect(e, cur)
+        for i in range(NF):
+            assert np.array_equal(got[i], slamklt.detect(ctx, e, f64[i], cur[i]))
+            assert np.array_equal(got[i], O.detect(O.Extractor(300, 8, (4, 6), 35), f64[i], cur[i]))
+    batch.close()
+
+
+def test_pyramid_copy_clone_swap(ctx, small_seq):
+    _, f64, _ = small_seq
+    a = slamklt.LKPyramid(ctx, f64[0], 2)
+    b = slamklt.LKPyramid(ctx, f64[1], 2)
+    la, lb = a.plane(2, "layer"), b.plane(2, "layer")
+    c = a.deepcopy()                      # SLAM.jl:216-219
+    assert np.array_equal(c.plane(2, "layer"), la) and c.has_gradients()
+    a.swap(b)                             # front_end.jl:459-461 as a pointer swap
+    assert np.array_equal(a.plane(2, "layer"), lb) and np.array_equal(b.plane(2, "layer"), la)
+    b.copy_from(a)                        # pyramid.jl:28-38
+    assert np.array_equal(b.plane(1, "Ix"), a.plane(1, "Ix"))
+    empty = slamklt.LKPyramid(ctx, None, 2, shape=(120, 200))
+    assert not empty.has_gradients()
+    with pytest.raises(slamklt.SlamKltError):
+        slamklt.fb_tracking(empty, a, np.array([[30.0, 30.0]]))
