@@ -103,8 +103,10 @@ void iir_dev(double sigma, int K, int KRr, IirDev* o) {
         mat3_pow(A, K << j, P);
         for (int i = 0; i < 9; ++i) o->P[j][i] = (float)P[i];
     }
-    mat3_pow(A, KRr, P);
-    for (int i = 0; i < 9; ++i) o->PK[i] = (float)P[i];
+    for (int j = 0; j < 5; ++j) {
+        mat3_pow(A, KRr << j, P);
+        for (int i = 0; i < 9; ++i) o->PR[j][i] = (float)P[i];
+    }
 }
 
 void iir_line_host(double* x, int n, double sigma, double iminus, double iplus) {

@@ -57,7 +57,7 @@ struct IirDev {
     float a1, a2, a3, scale, inv1ma;  // inv1ma = 1/(1 - (a1+a2+a3))
     float M[9];                       // Triggs-Sdika right-boundary matrix, row-major
     float P[5][9];                    // A^(K*2^j), j = 0..4, for the warp scan of the dim-1 kernel
-    float PK[9];                      // A^KR for the chunk carries of the dim-2 kernel
+    float PR[5][9];                   // A^(KR*2^j), j = 0..4, for the chunk-carry scan of the dim-2 kernel
 };
 
 struct LKLevel {

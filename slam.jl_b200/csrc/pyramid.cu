@@ -120,82 +120,125 @@ __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, 
     q2 = fmaf(P[6], r0, fmaf(P[7], r1, fmaf(P[8], r2, q2)));
 }
 
-template <int K>
-__device__ __forceinline__ void warp_iir_line(float (&x)[K], const int n, const int lane, const IirDev& c, const bool zero_border) {
+// NL independent lines are filtered together so that their dependent FMA / shuffle chains interleave (ILP = NL).
+template <int K, int NL>
+__device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, const int lane, const IirDev& c, const bool zero_border) {
     const int y0 = lane * K;
     const int nv = min(max(n - y0, 0), K);  // valid elements of this lane
     const int jl = n - 1 - y0;              // slot of the last element of the line, if it lives in this lane
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
     const int ln = (n - 1) / K;
-    float first = __shfl_sync(FULL, x[0], 0);
-    float lastv = 0.f;
+    float um[NL], iplus[NL];
 #pragma unroll
-    for (int j = 0; j < K; ++j)
-        if (j == jl) lastv = x[j];
-    lastv = __shfl_sync(FULL, lastv, ln);
-    const float iminus = zero_border ? 0.f : first, iplus = zero_border ? 0.f : lastv;
-    const float um = iminus * c.inv1ma;
-
+    for (int l = 0; l < NL; ++l) {
+        float first = __shfl_sync(FULL, x[l][0], 0);
+        float lastv = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j == jl) lastv = x[l][j];
+        lastv = __shfl_sync(FULL, lastv, ln);
+        um[l] = (zero_border ? 0.f : first) * c.inv1ma;
+        iplus[l] = zero_border ? 0.f : lastv;
+    }
     // forward, phase 1: chunk-local pass (lane 0 starts from the true left boundary state)
-    float s0 = lane == 0 ? um : 0.f, s1 = s0, s2 = s0;
+    float s0[NL], s1[NL], s2[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) { s0[l] = lane == 0 ? um[l] : 0.f; s1[l] = s0[l]; s2[l] = s0[l]; }
 #pragma unroll
     for (int j = 0; j < K; ++j)
         if (j < nv) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            s2 = s1; s1 = s0; s0 = u;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+                s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
+            }
         }
     // phase 2: inclusive scan of the chunk states, q_l += A^(K d) q_{l-d}
-    float q0 = s0, q1 = s1, q2 = s2;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int d = 1 << j;
-        float r0 = __shfl_up_sync(FULL, q0, d), r1 = __shfl_up_sync(FULL, q1, d), r2 = __shfl_up_sync(FULL, q2, d);
-        if (lane >= d) mat3_acc(c.P[j], r0, r1, r2, q0, q1, q2);
+        float r0[NL], r1[NL], r2[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            r0[l] = __shfl_up_sync(FULL, s0[l], d); r1[l] = __shfl_up_sync(FULL, s1[l], d); r2[l] = __shfl_up_sync(FULL, s2[l], d);
+        }
+        if (lane >= d) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) mat3_acc(c.P[j], r0[l], r1[l], r2[l], s0[l], s1[l], s2[l]);
+        }
     }
-    s0 = __shfl_up_sync(FULL, q0, 1); s1 = __shfl_up_sync(FULL, q1, 1); s2 = __shfl_up_sync(FULL, q2, 1);
-    if (lane == 0) { s0 = um; s1 = um; s2 = um; }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        float i0 = __shfl_up_sync(FULL, s0[l], 1), i1 = __shfl_up_sync(FULL, s1[l], 1), i2 = __shfl_up_sync(FULL, s2[l], 1);
+        if (lane == 0) { i0 = um[l]; i1 = um[l]; i2 = um[l]; }
+        s0[l] = i0; s1[l] = i1; s2[l] = i2;
+    }
     // phase 3: true pass
 #pragma unroll
     for (int j = 0; j < K; ++j)
         if (j < nv) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            x[j] = u;
-            s2 = s1; s1 = s0; s0 = u;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+                x[l][j] = u;
+                s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
+            }
         }
     // right boundary (Triggs & Sdika eq. 14): lane ln holds (u[n], u[n-1], u[n-2])
-    const float e0 = __shfl_sync(FULL, s0, ln), e1 = __shfl_sync(FULL, s1, ln), e2 = __shfl_sync(FULL, s2, ln);
-    const float up = iplus * c.inv1ma, vp = up * c.inv1ma;
-    const float d0 = e0 - up, d1 = e1 - up, d2 = e2 - up;
-    const float vr0 = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
-    const float vr1 = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
-    const float vr2 = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
-
+    float vr0[NL], vr1[NL], vr2[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const float e0 = __shfl_sync(FULL, s0[l], ln), e1 = __shfl_sync(FULL, s1[l], ln), e2 = __shfl_sync(FULL, s2[l], ln);
+        const float up = iplus[l] * c.inv1ma, vp = up * c.inv1ma;
+        const float d0 = e0 - up, d1 = e1 - up, d2 = e2 - up;
+        vr0[l] = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
+        vr1[l] = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
+        vr2[l] = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
+    }
     // backward, phase 1
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    float t0[NL], t1[NL], t2[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) { t0[l] = 0.f; t1[l] = 0.f; t2[l] = 0.f; }
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
         if (j < nv) {
-            if (j == jl) { t0 = vr0; t1 = vr1; t2 = vr2; }
-            else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                if (j == jl) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
+                else { float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l]; t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
+            }
         }
     }
-    q0 = t0; q1 = t1; q2 = t2;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
         const int d = 1 << j;
-        float r0 = __shfl_down_sync(FULL, q0, d), r1 = __shfl_down_sync(FULL, q1, d), r2 = __shfl_down_sync(FULL, q2, d);
-        if (lane + d < 32) mat3_acc(c.P[j], r0, r1, r2, q0, q1, q2);
+        float r0[NL], r1[NL], r2[NL];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            r0[l] = __shfl_down_sync(FULL, t0[l], d); r1[l] = __shfl_down_sync(FULL, t1[l], d); r2[l] = __shfl_down_sync(FULL, t2[l], d);
+        }
+        if (lane + d < 32) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) mat3_acc(c.P[j], r0[l], r1[l], r2[l], t0[l], t1[l], t2[l]);
+        }
     }
-    t0 = __shfl_down_sync(FULL, q0, 1); t1 = __shfl_down_sync(FULL, q1, 1); t2 = __shfl_down_sync(FULL, q2, 1);
-    if (lane == 31) { t0 = 0.f; t1 = 0.f; t2 = 0.f; }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        float i0 = __shfl_down_sync(FULL, t0[l], 1), i1 = __shfl_down_sync(FULL, t1[l], 1), i2 = __shfl_down_sync(FULL, t2[l], 1);
+        if (lane == 31) { i0 = 0.f; i1 = 0.f; i2 = 0.f; }
+        t0[l] = i0; t1[l] = i1; t2[l] = i2;
+    }
     const float sc = c.scale;
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
         if (j < nv) {
-            float v;
-            if (j == jl) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
-            else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-            x[j] = v * sc;
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                float v;
+                if (j == jl) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
+                else { v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l]; t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
+                x[l][j] = v * sc;
+            }
         }
     }
 }
@@ -228,15 +271,15 @@ __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
         float* fb = a.fs.frame(a.f0 + f);
         const float* in = fb + a.o_in + (size_t)xcol * a.pitch;
         float* out = fb + a.o_out0 + (size_t)xcol * a.pitch;
-        float x[K];
-        load_col<K>(in, y0, a.pitch, x);
-        warp_iir_line<K>(x, a.H, lane, c, a.zero_border != 0);
+        float x[1][K];
+        load_col<K>(in, y0, a.pitch, x[0]);
+        warp_iir_lines<K, 1>(x, a.H, lane, c, a.zero_border != 0);
         if (a.inv_n) {
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                if (y0 + j < a.H) x[j] *= __ldg(a.inv_n + y0 + j);
+                if (y0 + j < a.H) x[0][j] *= __ldg(a.inv_n + y0 + j);
         }
-        store_col<K>(out, y0, a.pitch, a.H, x);
+        store_col<K>(out, y0, a.pitch, a.H, x[0]);
     }
 }
 
@@ -295,7 +338,7 @@ __global__ void __launch_bounds__(128) k_cols_grad(ColArgs a, IirDev c) {
         const int xe = min(xb + GRAD_CS, W);
         for (int xcol = xb; xcol < xe; ++xcol) {
             load_col_halo<K>(I, xcol + 1, W, pitch, H, y0, lane, zb, ep);
-            float pyy[K], pxx[K], pyx[K];
+            float pp[3][K];
             float gi[2 * K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -304,7 +347,7 @@ __global__ void __launch_bounds__(128) k_cols_grad(ColArgs a, IirDev c) {
                 float gy = s0 * (0.5f * (em[j + 2] - em[j])) + s1 * (0.5f * (ec[j + 2] - ec[j])) + s0 * (0.5f * (ep[j + 2] - ep[j]));
                 float gx = s0 * (0.5f * (ep[j] - em[j])) + s1 * (0.5f * (ep[j + 1] - em[j + 1])) + s0 * (0.5f * (ep[j + 2] - em[j + 2]));
                 gi[2 * j] = gy; gi[2 * j + 1] = gx;
-                pyy[j] = gy * gy; pxx[j] = gx * gx; pyx[j] = gy * gx;
+                pp[0][j] = gy * gy; pp[1][j] = gx * gx; pp[2][j] = gy * gx;
             }
             // interleaved gradients: lane owns 2K consecutive floats starting at 2*y0
             {
@@ -320,13 +363,11 @@ __global__ void __launch_bounds__(128) k_cols_grad(ColArgs a, IirDev c) {
                     }
                 }
             }
-            warp_iir_line<K>(pyy, H, lane, c, false);
-            warp_iir_line<K>(pxx, H, lane, c, false);
-            warp_iir_line<K>(pyx, H, lane, c, false);
+            warp_iir_lines<K, 3>(pp, H, lane, c, false);
             float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
-            store_col<K>(o0, y0, pitch, H, pyy);
-            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pxx);
-            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pyx);
+            store_col<K>(o0, y0, pitch, H, pp[0]);
+            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pp[1]);
+            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pp[2]);
 #pragma unroll
             for (int j = 0; j < K + 2; ++j) { em[j] = ec[j]; ec[j] = ep[j]; }
         }
@@ -410,9 +451,11 @@ __device__ __forceinline__ void rows_bwd_true(float (&x)[KRt], int x0, int n, fl
 template <int KRt, int LR, int MODE>
 __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     constexpr int NCMAX = 32;
-    __shared__ float sF[NCMAX][3][LR];
-    __shared__ float sB[NCMAX][3][LR];
-    __shared__ double sP[MODE == 1 ? NCMAX : 1][LR];
+    constexpr int LRP = LR + 1;  // padded: the carry scans read these arrays with lane = chunk
+    __shared__ float sF[NCMAX][3][LRP];
+    __shared__ float sB[NCMAX][3][LRP];
+    __shared__ double sP[MODE == 1 ? NCMAX : 1][LRP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int rl = threadIdx.x % LR;
     const int ch = threadIdx.x / LR;
     const int NC = (a.W + KRt - 1) / KRt;
@@ -455,14 +498,18 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     else rows_fwd_local<KRt, false>(x, x0, n, a1, a2, a3, s0, s1, s2);
     sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2;
     __syncthreads();
-    if (ch == 0) {  // sequential carries over the chunks of this row
-        float q0 = sF[0][0][rl], q1 = sF[0][1][rl], q2 = sF[0][2][rl];
-        for (int k = 1; k < NC; ++k) {
-            float l0 = sF[k][0][rl], l1 = sF[k][1][rl], l2 = sF[k][2][rl];
-            sF[k][0][rl] = q0; sF[k][1][rl] = q1; sF[k][2][rl] = q2;  // incoming state of chunk k
-            mat3_acc(c.PK, q0, q1, q2, l0, l1, l2);
-            q0 = l0; q1 = l1; q2 = l2;
+    // carries: warp `wid` takes rows wid, wid+nwarp, ...; lane = chunk; Kogge-Stone scan q_k += A^(KR d) q_{k-d}
+    for (int rr = wid; rr < LR; rr += nwarp) {
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        if (lane < NC) { q0 = sF[lane][0][rr]; q1 = sF[lane][1][rr]; q2 = sF[lane][2][rr]; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int d = 1 << j;
+            float r0 = __shfl_up_sync(FULL, q0, d), r1 = __shfl_up_sync(FULL, q1, d), r2 = __shfl_up_sync(FULL, q2, d);
+            if (lane >= d) mat3_acc(c.PR[j], r0, r1, r2, q0, q1, q2);
         }
+        q0 = __shfl_up_sync(FULL, q0, 1); q1 = __shfl_up_sync(FULL, q1, 1); q2 = __shfl_up_sync(FULL, q2, 1);
+        if (lane >= 1 && lane < NC) { sF[lane][0][rr] = q0; sF[lane][1][rr] = q1; sF[lane][2][rr] = q2; }  // incoming state of chunk `lane`
     }
     __syncthreads();
     if (ch == 0) { s0 = um; s1 = um; s2 = um; }
@@ -482,14 +529,17 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     else rows_bwd_local<KRt, false>(x, x0, n, a1, a2, a3, vr0, vr1, vr2, t0, t1, t2);
     sB[ch][0][rl] = t0; sB[ch][1][rl] = t1; sB[ch][2][rl] = t2;
     __syncthreads();
-    if (ch == 0) {
-        float q0 = sB[NC - 1][0][rl], q1 = sB[NC - 1][1][rl], q2 = sB[NC - 1][2][rl];
-        for (int k = NC - 2; k >= 0; --k) {
-            float l0 = sB[k][0][rl], l1 = sB[k][1][rl], l2 = sB[k][2][rl];
-            sB[k][0][rl] = q0; sB[k][1][rl] = q1; sB[k][2][rl] = q2;
-            mat3_acc(c.PK, q0, q1, q2, l0, l1, l2);
-            q0 = l0; q1 = l1; q2 = l2;
+    for (int rr = wid; rr < LR; rr += nwarp) {
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        if (lane < NC) { q0 = sB[lane][0][rr]; q1 = sB[lane][1][rr]; q2 = sB[lane][2][rr]; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int d = 1 << j;
+            float r0 = __shfl_down_sync(FULL, q0, d), r1 = __shfl_down_sync(FULL, q1, d), r2 = __shfl_down_sync(FULL, q2, d);
+            if (lane + d < 32) mat3_acc(c.PR[j], r0, r1, r2, q0, q1, q2);
         }
+        q0 = __shfl_down_sync(FULL, q0, 1); q1 = __shfl_down_sync(FULL, q1, 1); q2 = __shfl_down_sync(FULL, q2, 1);
+        if (lane < NC - 1) { sB[lane][0][rr] = q0; sB[lane][1][rr] = q1; sB[lane][2][rr] = q2; }
     }
     __syncthreads();
     if (ch < NC - 1) { t0 = sB[ch][0][rl]; t1 = sB[ch][1][rl]; t2 = sB[ch][2][rl]; }
@@ -516,9 +566,15 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
         for (int j = 0; j < KRt; ++j) acc += (double)x[j];  // elements past the end of the line are 0
         sP[ch][rl] = acc;
         __syncthreads();
-        if (ch == 0) {
-            double run = 0.0;
-            for (int k = 0; k < NC; ++k) { double t = sP[k][rl]; sP[k][rl] = run; run += t; }
+        for (int rr = wid; rr < LR; rr += nwarp) {  // exclusive scan of the chunk totals, lane = chunk
+            double t = lane < NC ? sP[lane][rr] : 0.0;
+            double inc = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += o;
+            }
+            if (lane < NC) sP[lane][rr] = inc - t;
         }
         __syncthreads();
         acc = sP[ch][rl];
