@@ -121,11 +121,13 @@ __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, 
 }
 
 // NL independent lines are filtered together so that their dependent FMA / shuffle chains interleave (ILP = NL).
+// The line is extended to the full 32*K elements with its border value (x[n-1] for replicate, 0 for Fill(0)): the
+// Triggs-Sdika boundary is exactly the constant-extension assumption, so the result on [0, n) is unchanged while
+// every lane becomes a full chunk and no per-element predicate is needed.
 template <int K, int NL>
 __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, const int lane, const IirDev& c, const bool zero_border) {
     const int y0 = lane * K;
-    const int nv = min(max(n - y0, 0), K);  // valid elements of this lane
-    const int jl = n - 1 - y0;              // slot of the last element of the line, if it lives in this lane
+    const int jl = n - 1 - y0;  // slot of the last element of the line, if it lives in this lane
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
     const int ln = (n - 1) / K;
     float um[NL], iplus[NL];
@@ -139,20 +141,22 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
         lastv = __shfl_sync(FULL, lastv, ln);
         um[l] = (zero_border ? 0.f : first) * c.inv1ma;
         iplus[l] = zero_border ? 0.f : lastv;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j > jl) x[l][j] = iplus[l];  // constant extension past the end of the line
     }
     // forward, phase 1: chunk-local pass (lane 0 starts from the true left boundary state)
     float s0[NL], s1[NL], s2[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) { s0[l] = lane == 0 ? um[l] : 0.f; s1[l] = s0[l]; s2[l] = s0[l]; }
 #pragma unroll
-    for (int j = 0; j < K; ++j)
-        if (j < nv) {
+    for (int j = 0; j < K; ++j) {
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
-                s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
-            }
+        for (int l = 0; l < NL; ++l) {
+            float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+            s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
         }
+    }
     // phase 2: inclusive scan of the chunk states, q_l += A^(K d) q_{l-d}
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -175,38 +179,36 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     }
     // phase 3: true pass
 #pragma unroll
-    for (int j = 0; j < K; ++j)
-        if (j < nv) {
+    for (int j = 0; j < K; ++j) {
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
-                x[l][j] = u;
-                s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
-            }
+        for (int l = 0; l < NL; ++l) {
+            float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+            x[l][j] = u;
+            s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
         }
-    // right boundary (Triggs & Sdika eq. 14): lane ln holds (u[n], u[n-1], u[n-2])
+    }
+    // right boundary (Triggs & Sdika eq. 14) at the end of the extended line: lane 31 holds (u[N], u[N-1], u[N-2])
     float vr0[NL], vr1[NL], vr2[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-        const float e0 = __shfl_sync(FULL, s0[l], ln), e1 = __shfl_sync(FULL, s1[l], ln), e2 = __shfl_sync(FULL, s2[l], ln);
+        const float e0 = __shfl_sync(FULL, s0[l], 31), e1 = __shfl_sync(FULL, s1[l], 31), e2 = __shfl_sync(FULL, s2[l], 31);
         const float up = iplus[l] * c.inv1ma, vp = up * c.inv1ma;
         const float d0 = e0 - up, d1 = e1 - up, d2 = e2 - up;
         vr0[l] = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
         vr1[l] = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
         vr2[l] = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
     }
-    // backward, phase 1
+    // backward, phase 1 (the very last element takes the boundary value instead of the recursion)
     float t0[NL], t1[NL], t2[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) { t0[l] = 0.f; t1[l] = 0.f; t2[l] = 0.f; }
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
-        if (j < nv) {
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                if (j == jl) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
-                else { float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l]; t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
-            }
+        for (int l = 0; l < NL; ++l) {
+            float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l];
+            t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v;
+            if (j == K - 1 && lane == 31) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
         }
     }
 #pragma unroll
@@ -231,14 +233,12 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     const float sc = c.scale;
 #pragma unroll
     for (int j = K - 1; j >= 0; --j) {
-        if (j < nv) {
 #pragma unroll
-            for (int l = 0; l < NL; ++l) {
-                float v;
-                if (j == jl) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
-                else { v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l]; t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
-                x[l][j] = v * sc;
-            }
+        for (int l = 0; l < NL; ++l) {
+            float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l];
+            if (j == K - 1 && lane == 31) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
+            else { t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
+            x[l][j] = v * sc;
         }
     }
 }
@@ -395,61 +395,8 @@ __device__ __forceinline__ float* row_ptr(float* base, int pitch4, int k) {
     return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + (long long)pitch4 * k);
 }
 
-// FULLC: the chunk is complete and does not hold the last element of the line => no per-element predicates
-template <int KRt, bool FULLC>
-__device__ __forceinline__ void rows_fwd_local(const float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float& s0, float& s1, float& s2) {
-#pragma unroll
-    for (int j = 0; j < KRt; ++j)
-        if (FULLC || x0 + j < n) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            s2 = s1; s1 = s0; s0 = u;
-        }
-}
-template <int KRt, bool FULLC>
-__device__ __forceinline__ void rows_fwd_true(float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float& s0, float& s1, float& s2) {
-#pragma unroll
-    for (int j = 0; j < KRt; ++j)
-        if (FULLC || x0 + j < n) {
-            float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
-            x[j] = u;
-            s2 = s1; s1 = s0; s0 = u;
-        }
-}
-template <int KRt, bool FULLC>
-__device__ __forceinline__ void rows_bwd_local(const float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float vr0, float vr1, float vr2,
-                                               float& t0, float& t1, float& t2) {
-#pragma unroll
-    for (int j = KRt - 1; j >= 0; --j) {
-        if (FULLC) { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-        else {
-            const int idx = x0 + j;
-            if (idx < n) {
-                if (idx == n - 1) { t0 = vr0; t1 = vr1; t2 = vr2; }
-                else { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-            }
-        }
-    }
-}
-template <int KRt, bool FULLC>
-__device__ __forceinline__ void rows_bwd_true(float (&x)[KRt], int x0, int n, float a1, float a2, float a3, float sc, float vr0, float vr1, float vr2,
-                                              float t0, float t1, float t2) {
-#pragma unroll
-    for (int j = KRt - 1; j >= 0; --j) {
-        if (FULLC) { float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; x[j] = v * sc; }
-        else {
-            const int idx = x0 + j;
-            if (idx < n) {
-                float v;
-                if (idx == n - 1) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
-                else { v = x[j] + a1 * t0 + a2 * t1 + a3 * t2; t2 = t1; t1 = t0; t0 = v; }
-                x[j] = v * sc;
-            } else x[j] = 0.f;
-        }
-    }
-}
-
 template <int KRt, int LR, int MODE>
-__global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
+__global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_rows(RowArgs a, IirDev c) {
     constexpr int NCMAX = 32;
     constexpr int LRP = LR + 1;  // padded: the carry scans read these arrays with lane = chunk
     __shared__ float sF[NCMAX][3][LRP];
@@ -462,40 +409,44 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     const int r = blockIdx.x * LR + rl;
     const int plane = blockIdx.y;
     const int f = blockIdx.z;
-    const bool rowok = r < a.H;
+    const bool chok = ch < NC;  // the block is rounded up to whole warps
+    const bool rowok = r < a.H && chok;
     float* fb = a.fs.frame(a.f0 + f);
     const float* in = fb + a.o_in0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     float* out = fb + a.o_out0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
-    const int x0 = ch * KRt;
+    const int x0 = chok ? ch * KRt : 0;
     const int n = a.W;
     const int pitch4 = a.pitch * 4;
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
-    const bool fullc = x0 + KRt < n;  // uniform per warp when LR == 32 (and per half-warp when LR == 16)
+    const bool zb = a.zero_border != 0;
+    const float iminus = (zb || !rowok) ? 0.f : __ldg(in);
+    const float iplus = (zb || !rowok) ? 0.f : __ldg(row_ptr(in, pitch4, n - 1));
+    const float um = iminus * c.inv1ma;
 
+    // the line is extended to NC*KRt elements with its border value (see warp_iir_lines): every chunk is full
     float x[KRt];
     {
         const float* p = row_ptr(in, pitch4, x0);
-        if (fullc) {
 #pragma unroll
-            for (int j = 0; j < KRt; ++j) x[j] = __ldg(row_ptr(p, pitch4, j));
-        } else {
+        for (int j = 0; j < KRt; ++j) x[j] = __ldg(row_ptr(p, pitch4, min(j, n - 1 - x0)));
+        if (x0 + KRt > n) {
 #pragma unroll
-            for (int j = 0; j < KRt; ++j) x[j] = (x0 + j < n) ? __ldg(row_ptr(p, pitch4, j)) : 0.f;
+            for (int j = 0; j < KRt; ++j)
+                if (x0 + j >= n) x[j] = iplus;
         }
         if (!rowok) {
 #pragma unroll
             for (int j = 0; j < KRt; ++j) x[j] = 0.f;
         }
     }
-    const bool zb = a.zero_border != 0;
-    const float iminus = (zb || !rowok) ? 0.f : __ldg(in);
-    const float iplus = (zb || !rowok) ? 0.f : __ldg(row_ptr(in, pitch4, n - 1));
-    const float um = iminus * c.inv1ma;
 
     // forward phase 1
     float s0 = ch == 0 ? um : 0.f, s1 = s0, s2 = s0;
-    if (fullc) rows_fwd_local<KRt, true>(x, x0, n, a1, a2, a3, s0, s1, s2);
-    else rows_fwd_local<KRt, false>(x, x0, n, a1, a2, a3, s0, s1, s2);
+#pragma unroll
+    for (int j = 0; j < KRt; ++j) {
+        float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+        s2 = s1; s1 = s0; s0 = u;
+    }
     sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2;
     __syncthreads();
     // carries: warp `wid` takes rows wid, wid+nwarp, ...; lane = chunk; Kogge-Stone scan q_k += A^(KR d) q_{k-d}
@@ -514,19 +465,28 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
     __syncthreads();
     if (ch == 0) { s0 = um; s1 = um; s2 = um; }
     else { s0 = sF[ch][0][rl]; s1 = sF[ch][1][rl]; s2 = sF[ch][2][rl]; }
-    if (fullc) rows_fwd_true<KRt, true>(x, x0, n, a1, a2, a3, s0, s1, s2);
-    else rows_fwd_true<KRt, false>(x, x0, n, a1, a2, a3, s0, s1, s2);
-    // right boundary: only the last chunk holds (u[n], u[n-1], u[n-2])
+#pragma unroll
+    for (int j = 0; j < KRt; ++j) {
+        float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+        x[j] = u;
+        s2 = s1; s1 = s0; s0 = u;
+    }
+    // right boundary at the end of the extended line: only the last chunk's values are used
     const float up = iplus * c.inv1ma, vp = up * c.inv1ma;
     const float d0 = s0 - up, d1 = s1 - up, d2 = s2 - up;
     const float vr0 = fmaf(c.M[0], d0, fmaf(c.M[1], d1, fmaf(c.M[2], d2, vp)));
     const float vr1 = fmaf(c.M[3], d0, fmaf(c.M[4], d1, fmaf(c.M[5], d2, vp)));
     const float vr2 = fmaf(c.M[6], d0, fmaf(c.M[7], d1, fmaf(c.M[8], d2, vp)));
+    const bool lastc = ch == NC - 1;
 
     // backward phase 1
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-    if (fullc) rows_bwd_local<KRt, true>(x, x0, n, a1, a2, a3, vr0, vr1, vr2, t0, t1, t2);
-    else rows_bwd_local<KRt, false>(x, x0, n, a1, a2, a3, vr0, vr1, vr2, t0, t1, t2);
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2;
+        t2 = t1; t1 = t0; t0 = v;
+        if (j == KRt - 1 && lastc) { t0 = vr0; t1 = vr1; t2 = vr2; }
+    }
     sB[ch][0][rl] = t0; sB[ch][1][rl] = t1; sB[ch][2][rl] = t2;
     __syncthreads();
     for (int rr = wid; rr < LR; rr += nwarp) {
@@ -542,11 +502,18 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
         if (lane < NC - 1) { sB[lane][0][rr] = q0; sB[lane][1][rr] = q1; sB[lane][2][rr] = q2; }
     }
     __syncthreads();
-    if (ch < NC - 1) { t0 = sB[ch][0][rl]; t1 = sB[ch][1][rl]; t2 = sB[ch][2][rl]; }
+    if (!lastc) { t0 = sB[ch][0][rl]; t1 = sB[ch][1][rl]; t2 = sB[ch][2][rl]; }
     else { t0 = 0.f; t1 = 0.f; t2 = 0.f; }
-    if (fullc) rows_bwd_true<KRt, true>(x, x0, n, a1, a2, a3, c.scale, vr0, vr1, vr2, t0, t1, t2);
-    else rows_bwd_true<KRt, false>(x, x0, n, a1, a2, a3, c.scale, vr0, vr1, vr2, t0, t1, t2);
+    const float sc = c.scale;
+#pragma unroll
+    for (int j = KRt - 1; j >= 0; --j) {
+        float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2;
+        if (j == KRt - 1 && lastc) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
+        else { t2 = t1; t1 = t0; t0 = v; }
+        x[j] = v * sc;
+    }
 
+    const bool fullc = x0 + KRt <= n;
     if (MODE == 0) {
         float* q = row_ptr(out, pitch4, x0);
         if (a.inv_n) {
@@ -561,9 +528,14 @@ __global__ void __launch_bounds__(32 * LR) k_rows(RowArgs a, IirDev c) {
         }
     } else {
         // exclusive prefix along x in Float64: out[., j+1] = sum_{x' <= j} v[x']
+        if (!fullc) {
+#pragma unroll
+            for (int j = 0; j < KRt; ++j)
+                if (x0 + j >= n) x[j] = 0.f;  // the extension does not belong to the sums
+        }
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < KRt; ++j) acc += (double)x[j];  // elements past the end of the line are 0
+        for (int j = 0; j < KRt; ++j) acc += (double)x[j];
         sP[ch][rl] = acc;
         __syncthreads();
         for (int rr = wid; rr < LR; rr += nwarp) {  // exclusive scan of the chunk totals, lane = chunk
@@ -657,15 +629,17 @@ static void dispatch_cols(cudaStream_t s, int K, bool grad, const ColArgs& a, co
 
 static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int mode) {
     if (a.W <= 32 * 40) {
-        dim3 grid((a.H + 31) / 32, a.nplanes, a.n_frames);
+        dim3 grid((a.H + 15) / 16, a.nplanes, a.n_frames);
         const int NC = (a.W + 39) / 40;
-        if (mode == 0) k_rows<40, 32, 0><<<grid, 32 * NC, 0, s>>>(a, c);
-        else k_rows<40, 32, 1><<<grid, 32 * NC, 0, s>>>(a, c);
+        const int threads = ((16 * NC + 31) / 32) * 32;
+        if (mode == 0) k_rows<40, 16, 0><<<grid, threads, 0, s>>>(a, c);
+        else k_rows<40, 16, 1><<<grid, threads, 0, s>>>(a, c);
     } else {
         dim3 grid((a.H + 15) / 16, a.nplanes, a.n_frames);
         const int NC = (a.W + 63) / 64;
-        if (mode == 0) k_rows<64, 16, 0><<<grid, 16 * NC, 0, s>>>(a, c);
-        else k_rows<64, 16, 1><<<grid, 16 * NC, 0, s>>>(a, c);
+        const int threads = ((16 * NC + 31) / 32) * 32;
+        if (mode == 0) k_rows<64, 16, 0><<<grid, threads, 0, s>>>(a, c);
+        else k_rows<64, 16, 1><<<grid, threads, 0, s>>>(a, c);
     }
 }
 
