@@ -15,4 +15,8 @@ _sspec = importlib.util.spec_from_file_location("slam_jl_b200.synth", os.path.jo
 synth = importlib.util.module_from_spec(_sspec)
 sys.modules["slam_jl_b200.synth"] = synth
 _sspec.loader.exec_module(synth)
+_dspec = importlib.util.spec_from_file_location("slam_jl_b200.dist", os.path.join(_pkg, "dist.py"))
+dist = importlib.util.module_from_spec(_dspec)
+sys.modules["slam_jl_b200.dist"] = dist
+_dspec.loader.exec_module(dist)
 globals().update({k: v for k, v in vars(_mod).items() if not k.startswith("__")})
