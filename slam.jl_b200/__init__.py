@@ -29,7 +29,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_CSRC, "libslamklt.so")
+LIB_PATH = os.environ.get("SLAMKLT_LIB", os.path.join(_CSRC, "libslamklt.so"))  # override for kernel experiments only
 
 F64, F32, U8 = 0, 1, 2
 MODE_UPDATE, MODE_CTOR = 0, 1

@@ -20,9 +20,9 @@
 namespace sk {
 
 template <typename T>
-__device__ __forceinline__ const T* col_ptr(const T* base, int stride_bytes, int k) {
-    // base + k columns: one IMAD.WIDE instead of a 64-bit multiply-shift-add chain
-    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (long long)stride_bytes * k);
+__device__ __forceinline__ const T* col_ptr(const T* base, unsigned stride_bytes, unsigned k) {
+    // base + k columns: one IMAD.WIDE.U32 (u32 x u32 + u64) instead of a 64-bit multiply-shift-add chain
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (unsigned long long)stride_bytes * k);
 }
 
 __device__ __forceinline__ float warp_sum_f(float v) {
@@ -31,8 +31,11 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
+#ifndef LK_MIN_BLOCKS
+#define LK_MIN_BLOCKS 4
+#endif
 template <int W2>
-__global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
+__global__ void __launch_bounds__(128, (W2 <= 19 ? LK_MIN_BLOCKS : (W2 <= 23 ? 3 : 2))) k_lk(const LKArgs a) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int total = a.n_frames * a.n_per_frame;
@@ -66,7 +69,8 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
         }
         const double eps = back ? 1e-2 : a.eps;  // tracker.jl:51-54 does not forward epsilon to the backward pass
         const LKLevel& L = a.lv[lvl];
-        const int H = L.H, W = L.W, pitch = L.pitch, pitch4 = L.pitch * 4;
+        const int H = L.H, W = L.W, pitch = L.pitch;
+        const unsigned pitch4 = (unsigned)L.pitch * 4u;
         const double inv = 1.0 / (double)(1 << lvl);
         const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);  // get_pyramid_coordinate, lucas_kanade.jl:197
         // get_offsets(point, point), lucas_kanade.jl:199-208, in integer arithmetic
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
                         float iv = 0.f;
                         if (okk) {
                             iv = __ldg(col_ptr(pI, pitch4, k));
-                            g2 = __ldg(col_ptr(pG, 2 * pitch4, k));
+                            g2 = __ldg(col_ptr(pG, 2u * pitch4, k));
                         }
                         tI[k] = iv; tIy[k] = g2.x; tIx[k] = g2.y;
                     }
@@ -136,11 +140,11 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
             }
             if (it >= a.iterations) break;
             const double pcy = (double)py + (dy + cy), pcx = (double)px + (dx + cx);
-            if (!(1.0 <= pcy && pcy <= (double)H && 1.0 <= pcx && pcx <= (double)W)) { ok = false; break; }
-            // get_offsets(point, putative_correspondence): floor(min(w, min(p, pc) - 1)) = min(w, min(p, floor pc) - 1),
-            // floor(min(w, H - max(p, pc))) = min(w, H - max(p, ceil pc))
-            const int fy = (int)floor(pcy), fx = (int)floor(pcx);
-            const int cyi = fy + (pcy > (double)fy ? 1 : 0), cxi = fx + (pcx > (double)fx ? 1 : 0);
+            // floor / ceil as integers serve both lies_in (1 <= pc <= size  <=>  floor >= 1 && ceil <= size) and get_offsets:
+            // floor(min(w, min(p, pc) - 1)) = min(w, min(p, floor pc) - 1), floor(min(w, H - max(p, pc))) = min(w, H - max(p, ceil pc))
+            const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
+            const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
+            if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
             const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
             const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
             if (nup != up || ndown != down || nleft != left || nright != right) {
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(128, 4) k_lk(const LKArgs a) {
             if (fabs(ffy) < eps && fabs(ffx) < eps) break;
             cy += ffy; cx += ffx;
             const double ny = pcy + ffy, nx = pcx + ffx;
-            if (!(1.0 <= ny && ny <= (double)H && 1.0 <= nx && nx <= (double)W)) { ok = false; break; }
+            if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
         }
         if (!ok) break;
         dy += cy; dx += cx;
