@@ -174,6 +174,7 @@ struct slamklt_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the pipelined batch step
     cudaStream_t d2h_stream = nullptr;   // D2H of the pipelined batch step
+    PyrStreams pyr_streams{};            // build DAG: main + two side streams
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
@@ -312,6 +313,11 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    c->pyr_streams.main = c->stream;
+    CK(cudaStreamCreateWithFlags(&c->pyr_streams.b, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->pyr_streams.c, cudaStreamNonBlocking));
+    for (auto& e : c->pyr_streams.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->pyr_streams.parallel = getenv("SLAMKLT_SERIAL_BUILD") == nullptr;
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
@@ -335,6 +341,9 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     for (auto e : c->pipe_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->d2h_stream);
+    for (auto& e : c->pyr_streams.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->pyr_streams.b);
+    cudaStreamDestroy(c->pyr_streams.c);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -468,7 +477,7 @@ static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const
     }
     c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64, c->hk());
     CKL();
-    c->launches += launch_pyramid(c->stream, fs, f0, n_frames, g, sigma, mode, ny, nx, c->hk());
+    c->launches += launch_pyramid(c->pyr_streams, fs, f0, n_frames, g, sigma, mode, ny, nx, c->hk());
     CKL();
     prof_end(c);
     return 0;

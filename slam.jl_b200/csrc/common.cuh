@@ -103,7 +103,10 @@ inline void mark(const Hook* h, const char* name) { if (h && h->fn) h->fn(h->use
 // launchers (each returns the number of kernels it launched; errors are picked up by cudaGetLastError in api.cu)
 int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t src_frame_stride_elems, FrameSet dst, int dst_f0,
                    int n_frames, const PyrGeom& g, double* dst64 /*nullable: also keep f64 copy, frame stride H*W*/, const Hook* hk);
-int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
+// streams/events for the pyramid build DAG: the blur chain (main) runs concurrently with the gradient stages (b: level 0,
+// c: levels >= 1), so the small coarse-level kernels overlap the big level-0 ones
+struct PyrStreams { cudaStream_t main, b, c; cudaEvent_t ev[MAX_LAYERS + 3]; bool parallel; };
+int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */, const Hook* hk);
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);

@@ -645,37 +645,21 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int
 
 static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
 
-int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
+int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx, const Hook* hk) {
     int launches = 0;
     char nm[48];
     const bool ctor = mode == SLAMKLT_MODE_CTOR;
-    // 1. Gaussian pyramid (sigma chain): layer l -> blur l -> layer l+1
-    for (int l = 0; l + 1 < g.nl; ++l) {
-        const LevelGeom& L = g.lv[l];
-        const LevelGeom& N = g.lv[l + 1];
-        const int K = pick_K(L.H);
-        IirDev c;
-        iir_dev(sigma, K, krow_of(L.W), &c);
-        ColArgs ca{};
-        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
-        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
-        ca.plane_elems = L.plane_elems; ca.inv_n = ctor ? inv_ny[l] : nullptr;
-        snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
-        dispatch_cols(s, K, false, ca, c);
-        RowArgs ra{};
-        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
-        ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
-        ra.inv_n = ctor ? inv_nx[l] : nullptr;
-        snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
-        dispatch_rows(s, ra, c, 0);
-        snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
-        dim3 grid((N.H + 127) / 128, N.W, n_frames);
-        k_resize<<<grid, 128, 0, s>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
-        launches += 3;
+    const bool par = ps.parallel && hk == nullptr && g.nl > 1;  // per-kernel profiling needs a serial stream
+    cudaStream_t sA = ps.main, sB = par ? ps.b : ps.main, sC = par ? ps.c : ps.main;
+    cudaEvent_t evStart = ps.ev[MAX_LAYERS], evB = ps.ev[MAX_LAYERS + 1], evC = ps.ev[MAX_LAYERS + 2];
+    if (par) {
+        cudaEventRecord(evStart, sA);  // level-0 layer is ready (convert ran on main)
+        cudaStreamWaitEvent(sB, evStart, 0);
+        cudaStreamWaitEvent(sC, evStart, 0);
     }
-    // 2. gradients + smoothed structure-tensor planes (stored as row prefix sums), every level
-    for (int l = 0; l < g.nl; ++l) {
+    auto grad_level = [&](cudaStream_t s, int l) {
+        // gradients + smoothed structure-tensor planes (stored as row prefix sums)
         const LevelGeom& L = g.lv[l];
         const int K = pick_K(L.H);
         IirDev c;
@@ -693,6 +677,42 @@ int launch_pyramid(cudaStream_t s, FrameSet fs, int f0, int n_frames, const PyrG
         snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
         dispatch_rows(s, ra, c, 1);
         launches += 2;
+    };
+    // stream B: level-0 gradients, concurrent with the blur chain
+    grad_level(sB, 0);
+    if (par) cudaEventRecord(evB, sB);
+    // main: Gaussian pyramid (sigma chain): layer l -> blur l -> layer l+1.  Its y-pass scratch is DP_TMP so that it
+    // does not collide with the gradient stage's T0..T2 of the same level.
+    for (int l = 0; l + 1 < g.nl; ++l) {
+        const LevelGeom& L = g.lv[l];
+        const LevelGeom& N = g.lv[l + 1];
+        const int K = pick_K(L.H);
+        IirDev c;
+        iir_dev(sigma, K, krow_of(L.W), &c);
+        ColArgs ca{};
+        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
+        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_TMP);
+        ca.plane_elems = L.plane_elems; ca.inv_n = ctor ? inv_ny[l] : nullptr;
+        snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
+        dispatch_cols(sA, K, false, ca, c);
+        RowArgs ra{};
+        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
+        ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_TMP); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
+        ra.inv_n = ctor ? inv_nx[l] : nullptr;
+        snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
+        dispatch_rows(sA, ra, c, 0);
+        snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
+        dim3 grid((N.H + 127) / 128, N.W, n_frames);
+        k_resize<<<grid, 128, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
+        launches += 3;
+        // stream C: gradients of level l+1 as soon as its layer exists
+        if (par) { cudaEventRecord(ps.ev[l + 1], sA); cudaStreamWaitEvent(sC, ps.ev[l + 1], 0); }
+        grad_level(sC, l + 1);
+    }
+    if (par) {
+        cudaEventRecord(evC, sC);
+        cudaStreamWaitEvent(sA, evB, 0);
+        cudaStreamWaitEvent(sA, evC, 0);
     }
     return launches;
 }
