@@ -164,6 +164,8 @@ int slamklt_batch_upload(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, i
 /* device-side work only: build all n_frames pyramids, then forward-backward track every pair */
 int slamklt_batch_build(slamklt_ctx* ctx, slamklt_batch* b, double sigma, int mode);
 int slamklt_batch_track(slamklt_ctx* ctx, slamklt_batch* b, const slamklt_lk_params* p);
+/* build + track of the uploaded frames in one asynchronous call (device-resident step) */
+int slamklt_batch_process(slamklt_ctx* ctx, slamklt_batch* b, double sigma, int mode, const slamklt_lk_params* p);
 /* async D2H of n_frames x n_pts x 2 tracked points and n_frames x n_pts status bytes, then stream sync */
 int slamklt_batch_download(slamklt_ctx* ctx, slamklt_batch* b, double* out_pts_yx, uint8_t* status);
 int slamklt_batch_rotate(slamklt_ctx* ctx, slamklt_batch* b);

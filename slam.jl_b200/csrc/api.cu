@@ -175,6 +175,7 @@ struct slamklt_ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of the pipelined batch step
     cudaStream_t d2h_stream = nullptr;   // D2H of the pipelined batch step
     PyrStreams pyr_streams{};            // build DAG: main + two side streams
+    cudaStream_t lk_stream = nullptr;    // tracking of chunk k overlaps the build of chunk k+1
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
@@ -314,6 +315,7 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     c->pyr_streams.main = c->stream;
+    CK(cudaStreamCreateWithFlags(&c->lk_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->pyr_streams.b, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->pyr_streams.c, cudaStreamNonBlocking));
     for (auto& e : c->pyr_streams.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -342,6 +344,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->d2h_stream);
     for (auto& e : c->pyr_streams.ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->lk_stream);
     cudaStreamDestroy(c->pyr_streams.b);
     cudaStreamDestroy(c->pyr_streams.c);
     cudaStreamDestroy(c->stream);
@@ -917,8 +920,91 @@ int slamklt_batch_rotate(slamklt_ctx* c, slamklt_batch* b) {
     return 0;
 }
 
-// Whole step through host buffers.  The batch is cut into chunks of frames; the H2D copy of chunk k+1 (copy stream)
-// overlaps the pyramid build + tracking of chunk k (compute stream), and the D2H of chunk k's results overlaps chunk k+1.
+// Chunked pipeline shared by slamklt_batch_step (host buffers) and slamklt_batch_process (device-resident frames):
+// H2D of chunk k+1 (copy stream) || pyramid build of chunk k (main + side streams) || tracking of chunk k-1 (lk stream)
+// || D2H of chunk k-2 (d2h stream).  imgs == nullptr: frames already sit in the batch staging buffer.
+static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
+                          const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts,
+                          uint8_t* status, int want_chunks) {
+    int r;
+    const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
+    const size_t es = dtype_size(dtype), fbytes = (size_t)H * W * es;
+    if ((r = b->staging.ensure((size_t)nf * fbytes))) return r;
+    const int chunk = nf >= 2 * want_chunks ? (nf + want_chunks - 1) / want_chunks : nf;
+    const int nchunks = (nf + chunk - 1) / chunk;
+    while ((int)c->pipe_ev.size() < 3 * nchunks + 1) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_ev.push_back(e);
+    }
+    cudaEvent_t* evH2D = c->pipe_ev.data();
+    cudaEvent_t* evBuilt = c->pipe_ev.data() + nchunks;
+    cudaEvent_t* evLK = c->pipe_ev.data() + 2 * nchunks;
+    cudaEvent_t evStart = c->pipe_ev[3 * nchunks];
+    const bool side_lk = !c->prof_on;  // the per-kernel profiler times one serial stream
+    cudaStream_t lks = side_lk ? c->lk_stream : c->stream;
+    // order the side streams after everything already queued on the compute stream (staging / slot reuse)
+    CK(cudaEventRecord(evStart, c->stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, evStart, 0));
+    if (side_lk) CK(cudaStreamWaitEvent(c->lk_stream, evStart, 0));
+    if (imgs) {
+        if (n_pts > 0) {
+            CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)nf * n_pts * 16, cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d += (uint64_t)nf * n_pts * 16;
+        }
+        b->n_pts = n_pts; b->up_dtype = dtype; b->up_ld = ld;
+        const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
+        for (int k = 0; k < nchunks; ++k) {
+            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+            char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
+            if (contiguous) {
+                CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
+            } else {
+                for (int f = f0; f < f1; ++f)
+                    CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
+                                         (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            c->h2d += (uint64_t)n * fbytes;
+            CK(cudaEventRecord(evH2D[k], c->copy_stream));
+        }
+    }
+    LKArgs a{};
+    a.A = fs_of(b); a.B = fs_of(b);
+    fill_lk_levels(b->g, &a);
+    a.mode = 1;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters;
+    a.n_per_frame = n_pts;
+    for (int k = 0; k < nchunks; ++k) {
+        const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+        const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
+        if (imgs) CK(cudaStreamWaitEvent(c->stream, evH2D[k], 0));
+        if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr))) return r;
+        if (n_pts > 0) {
+            if (side_lk) { CK(cudaEventRecord(evBuilt[k], c->stream)); CK(cudaStreamWaitEvent(lks, evBuilt[k], 0)); }
+            a.offA = f0; a.offB = f0 + 1; a.n_frames = n;
+            a.pts = (const double*)b->pts.p + (size_t)f0 * n_pts * 2;
+            a.out_pts = (double*)b->outp.p + (size_t)f0 * n_pts * 2;
+            a.status = (uint8_t*)b->status.p + (size_t)f0 * n_pts;
+            c->launches += launch_lk(lks, a, c->hk());
+            CKL();
+            prof_end(c);
+            CK(cudaEventRecord(evLK[k], lks));
+            if (out_pts && status) {
+                CK(cudaStreamWaitEvent(c->d2h_stream, evLK[k], 0));
+                CK(cudaMemcpyAsync(out_pts + (size_t)f0 * n_pts * 2, a.out_pts, (size_t)n * n_pts * 16, cudaMemcpyDeviceToHost, c->d2h_stream));
+                CK(cudaMemcpyAsync(status + (size_t)f0 * n_pts, a.status, (size_t)n * n_pts, cudaMemcpyDeviceToHost, c->d2h_stream));
+                c->d2h += (uint64_t)n * n_pts * 17;
+            }
+        }
+    }
+    // later work on the compute stream (next step's builds overwrite these slots) is ordered after the last tracking kernel
+    if (n_pts > 0) CK(cudaStreamWaitEvent(c->stream, evLK[nchunks - 1], 0));
+    return 0;
+}
+
+// Whole step through host buffers: upload + build + track + download + rotate, pipelined in chunks of frames.
 int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
                        const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
     if (!c || !b || !imgs) return fail(SLAMKLT_E_INVALID, "NULL argument");
@@ -933,75 +1019,30 @@ int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int d
     {
         std::lock_guard<std::mutex> lk(c->mu);
         CK(cudaSetDevice(c->device));
-        const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
-        const size_t es = dtype_size(dtype), fbytes = (size_t)H * W * es;
-        if ((r = b->staging.ensure((size_t)nf * fbytes))) return r;
         // more chunks hide more of the copy but run the kernels on smaller grids: 8 for 8-byte pixels, fewer for light copies
         const int want = dtype == SLAMKLT_F64 ? 8 : (dtype == SLAMKLT_F32 ? 4 : 2);
-        const int chunk = nf >= 2 * want ? (nf + want - 1) / want : nf;
-        const int nchunks = (nf + chunk - 1) / chunk;
-        while ((int)c->pipe_ev.size() < 2 * nchunks + 1) {
-            cudaEvent_t e;
-            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->pipe_ev.push_back(e);
-        }
-        // order the copy stream after everything already queued on the compute stream (staging reuse)
-        CK(cudaEventRecord(c->pipe_ev[2 * nchunks], c->stream));
-        CK(cudaStreamWaitEvent(c->copy_stream, c->pipe_ev[2 * nchunks], 0));
-        if (n_pts > 0) {
-            CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)nf * n_pts * 16, cudaMemcpyHostToDevice, c->copy_stream));
-            c->h2d += (uint64_t)nf * n_pts * 16;
-        }
-        b->n_pts = n_pts; b->up_dtype = dtype; b->up_ld = ld;
-        const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
-        LKArgs a{};
-        a.A = fs_of(b); a.B = fs_of(b);
-        fill_lk_levels(b->g, &a);
-        a.mode = 1;
-        a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
-        a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-        a.counters = c->d_counters;
-        a.n_per_frame = n_pts;
-        // 1. queue every H2D chunk on the copy stream
-        for (int k = 0; k < nchunks; ++k) {
-            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
-            char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
-            if (contiguous) {
-                CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
-            } else {
-                for (int f = f0; f < f1; ++f)
-                    CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
-                                         (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
-            }
-            c->h2d += (uint64_t)n * fbytes;
-            CK(cudaEventRecord(c->pipe_ev[2 * k], c->copy_stream));
-        }
-        // 2. compute chunk k as soon as its frames have landed; results leave on a third stream
-        for (int k = 0; k < nchunks; ++k) {
-            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
-            const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
-            CK(cudaStreamWaitEvent(c->stream, c->pipe_ev[2 * k], 0));
-            if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr))) return r;
-            if (n_pts > 0) {
-                a.offA = f0; a.offB = f0 + 1; a.n_frames = n;
-                a.pts = (const double*)b->pts.p + (size_t)f0 * n_pts * 2;
-                a.out_pts = (double*)b->outp.p + (size_t)f0 * n_pts * 2;
-                a.status = (uint8_t*)b->status.p + (size_t)f0 * n_pts;
-                c->launches += launch_lk(c->stream, a, c->hk());
-                CKL();
-                prof_end(c);
-                CK(cudaEventRecord(c->pipe_ev[2 * k + 1], c->stream));
-                CK(cudaStreamWaitEvent(c->d2h_stream, c->pipe_ev[2 * k + 1], 0));
-                CK(cudaMemcpyAsync(out_pts + (size_t)f0 * n_pts * 2, a.out_pts, (size_t)n * n_pts * 16, cudaMemcpyDeviceToHost, c->d2h_stream));
-                CK(cudaMemcpyAsync(status + (size_t)f0 * n_pts, a.status, (size_t)n * n_pts, cudaMemcpyDeviceToHost, c->d2h_stream));
-                c->d2h += (uint64_t)n * n_pts * 17;
-            }
-        }
+        if ((r = batch_pipeline(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, want))) return r;
         CK(cudaStreamSynchronize(c->d2h_stream));
+        CK(cudaStreamSynchronize(c->lk_stream));
         CK(cudaStreamSynchronize(c->copy_stream));
         CK(cudaStreamSynchronize(c->stream));
     }
     return slamklt_batch_rotate(c, b);
+}
+
+// Device-resident step: frames and points were uploaded before (slamklt_batch_upload); build every pyramid and track every
+// pair in one asynchronous call.  Results are fetched with slamklt_batch_download (which synchronises).
+int slamklt_batch_process(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode, const slamklt_lk_params* p) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
+    int r = check_lk(p, b->g.nl, b->g.nl);
+    if (r) return r;
+    if (!b->primed) return fail(SLAMKLT_E_INVALID, "batch slot 0 was never built (call slamklt_batch_prime)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    // measured on B200: chunking a device-resident batch only shrinks the grids (2.57 vs 2.30 ms per 64 frames), so one chunk
+    return batch_pipeline(c, b, nullptr, b->up_dtype, b->up_ld, 0, nullptr, b->n_pts, sigma, mode, p, nullptr, nullptr, 1);
 }
 
 int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out) {

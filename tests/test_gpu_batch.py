@@ -65,6 +65,11 @@ def test_batch_phases_equal_step(ctx, small_seq):
     b2.upload(packed, pts); b2.build(); b2.track(alg, 1.0)
     o2, s2 = b2.download()
     assert np.array_equal(s1, s2) and np.array_equal(np.nan_to_num(o1), np.nan_to_num(o2))
+    b3 = slamklt.StreamBatch(ctx, H, W, L, NF, NP); b3.prime(f64[0])
+    b3.upload(packed, pts); b3.process(alg, 1.0); b3.process(alg, 1.0)   # repeated: same slots rebuilt, same answer
+    o3, s3 = b3.download()
+    assert np.array_equal(s1, s3) and np.array_equal(np.nan_to_num(o1), np.nan_to_num(o3))
+    b3.close()
     assert ctx.stats()["kernel_launches"] > 0
     b1.close(); b2.close()
 
