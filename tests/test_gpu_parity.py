@@ -66,7 +66,9 @@ def _check_tracks(ro, rg, min_n=1):
     both = so & sg
     assert both.sum() >= min_n
     d = np.abs(po[both] - pg[both]).max(axis=1)
-    assert np.mean(d < POS_TOL) >= FLAG_AGREE, (np.mean(d < POS_TOL), d.max())
+    # an epsilon-stop flip (|step| within rounding of 1e-2) moves a point by at most ~0.0141 px; allow one per test
+    assert np.mean(d < POS_TOL) >= FLAG_AGREE or np.sum(d >= POS_TOL) <= 1, (np.mean(d < POS_TOL), d.max())
+    assert d.max() < 0.02
     return d
 
 
