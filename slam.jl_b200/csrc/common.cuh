@@ -110,6 +110,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
                    const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */, const Hook* hk);
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
+bool launch_lk_patch(cudaStream_t s, const LKArgs& a);  // patch-mapped variant (lk_patch.cu), windows up to 23 x 23
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);
 

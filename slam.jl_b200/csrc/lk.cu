@@ -15,6 +15,8 @@
 // instructions and 20% "no instruction" stalls in the first version).
 // Planes carry one zeroed guard row and guard column (pitch >= H+1, W+1 columns allocated), so the bilinear tap
 // that falls on H+1 / W+1 with weight exactly 0 needs no clamp.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sk {
@@ -219,9 +221,12 @@ int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     const int total = a.n_frames * a.n_per_frame;
     if (total <= 0) return 0;
     mark(hk, a.mode ? "k_lk_fb" : "k_lk_optflow");
-    const int wpb = 4;
+    static const int wpb_env = getenv("SLAMKLT_LK_WPB") ? atoi(getenv("SLAMKLT_LK_WPB")) : 0;  // experiment knob
+    const int wpb = (wpb_env >= 1 && wpb_env <= 4) ? wpb_env : 4;
     const int blocks = (total + wpb - 1) / wpb;
     const int w2 = 2 * a.window + 1;
+    static const bool use_rows = getenv("SLAMKLT_LK_VARIANT") && getenv("SLAMKLT_LK_VARIANT")[0] == 'r';  // A/B knob
+    if (!use_rows && launch_lk_patch(s, a)) return 1;
     if (w2 <= 19) k_lk<19><<<blocks, wpb * 32, 0, s>>>(a);
     else if (w2 <= 23) k_lk<23><<<blocks, wpb * 32, 0, s>>>(a);
     else k_lk<31><<<blocks, wpb * 32, 0, s>>>(a);

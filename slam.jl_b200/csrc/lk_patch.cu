@@ -1,0 +1,270 @@
+// Pyramidal Lucas-Kanade with forward-backward check, patch-mapped variant (sm_100a).
+//
+// Same semantics as lk.cu (reference: lucas_kanade.jl:9-212, utils.jl:5-45, tracker.jl:17-68); different mapping.
+// lk.cu gives every window ROW to a lane: a 19-row window keeps 20 of 32 lanes busy and needs one shuffle per tap.
+// Here the 32 lanes tile the window as 8 row-groups x 4 column-groups; a lane owns a PR x PC patch of the template
+// (3 x 5 for the 19 x 19 window) in registers and reads its own (PR+1) x (PC+1) bilinear taps from a target tile staged
+// in shared memory: no shuffles in the sampling loop, all lanes busy, loads with immediate offsets.
+// The target tile (TC columns x TR rows around the current estimate) is staged once per level with 16-byte loads and
+// re-staged only if the estimate walks out of its margin.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace sk {
+
+template <typename T>
+__device__ __forceinline__ const T* col_ptr2(const T* base, unsigned stride_bytes, unsigned k) {
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + (unsigned long long)stride_bytes * k);
+}
+
+__device__ __forceinline__ float warp_sum_f2(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int W2, int PR, int PC>
+__global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
+    static_assert(PR * 8 >= W2 && PC * 4 >= W2, "patch grid must cover the window");
+    constexpr int RSPAN = PR * 8 + 1, CSPAN = PC * 4 + 1;  // tap rows / columns touched by the lanes
+    // tile rows: multiple of 4 (16-byte staging), >= RSPAN + 8, and PC*TR = 8 (mod 32) so that the 8 x 4 lane grid (row
+    // stride PR = 3 words, column-group stride PC*TR words) hits 32 distinct banks: TR = 40 for PC = 5, 44 for PC = 6
+    constexpr int TR = PC == 5 ? 40 : 44;
+    static_assert(TR >= RSPAN + 8 && TR % 4 == 0 && (PC * TR) % 32 == 8 && PR == 3, "tile geometry");
+    constexpr int TC = CSPAN + 8;                           // tile columns
+    constexpr int RG = TR / 4, CGN = 32 / RG;               // staging: RG row groups per column, CGN columns per instruction
+    __shared__ __align__(16) float sTile[4][TC][TR];
+    float (*sT)[TR] = sTile[threadIdx.x >> 5];
+
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int total = a.n_frames * a.n_per_frame;
+    if (gw >= total) return;
+    const int f = gw / a.n_per_frame;
+    const float* fbA = a.A.frame(a.offA + f);
+    const float* fbB = a.B.frame(a.offB + f);
+    const double pty = a.pts[2 * (size_t)gw], ptx = a.pts[2 * (size_t)gw + 1];
+    double dy = 0.0, dx = 0.0;
+    if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
+
+    const int w = a.window;
+    const int nstage = a.levels + 1 + (a.mode ? 1 : 0);
+    unsigned int wpx = 0, nit = 0;
+    double qy = pty, qx = ptx;
+    bool ok = true;
+    uint8_t result = 0;
+
+    const int rgp = lane & 7, cgp = lane >> 3;  // patch row group / column group of this lane
+    const int pi0 = rgp * PR, pj0 = cgp * PC;   // first window row / column of the patch
+    float tI[PR][PC], tIy[PR][PC], tIx[PR][PC];
+    int ty0 = 0, tx0 = 0;
+    bool pending = false;
+    const int srg = lane % RG, scg = lane / RG;  // staging role of this lane: 16-byte row group / column group
+
+    for (int s = 0; s < nstage; ++s) {
+        const bool back = s > a.levels;
+        const int lvl = back ? 0 : a.levels - s;
+        if (back) {
+            qy = pty + dy; qx = ptx + dx;  // tracker.jl:37-46
+            if (lane == 0 && a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
+            result = 2;
+            dy = -dy; dx = -dx;
+            const float* t = fbA; fbA = fbB; fbB = t;
+        }
+        const double eps = back ? 1e-2 : a.eps;
+        const LKLevel& L = a.lv[lvl];
+        const int H = L.H, W = L.W, pitch = L.pitch;
+        const unsigned pitch4 = (unsigned)L.pitch * 4u;
+        const double inv = 1.0 / (double)(1 << lvl);
+        const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);
+        int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
+        bool setup = true;
+        double g00 = 0, g01 = 0, g11 = 0;
+        double cy = 0.0, cx = 0.0;
+        int it = 0;
+        {
+            // stage the target tile for the first iteration's position now, so that its latency overlaps the G and
+            // template loads and the 2x2 solve below (asynchronous global->shared copies, no registers involved)
+            const int fy0 = __double2int_rd((double)py + dy), fx0 = __double2int_rd((double)px + dx);
+            // the estimate may be anywhere (bounds are checked later, lies_in): clamp so the copies stay inside the frame block
+            const int ay0 = min(max(fy0 - up - 1, 0), H), ax0 = min(max(fx0 - left - 1, 0), W);
+            if (pending) cp_async_wait_all();
+            __syncwarp();
+            ty0 = max(0, ay0 - 4) & ~3;
+            tx0 = max(0, ax0 - 4);
+            const float* src = fbB + L.oI + (size_t)(tx0 + scg) * pitch + (ty0 + 4 * srg);
+#pragma unroll
+            for (int j = 0; j < (TC + CGN - 1) / CGN; ++j)
+                if (scg < CGN && CGN * j + scg < TC) cp_async16(&sT[CGN * j + scg][4 * srg], col_ptr2(src, (unsigned)CGN * pitch4, j));
+            cp_async_commit();
+            pending = true;
+        }
+        while (true) {
+            const int nrows = up + down + 1, ncols = left + right + 1;
+            if (setup) {
+                const int r0 = py - up, c0 = px - left;
+                if (nrows < 1 || ncols < 1 || r0 < 1 || c0 < 1 || py + down > H || px + right > W) { ok = false; break; }
+                // ---- G from the row prefix planes, lane = window row (as in lk.cu)
+                float syy, sxx, syx;
+                {
+                    const float* colA = fbA + (size_t)(r0 - 1 + min(lane, nrows - 1));
+                    const size_t lo = (size_t)(c0 - 1) * pitch, hi = (size_t)(px + right) * pitch;
+                    syy = __ldg(colA + L.oRyy + hi) - __ldg(colA + L.oRyy + lo);
+                    sxx = __ldg(colA + L.oRxx + hi) - __ldg(colA + L.oRxx + lo);
+                    syx = __ldg(colA + L.oRyx + hi) - __ldg(colA + L.oRyx + lo);
+                    if (lane >= nrows) { syy = 0.f; sxx = 0.f; syx = 0.f; }
+                }
+                // ---- template patch of this lane into registers; entries outside the (clipped) window get zero gradients
+                {
+                    const float* pI = fbA + L.oI + (size_t)(r0 - 1 + pi0) + (size_t)(c0 - 1 + pj0) * pitch;
+                    const float2* pG = reinterpret_cast<const float2*>(fbA + L.oG) + (size_t)(r0 - 1 + pi0) + (size_t)(c0 - 1 + pj0) * pitch;
+#pragma unroll
+                    for (int j = 0; j < PC; ++j) {
+                        const float* cI = col_ptr2(pI, pitch4, j);
+                        const float2* cG = col_ptr2(pG, 2u * pitch4, j);
+#pragma unroll
+                        for (int i = 0; i < PR; ++i) {
+                            const bool okk = (pi0 + i < nrows) && (pj0 + j < ncols);
+                            float iv = 0.f;
+                            float2 g2 = make_float2(0.f, 0.f);
+                            if (okk) { iv = __ldg(cI + i); g2 = __ldg(cG + i); }
+                            tI[i][j] = iv; tIy[i][j] = g2.x; tIx[i][j] = g2.y;
+                        }
+                    }
+                }
+                const double ga = (double)warp_sum_f2(syy), gc = (double)warp_sum_f2(sxx), gb = (double)warp_sum_f2(syx);
+                const double E = 0.5 * (ga + gc), F = 0.5 * (ga - gc);
+                const double R = sqrt(F * F + gb * gb), Q = fabs(E);
+                const double s1 = Q + R, s2 = fabs(Q - R);
+                const double min_eig = fmin(s1, s2) / (double)(nrows * ncols);
+                if (min_eig < a.eig_thr) { ok = false; break; }
+                const double tol = 1.4901161193847656e-08;
+                if (s2 > tol) {
+                    const double id = 1.0 / (ga * gc - gb * gb);
+                    g00 = gc * id; g01 = -gb * id; g11 = ga * id;
+                } else {
+                    g00 = g01 = g11 = 0.0;
+                    const double l1 = E + (E >= 0 ? R : -R);
+                    if (fabs(l1) > tol) {
+                        double vx = gb, vy = l1 - ga;
+                        if (fabs(vx) + fabs(vy) < 1e-300) { vx = l1 - gc; vy = gb; }
+                        if (fabs(vx) + fabs(vy) < 1e-300) { vx = fabs(ga) >= fabs(gc) ? 1.0 : 0.0; vy = 1.0 - vx; }
+                        const double nn = 1.0 / ((vx * vx + vy * vy) * l1);
+                        g00 = vx * vx * nn; g01 = vx * vy * nn; g11 = vy * vy * nn;
+                    }
+                }
+                setup = false;
+            }
+            if (it >= a.iterations) break;
+            const double pcy = (double)py + (dy + cy), pcx = (double)px + (dx + cx);
+            const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
+            const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
+            if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
+            const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
+            const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
+            if (nup != up || ndown != down || nleft != left || nright != right) {
+                up = nup; down = ndown; left = nleft; right = nright;
+                setup = true;
+                continue;
+            }
+            const float wy = (float)(pcy - (double)fy), wx = (float)(pcx - (double)fx);
+            const int ay = fy - up - 1, ax = fx - left - 1;  // 0-based first tap row / column
+            int oy = ay - ty0, ox = ax - tx0;
+            if (oy < 0 || oy + RSPAN > TR || ox < 0 || ox + CSPAN > TC) {
+                // the estimate walked out of the staged tile (or the window was re-clipped): stage again around it
+                __syncwarp();
+                ty0 = max(0, ay - 4) & ~3;
+                tx0 = max(0, ax - 4);
+                oy = ay - ty0; ox = ax - tx0;
+                const float* src = fbB + L.oI + (size_t)(tx0 + scg) * pitch + (ty0 + 4 * srg);
+#pragma unroll
+                for (int j = 0; j < (TC + CGN - 1) / CGN; ++j)
+                    if (scg < CGN && CGN * j + scg < TC) cp_async16(&sT[CGN * j + scg][4 * srg], col_ptr2(src, (unsigned)CGN * pitch4, j));
+                cp_async_commit();
+                pending = true;
+            }
+            if (pending) { cp_async_wait_all(); __syncwarp(); pending = false; }
+            // ---- prepare_linear_system (lucas_kanade.jl:159-173) on this lane's patch
+            const float* tb = &sT[ox + pj0][oy + pi0];
+            float by = 0.f, bx = 0.f;
+            float vprev[PR];  // vertical lerps of the previous tap column
+#pragma unroll
+            for (int i = 0; i < PR; ++i) {
+                const float t0 = tb[i], t1 = tb[i + 1];
+                vprev[i] = fmaf(wy, t1 - t0, t0);
+            }
+#pragma unroll
+            for (int j = 0; j < PC; ++j) {
+                float tcol[PR + 1];
+#pragma unroll
+                for (int i = 0; i <= PR; ++i) tcol[i] = tb[(j + 1) * TR + i];
+#pragma unroll
+                for (int i = 0; i < PR; ++i) {
+                    const float vcur = fmaf(wy, tcol[i + 1] - tcol[i], tcol[i]);
+                    const float val = fmaf(wx, vcur - vprev[i], vprev[i]);
+                    const float dI = tI[i][j] - val;
+                    by = fmaf(dI, tIy[i][j], by);
+                    bx = fmaf(dI, tIx[i][j], bx);
+                    vprev[i] = vcur;
+                }
+            }
+            const double sby = (double)warp_sum_f2(by), sbx = (double)warp_sum_f2(bx);
+            wpx += (unsigned)(nrows * ncols);
+            nit += 1;
+            ++it;
+            const double ffy = g00 * sby + g01 * sbx, ffx = g01 * sby + g11 * sbx;
+            if (fabs(ffy) < eps && fabs(ffx) < eps) break;
+            cy += ffy; cx += ffx;
+            const double ny = pcy + ffy, nx = pcx + ffx;
+            if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
+        }
+        if (!ok) break;
+        dy += cy; dx += cx;
+        if (lvl > 0) { dy *= 2.0; dx *= 2.0; }
+    }
+
+    if (pending) cp_async_wait_all();  // never leave with copies in flight
+    if (a.mode == 0) {
+        if (lane == 0) {
+            if (a.disp_out) { a.disp_out[2 * (size_t)gw] = dy; a.disp_out[2 * (size_t)gw + 1] = dx; }
+            a.status[gw] = ok ? 1 : 0;
+        }
+    } else if (lane == 0) {
+        if (result == 0) {
+            if (a.out_pts) {
+                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        } else if (ok) {
+            const double by = qy + dy, bx = qx + dx;
+            const double ey = pty - by, ex = ptx - bx;
+            if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+        }
+        a.status[gw] = result;
+    }
+    if (lane == 0 && a.counters) {
+        atomicAdd(a.counters, (unsigned long long)wpx);
+        atomicAdd(a.counters + 1, (unsigned long long)nit);
+    }
+}
+
+// returns false when this variant does not cover the window size
+bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
+    const int total = a.n_frames * a.n_per_frame;
+    const int blocks = (total + 3) / 4;
+    const int w2 = 2 * a.window + 1;
+    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 128, 0, s>>>(a);
+    else if (w2 <= 23) k_lk_patch<23, 3, 6><<<blocks, 128, 0, s>>>(a);
+    else return false;
+    return true;
+}
+
+}  // namespace sk
