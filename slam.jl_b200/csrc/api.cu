@@ -478,9 +478,12 @@ static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const
         int r = get_norms(c, g, sigma, ny, nx);
         if (r) return r;
     }
-    c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64, c->hk());
-    CKL();
-    c->launches += launch_pyramid(c->pyr_streams, fs, f0, n_frames, g, sigma, mode, ny, nx, c->hk());
+    if (img64) {  // a Float64 copy is wanted as well (batched detect on non-Float64 frames): separate conversion pass
+        c->launches += launch_convert(c->stream, staged, dtype, g.H0, (size_t)g.H0 * g.W0, fs, f0, n_frames, g, img64, c->hk());
+        CKL();
+    }
+    // level 0 is converted on the fly by the fused column kernel (no separate conversion pass)
+    c->launches += launch_pyramid(c->pyr_streams, fs, f0, n_frames, g, sigma, mode, ny, nx, staged, dtype, c->hk());
     CKL();
     prof_end(c);
     return 0;

@@ -107,7 +107,8 @@ int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t sr
 // c: levels >= 1), so the small coarse-level kernels overlap the big level-0 ones
 struct PyrStreams { cudaStream_t main, b, c; cudaEvent_t ev[MAX_LAYERS + 3]; bool parallel; };
 int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
-                   const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */, const Hook* hk);
+                   const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */,
+                   const void* raw /* staged host image(s) or nullptr */, int dtype, const Hook* hk);
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
 bool launch_lk_patch(cudaStream_t s, const LKArgs& a);  // patch-mapped variant (lk_patch.cu), windows up to 23 x 23

@@ -256,6 +256,13 @@ struct ColArgs {
     size_t o_grad;         // grad only: interleaved (Iy, Ix)
     size_t plane_elems;
     const float* inv_n;    // blur NA mode: 1/ny[y]
+    // fused kernel only: level 0 reads the staged host image directly (and writes the layer), levels < L also run the
+    // y pass of the pyramid blur
+    const void* raw;       // nullptr: read the layer plane
+    int raw_ld;
+    size_t raw_stride;     // elements per frame
+    int do_blur;
+    size_t o_tmp;          // y-filtered blur output
 };
 
 // One warp per (frame, column).
@@ -315,6 +322,136 @@ __device__ __forceinline__ void load_col_halo(const float* __restrict__ I, int x
 #pragma unroll
         for (int j = 1; j <= K + 1; ++j)
             if (y0 + j - 1 == H) e[j] = e[j - 1];
+    }
+}
+
+// SRC: 0 layer plane (fp32), 1 raw Float64, 2 raw Float32, 3 raw UInt8 (value / 255)
+template <int K, int SRC>
+__device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y0, float (&x)[K]) {
+    if constexpr (SRC == 0) {
+        load_col<K>(I + (size_t)xc * a.pitch, y0, a.pitch, x);
+    } else if constexpr (SRC == 1) {
+        const double* col = reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
+        if ((a.raw_ld & 1) == 0) {  // 16-byte aligned column starts: K is even, so pairs never straddle the end of a valid run
+#pragma unroll
+            for (int v = 0; v < K / 2; ++v) {
+                const int y = y0 + 2 * v;
+                double2 t = make_double2(0.0, 0.0);
+                if (y + 1 < a.H) t = __ldg(reinterpret_cast<const double2*>(col + y));
+                else if (y < a.H) t.x = __ldg(col + y);
+                x[2 * v] = (float)t.x; x[2 * v + 1] = (float)t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? (float)__ldg(col + y0 + j) : 0.f;
+        }
+    } else if constexpr (SRC == 2) {
+        const float* col = reinterpret_cast<const float*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? __ldg(col + y0 + j) : 0.f;
+    } else {
+        const uint8_t* col = reinterpret_cast<const uint8_t*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? (float)((double)__ldg(col + y0 + j) / 255.0) : 0.f;
+    }
+}
+
+template <int K, int SRC>
+__device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float* __restrict__ I, int f, int xcol, int y0, int lane, bool zb,
+                                                  float (&e)[K + 2]) {
+    const int W = a.W, H = a.H;
+    float x[K];
+    const bool inside = xcol >= 0 && xcol < W;
+    if (inside || !zb) {
+        const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
+        load_col_any<K, SRC>(a, I, f, xc, y0, x);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = 0.f;
+    }
+    float upv = __shfl_up_sync(FULL, x[K - 1], 1);
+    float dnv = __shfl_down_sync(FULL, x[0], 1);
+    if (lane == 0) upv = zb ? 0.f : x[0];
+    if (lane == 31) dnv = 0.f;
+    e[0] = upv;
+#pragma unroll
+    for (int j = 0; j < K; ++j) e[j + 1] = x[j];
+    e[K + 1] = dnv;
+    if (!zb) {
+#pragma unroll
+        for (int j = 1; j <= K + 1; ++j)
+            if (y0 + j - 1 == H) e[j] = e[j - 1];
+    }
+}
+
+// Fused column kernel: [level 0: input conversion + layer store] + Scharr + products + y pass of the sigma=4 filter
+// + [levels < L: y pass of the pyramid blur].  One read of the source column per output column (+2 halo columns per strip).
+template <int K, int SRC>
+__global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int H = a.H, W = a.W, pitch = a.pitch;
+    const int strips = (W + GRAD_CS - 1) / GRAD_CS;
+    const int total = a.n_frames * strips;
+    const int y0 = lane * K;
+    const bool zb = a.zero_border != 0;
+    for (int w = warp; w < total; w += nwarps) {
+        const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
+        float* fb = a.fs.frame(a.f0 + f);
+        const float* I = fb + a.o_in;
+        float em[K + 2], ec[K + 2], ep[K + 2];
+        load_col_halo_any<K, SRC>(a, I, f, xb - 1, y0, lane, zb, em);
+        load_col_halo_any<K, SRC>(a, I, f, xb, y0, lane, zb, ec);
+        const int xe = min(xb + GRAD_CS, W);
+        for (int xcol = xb; xcol < xe; ++xcol) {
+            load_col_halo_any<K, SRC>(a, I, f, xcol + 1, y0, lane, zb, ep);
+            float pp[3][K];
+            {
+                float gi[2 * K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
+                    float gy = s0 * (0.5f * (em[j + 2] - em[j])) + s1 * (0.5f * (ec[j + 2] - ec[j])) + s0 * (0.5f * (ep[j + 2] - ep[j]));
+                    float gx = s0 * (0.5f * (ep[j] - em[j])) + s1 * (0.5f * (ep[j + 1] - em[j + 1])) + s0 * (0.5f * (ep[j + 2] - em[j + 2]));
+                    gi[2 * j] = gy; gi[2 * j + 1] = gx;
+                    pp[0][j] = gy * gy; pp[1][j] = gx * gx; pp[2][j] = gy * gx;
+                }
+                float* og = fb + a.o_grad + (size_t)xcol * (2 * pitch);
+#pragma unroll
+                for (int v = 0; v < K / 2; ++v) {
+                    const int y = y0 + 2 * v;
+                    if (y < pitch) {
+                        float4 t;
+                        t.x = y < H ? gi[4 * v] : 0.f; t.y = y < H ? gi[4 * v + 1] : 0.f;
+                        t.z = y + 1 < H ? gi[4 * v + 2] : 0.f; t.w = y + 1 < H ? gi[4 * v + 3] : 0.f;
+                        *reinterpret_cast<float4*>(og + 2 * y) = t;
+                    }
+                }
+            }
+            warp_iir_lines<K, 3>(pp, H, lane, c4, false);
+            float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
+            store_col<K>(o0, y0, pitch, H, pp[0]);
+            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pp[1]);
+            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pp[2]);
+            if (SRC != 0 || a.do_blur) {
+                float bl[1][K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) bl[0][j] = (y0 + j < H) ? ec[j + 1] : 0.f;
+                if (SRC != 0) store_col<K>(fb + a.o_in + (size_t)xcol * pitch, y0, pitch, H, bl[0]);  // the converted layer
+                if (a.do_blur) {
+                    warp_iir_lines<K, 1>(bl, H, lane, c1, zb);
+                    if (a.inv_n) {
+#pragma unroll
+                        for (int j = 0; j < K; ++j)
+                            if (y0 + j < H) bl[0][j] *= __ldg(a.inv_n + y0 + j);
+                    }
+                    store_col<K>(fb + a.o_tmp + (size_t)xcol * pitch, y0, pitch, H, bl[0]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < K + 2; ++j) { em[j] = ec[j]; ec[j] = ep[j]; }
+        }
     }
 }
 
@@ -388,11 +525,12 @@ struct RowArgs {
     const float* inv_n;                 // NA mode: 1/nx[x]
 };
 
-__device__ __forceinline__ const float* row_ptr(const float* base, int pitch4, int k) {
-    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (long long)pitch4 * k);
+// base + k columns as one IMAD.WIDE.U32 (u32 x u32 + u64)
+__device__ __forceinline__ const float* row_ptr(const float* base, unsigned pitch4, unsigned k) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned long long)pitch4 * k);
 }
-__device__ __forceinline__ float* row_ptr(float* base, int pitch4, int k) {
-    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + (long long)pitch4 * k);
+__device__ __forceinline__ float* row_ptr(float* base, unsigned pitch4, unsigned k) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + (unsigned long long)pitch4 * k);
 }
 
 template <int KRt, int LR, int MODE>
@@ -416,7 +554,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     float* out = fb + a.o_out0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     const int x0 = chok ? ch * KRt : 0;
     const int n = a.W;
-    const int pitch4 = a.pitch * 4;
+    const unsigned pitch4 = (unsigned)a.pitch * 4u;
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
     const bool zb = a.zero_border != 0;
     const float iminus = (zb || !rowok) ? 0.f : __ldg(in);
@@ -428,7 +566,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     {
         const float* p = row_ptr(in, pitch4, x0);
 #pragma unroll
-        for (int j = 0; j < KRt; ++j) x[j] = __ldg(row_ptr(p, pitch4, min(j, n - 1 - x0)));
+        for (int j = 0; j < KRt; ++j) x[j] = __ldg(row_ptr(p, pitch4, (unsigned)max(min(j, n - 1 - x0), 0)));
         if (x0 + KRt > n) {
 #pragma unroll
             for (int j = 0; j < KRt; ++j)
@@ -645,74 +783,89 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int
 
 static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
 
+template <int K>
+static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
+    const int total_warps = a.n_frames * ((a.W + GRAD_CS - 1) / GRAD_CS);
+    const int wpb = 4;
+    int blocks = (total_warps + wpb - 1) / wpb;
+    const int maxb = 148 * 16;
+    if (blocks > maxb) blocks = maxb;
+    switch (src) {
+        case 0: k_cols_all<K, 0><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
+        case 1: k_cols_all<K, 1><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
+        case 2: k_cols_all<K, 2><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
+        default: k_cols_all<K, 3><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
+    }
+}
+
+static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
+    switch (K) {
+        case 2: launch_cols_all<2>(s, src, a, c4, c1); break;
+        case 4: launch_cols_all<4>(s, src, a, c4, c1); break;
+        case 6: launch_cols_all<6>(s, src, a, c4, c1); break;
+        case 8: launch_cols_all<8>(s, src, a, c4, c1); break;
+        case 12: launch_cols_all<12>(s, src, a, c4, c1); break;
+        case 16: launch_cols_all<16>(s, src, a, c4, c1); break;
+        case 24: launch_cols_all<24>(s, src, a, c4, c1); break;
+        case 34: launch_cols_all<34>(s, src, a, c4, c1); break;
+    }
+}
+
+// Build the pyramids of n_frames frames.  raw != nullptr: level 0 is read from the staged host image (dtype, compact
+// ld = H0) and the layer plane is written on the way; raw == nullptr: the level-0 layer is already in place.
+// Per level: k_cols_all (main) -> { k_rows blur -> k_resize -> next level (main)  ||  k_rows struct/prefix (side stream) }.
 int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
-                   const float* const* inv_ny, const float* const* inv_nx, const Hook* hk) {
+                   const float* const* inv_ny, const float* const* inv_nx, const void* raw, int dtype, const Hook* hk) {
     int launches = 0;
     char nm[48];
     const bool ctor = mode == SLAMKLT_MODE_CTOR;
-    const bool par = ps.parallel && hk == nullptr && g.nl > 1;  // per-kernel profiling needs a serial stream
-    cudaStream_t sA = ps.main, sB = par ? ps.b : ps.main, sC = par ? ps.c : ps.main;
-    cudaEvent_t evStart = ps.ev[MAX_LAYERS], evB = ps.ev[MAX_LAYERS + 1], evC = ps.ev[MAX_LAYERS + 2];
-    if (par) {
-        cudaEventRecord(evStart, sA);  // level-0 layer is ready (convert ran on main)
-        cudaStreamWaitEvent(sB, evStart, 0);
-        cudaStreamWaitEvent(sC, evStart, 0);
-    }
-    auto grad_level = [&](cudaStream_t s, int l) {
-        // gradients + smoothed structure-tensor planes (stored as row prefix sums)
+    const bool par = ps.parallel && hk == nullptr;  // per-kernel profiling needs a serial stream
+    cudaStream_t sA = ps.main, sB = par ? ps.b : ps.main;
+    cudaEvent_t evB = ps.ev[MAX_LAYERS + 1];
+    for (int l = 0; l < g.nl; ++l) {
         const LevelGeom& L = g.lv[l];
+        const bool blur = l + 1 < g.nl;
         const int K = pick_K(L.H);
-        IirDev c;
-        iir_dev(4.0, K, krow_of(L.W), &c);  // lucas_kanade.jl:112
+        IirDev c4, c1;
+        iir_dev(4.0, K, krow_of(L.W), &c4);  // lucas_kanade.jl:112
+        iir_dev(sigma, K, krow_of(L.W), &c1);
         ColArgs ca{};
         ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
         ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
-        ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems; ca.inv_n = nullptr;
-        snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
-        dispatch_cols(s, K, true, ca, c);
+        ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems;
+        ca.inv_n = (ctor && blur) ? inv_ny[l] : nullptr;
+        ca.do_blur = blur; ca.o_tmp = plane_off(L, DP_TMP);
+        const int src = (l == 0 && raw) ? (dtype == SLAMKLT_F64 ? 1 : (dtype == SLAMKLT_F32 ? 2 : 3)) : 0;
+        ca.raw = src ? raw : nullptr; ca.raw_ld = g.H0; ca.raw_stride = (size_t)g.H0 * g.W0;
+        snprintf(nm, sizeof(nm), "k_cols_all_L%d", l); mark(hk, nm);
+        dispatch_cols_all(sA, K, src, ca, c4, c1);
+        launches += 1;
+        if (par) { cudaEventRecord(ps.ev[l], sA); cudaStreamWaitEvent(sB, ps.ev[l], 0); }
+        // x pass of the three structure planes + row prefix (side stream)
         RowArgs ra{};
         ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
         ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_RYY); ra.plane_elems = L.plane_elems;
         ra.inv_n = nullptr;
         snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
-        dispatch_rows(s, ra, c, 1);
-        launches += 2;
-    };
-    // stream B: level-0 gradients, concurrent with the blur chain
-    grad_level(sB, 0);
-    if (par) cudaEventRecord(evB, sB);
-    // main: Gaussian pyramid (sigma chain): layer l -> blur l -> layer l+1.  Its y-pass scratch is DP_TMP so that it
-    // does not collide with the gradient stage's T0..T2 of the same level.
-    for (int l = 0; l + 1 < g.nl; ++l) {
-        const LevelGeom& L = g.lv[l];
-        const LevelGeom& N = g.lv[l + 1];
-        const int K = pick_K(L.H);
-        IirDev c;
-        iir_dev(sigma, K, krow_of(L.W), &c);
-        ColArgs ca{};
-        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
-        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_TMP);
-        ca.plane_elems = L.plane_elems; ca.inv_n = ctor ? inv_ny[l] : nullptr;
-        snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
-        dispatch_cols(sA, K, false, ca, c);
-        RowArgs ra{};
-        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 1;
-        ra.zero_border = ctor; ra.o_in0 = plane_off(L, DP_TMP); ra.o_out0 = plane_off(L, DP_BLUR); ra.plane_elems = L.plane_elems;
-        ra.inv_n = ctor ? inv_nx[l] : nullptr;
-        snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
-        dispatch_rows(sA, ra, c, 0);
-        snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
-        dim3 grid((N.H + 127) / 128, N.W, n_frames);
-        k_resize<<<grid, 128, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
-        launches += 3;
-        // stream C: gradients of level l+1 as soon as its layer exists
-        if (par) { cudaEventRecord(ps.ev[l + 1], sA); cudaStreamWaitEvent(sC, ps.ev[l + 1], 0); }
-        grad_level(sC, l + 1);
+        dispatch_rows(sB, ra, c4, 1);
+        launches += 1;
+        if (blur) {
+            const LevelGeom& N = g.lv[l + 1];
+            RowArgs rb{};
+            rb.fs = fs; rb.f0 = f0; rb.n_frames = n_frames; rb.H = L.H; rb.W = L.W; rb.pitch = L.pitch; rb.nplanes = 1;
+            rb.zero_border = ctor; rb.o_in0 = plane_off(L, DP_TMP); rb.o_out0 = plane_off(L, DP_BLUR); rb.plane_elems = L.plane_elems;
+            rb.inv_n = ctor ? inv_nx[l] : nullptr;
+            snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
+            dispatch_rows(sA, rb, c1, 0);
+            snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
+            dim3 grid((N.H + 127) / 128, N.W, n_frames);
+            k_resize<<<grid, 128, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
+            launches += 2;
+        }
     }
     if (par) {
-        cudaEventRecord(evC, sC);
+        cudaEventRecord(evB, sB);
         cudaStreamWaitEvent(sA, evB, 0);
-        cudaStreamWaitEvent(sA, evC, 0);
     }
     return launches;
 }
