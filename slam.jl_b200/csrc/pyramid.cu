@@ -671,10 +671,15 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
             for (int j = 0; j < KRt; ++j)
                 if (x0 + j >= n) x[j] = 0.f;  // the extension does not belong to the sums
         }
-        double acc = 0.0;
+        // chunk totals in fp32 (4 partial sums), scanned across chunks in Float64; inside the chunk the running sum is
+        // fp32 on top of a two-float (hi + lo) copy of the Float64 base, which keeps the conversion pipe (XU) out of the
+        // per-element path.  Errors of the base are common to both ends of a window difference and cancel.
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < KRt; ++j) acc += (double)x[j];
-        sP[ch][rl] = acc;
+        for (int j = 0; j + 3 < KRt; j += 4) { p0 += x[j]; p1 += x[j + 1]; p2 += x[j + 2]; p3 += x[j + 3]; }
+#pragma unroll
+        for (int j = KRt & ~3; j < KRt; ++j) p0 += x[j];
+        sP[ch][rl] = (double)((p0 + p1) + (p2 + p3));
         __syncthreads();
         for (int rr = wid; rr < LR; rr += nwarp) {  // exclusive scan of the chunk totals, lane = chunk
             double t = lane < NC ? sP[lane][rr] : 0.0;
@@ -687,13 +692,15 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
             if (lane < NC) sP[lane][rr] = inc - t;
         }
         __syncthreads();
-        acc = sP[ch][rl];
+        const double base = sP[ch][rl];
+        const float bh = (float)base, bl = (float)(base - (double)bh);
         if (rowok) {
             float* q = row_ptr(out, pitch4, x0 + 1);
+            float local = 0.f;
 #pragma unroll
             for (int j = 0; j < KRt; ++j) {
-                acc += (double)x[j];
-                if (fullc || x0 + j < n) *row_ptr(q, pitch4, j) = (float)acc;
+                local += x[j];
+                if (fullc || x0 + j < n) *row_ptr(q, pitch4, j) = bh + (local + bl);
             }
         }
     }
