@@ -346,13 +346,18 @@ def main():
     else:
         lvl = int(dom_name.rsplit("L", 1)[1]) if "_L" in dom_name else 0
         px = dims[lvl][0] * dims[lvl][1] * N_FRAMES
-        per_px = {"k_cols_grad": 24, "k_rows_struct": 24, "k_cols_blur": 8, "k_rows_blur": 8, "k_resize": 5, "k_convert": 12}
+        per_px = {"k_cols_all": 36 if lvl == 0 else 32, "k_rows_struct": 24, "k_rows_blur": 8, "k_resize": 5, "k_convert": 12}
         key = dom_name.rsplit("_L", 1)[0]
         alg_bytes = per_px.get(key, 8) * px
         alg_note = f"{per_px.get(key, 8)} B/px (reads+writes of that stage) x level-{lvl} pixels x 64"
     achieved = alg_bytes / (dom_ms / 1e3) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "round1_traffic.json")))["dram_bytes_per_launch"].get(dom_name)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                 "algorithmic_bytes_note": alg_note, "ms_per_launch": dom_ms, "peak_source": peak_src}
     # whole-step view: all algorithmic bytes of a step over the step time
     step_bytes = (b_pyr + b_lk) * N_FRAMES
