@@ -99,14 +99,20 @@ void iir_dev(double sigma, int K, int KRr, IirDev* o) {
     for (int i = 0; i < 9; ++i) o->M[i] = (float)M[i];
     const double A[9] = {a[0], a[1], a[2], 1, 0, 0, 0, 1, 0};  // companion matrix of the recursion
     double P[9];
-    for (int j = 0; j < 5; ++j) {
-        mat3_pow(A, K << j, P);
-        for (int i = 0; i < 9; ++i) o->P[j][i] = (float)P[i];
-    }
-    for (int j = 0; j < 5; ++j) {
-        mat3_pow(A, KRr << j, P);
-        for (int i = 0; i < 9; ++i) o->PR[j][i] = (float)P[i];
-    }
+    // the recursion is stable (spectral radius 0.20 at sigma 1, 0.69 at sigma 4), so A^(chunk * 2^j) underflows any fp32
+    // significance after a few doublings: a Kogge-Stone step whose matrix is below 1e-13 cannot change the result
+    auto fill = [&](int chunk, float (*dst)[9]) {
+        int need = 0;
+        for (int j = 0; j < 5; ++j) {
+            mat3_pow(A, chunk << j, P);
+            double mx = 0;
+            for (int i = 0; i < 9; ++i) { dst[j][i] = (float)P[i]; mx = std::fmax(mx, std::fabs(P[i])); }
+            if (mx > 1e-13) need = j + 1;
+        }
+        return need;
+    };
+    o->nsc = fill(K, o->P);
+    o->nsr = fill(KRr, o->PR);
 }
 
 void iir_line_host(double* x, int n, double sigma, double iminus, double iplus) {

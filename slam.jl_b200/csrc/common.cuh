@@ -58,6 +58,7 @@ struct IirDev {
     float M[9];                       // Triggs-Sdika right-boundary matrix, row-major
     float P[5][9];                    // A^(K*2^j), j = 0..4, for the warp scan of the dim-1 kernel
     float PR[5][9];                   // A^(KR*2^j), j = 0..4, for the chunk-carry scan of the dim-2 kernel
+    int nsc, nsr;                     // scan steps actually needed: later powers of A are below 1e-13 and are skipped
 };
 
 struct LKLevel {

@@ -160,6 +160,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     // phase 2: inclusive scan of the chunk states, q_l += A^(K d) q_{l-d}
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
+        if (j >= c.nsc) break;
         const int d = 1 << j;
         float r0[NL], r1[NL], r2[NL];
 #pragma unroll
@@ -213,6 +214,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
+        if (j >= c.nsc) break;
         const int d = 1 << j;
         float r0[NL], r1[NL], r2[NL];
 #pragma unroll
@@ -593,6 +595,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
         if (lane < NC) { q0 = sF[lane][0][rr]; q1 = sF[lane][1][rr]; q2 = sF[lane][2][rr]; }
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
+            if (j >= c.nsr) break;
             const int d = 1 << j;
             float r0 = __shfl_up_sync(FULL, q0, d), r1 = __shfl_up_sync(FULL, q1, d), r2 = __shfl_up_sync(FULL, q2, d);
             if (lane >= d) mat3_acc(c.PR[j], r0, r1, r2, q0, q1, q2);
@@ -632,6 +635,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
         if (lane < NC) { q0 = sB[lane][0][rr]; q1 = sB[lane][1][rr]; q2 = sB[lane][2][rr]; }
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
+            if (j >= c.nsr) break;
             const int d = 1 << j;
             float r0 = __shfl_down_sync(FULL, q0, d), r1 = __shfl_down_sync(FULL, q1, d), r2 = __shfl_down_sync(FULL, q2, d);
             if (lane + d < 32) mat3_acc(c.PR[j], r0, r1, r2, q0, q1, q2);
