@@ -142,6 +142,16 @@ int slamklt_optflow(slamklt_ctx* ctx, const slamklt_pyr* first, const slamklt_py
 int slamklt_fb_track(slamklt_ctx* ctx, const slamklt_pyr* previous, const slamklt_pyr* current, const double* pts_yx,
                      const double* disp_yx, int n, const slamklt_lk_params* p, double* out_pts_yx, uint8_t* status);
 
+/* Tracking part of optical_flow_matching!(map_manager, frame, from, to, stereo) -- map_manager.jl:451-564,
+ * in one launch: keypoints with has_prior[i] != 0 (3-D keypoints whose map point projects into the image) are first
+ * tracked with prior_disp_yx[i] (= (projection - pixel) / 2^levels_3d, map_manager.jl:466,494) on levels_3d levels (the
+ * reference hard-codes 1, map_manager.jl:458); those that fail, and all others, are tracked from a zero displacement on
+ * p->pyramid_levels levels (map_manager.jl:531-551).  status bit0 = tracked, bit1 = forward pass of the deciding attempt ok,
+ * bit2 = tracked by the prior pass.  out_pts_yx[i] is written only where bit1 is set. */
+int slamklt_flow_matching(slamklt_ctx* ctx, const slamklt_pyr* from, const slamklt_pyr* to, const double* pts_yx,
+                          const double* prior_disp_yx, const uint8_t* has_prior, int n, const slamklt_lk_params* p,
+                          int levels_3d, double* out_pts_yx, uint8_t* status);
+
 /* ---- Extractor ------------------------------------------------------------------------- */
 /* detect(e, image, current_points; sigma_mask) -- extractor.jl:63-95.  out_yx: cap pairs of Int64.
  * *n_out receives the number of detected keypoints (no global cap, like the reference). */

@@ -79,7 +79,7 @@ SYMBOLS = [
     "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_profile", "slamklt_profile_report", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
     "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
-    "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
+    "slamklt_flow_matching", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
     "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
     "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
 ]
@@ -113,6 +113,7 @@ def lib():
         L.slamklt_pyr_download.argtypes = [vp, vp, C.c_int, C.c_int, dp]
         L.slamklt_optflow.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), u8p, ip]
         L.slamklt_fb_track.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), dp, u8p]
+        L.slamklt_flow_matching.argtypes = [vp, vp, vp, dp, dp, u8p, C.c_int, C.POINTER(LKParams), C.c_int, dp, u8p]
         L.slamklt_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(DetectParams),
                                      i64p, C.c_int, ip]
         L.slamklt_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -331,6 +332,28 @@ def fb_tracking(previous: LKPyramid, current: LKPyramid, keypoints, displacement
     _ck(lib().slamklt_fb_track(previous.ctx._h, previous._h, current._h, _dp(pts), None if d is None else _dp(d), n,
                                C.byref(p), _dp(out), st.ctypes.data_as(C.POINTER(C.c_uint8))))
     return out, (st & 1).astype(bool), ((st >> 1) & 1).astype(bool)
+
+
+def optical_flow_matching(from_pyramid: LKPyramid, to_pyramid: LKPyramid, pixels, prior_displacement, is_3d, window_size=9,
+                          pyramid_levels=3, pyramid_levels_3d=1, max_distance=1.0, iterations=30, eigenvalue_threshold=1e-4,
+                          eps=1e-2):
+    """Tracking part of optical_flow_matching! (map_manager.jl:451-564) in one launch: 3-D keypoints first with their prior
+    on pyramid_levels_3d levels, failures and 2-D keypoints on pyramid_levels levels from a zero displacement.
+    Returns (new_keypoints, status, tracked_by_prior_pass)."""
+    pts = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 2)
+    n = len(pts)
+    pri = np.ascontiguousarray(prior_displacement, dtype=np.float64).reshape(-1, 2)
+    flg = np.ascontiguousarray(is_3d, dtype=np.uint8).reshape(-1)
+    assert len(pri) == n and len(flg) == n
+    out = np.full((n, 2), np.nan)
+    st = np.zeros(n, dtype=np.uint8)
+    if n == 0:
+        return out, st.astype(bool), st.astype(bool)
+    p = LKParams(iterations, window_size, pyramid_levels, 0, eigenvalue_threshold, eps, float(max_distance))
+    _ck(lib().slamklt_flow_matching(from_pyramid.ctx._h, from_pyramid._h, to_pyramid._h, _dp(pts), _dp(pri),
+                                    flg.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.byref(p), int(pyramid_levels_3d), _dp(out),
+                                    st.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out, (st & 1).astype(bool), ((st >> 2) & 1).astype(bool)
 
 
 class Extractor:

@@ -713,6 +713,56 @@ int slamklt_fb_track(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B,
     return 0;
 }
 
+int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B, const double* pts, const double* prior,
+                          const uint8_t* has_prior, int n, const slamklt_lk_params* p, int levels_3d, double* out_pts, uint8_t* status) {
+    if (!c || !A || !B) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    int r = check_lk(p, A->g.nl, B->g.nl);
+    if (r) return r;
+    if (levels_3d < 0 || !(A->g.nl > levels_3d && B->g.nl > levels_3d)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");
+    if (p->window_size > 11) return fail(SLAMKLT_E_INVALID, "flow_matching supports window_size <= 11");
+    if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
+    if (n == 0) return 0;
+    if (!pts || !prior || !has_prior || !out_pts || !status) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (A->g.H0 != B->g.H0 || A->g.W0 != B->g.W0) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
+    if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if ((r = c->pts.ensure((size_t)n * 16))) return r;
+    if ((r = c->disp.ensure((size_t)n * 16))) return r;
+    if ((r = c->outp.ensure((size_t)n * 16))) return r;
+    if ((r = c->status.ensure((size_t)n))) return r;
+    if ((r = c->cur.ensure((size_t)n))) return r;
+    CK(cudaMemcpyAsync(c->pts.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->disp.p, prior, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->cur.p, has_prior, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += (uint64_t)n * 33;
+    LKArgs a{};
+    a.A = fs_of(A); a.B = fs_of(B); a.offA = 0; a.offB = 0;
+    fill_lk_levels(A->g, &a);
+    a.mode = 2;
+    a.pts = (const double*)c->pts.p; a.disp_in = (const double*)c->disp.p; a.disp_out = nullptr;
+    a.out_pts = (double*)c->outp.p; a.status = (uint8_t*)c->status.p;
+    a.has_prior = (const uint8_t*)c->cur.p; a.levels3d = levels_3d;
+    a.n_per_frame = n; a.n_frames = 1;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters;
+    mark(c->hk(), "k_lk_matching");
+    if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
+    c->launches += 1;
+    CKL();
+    prof_end(c);
+    if ((r = c->h_out.ensure((size_t)n * 16))) return r;
+    CK(cudaMemcpyAsync(c->h_out.p, c->outp.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status, c->status.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += (uint64_t)n * 17;
+    const double* h = (const double*)c->h_out.p;
+    for (int i = 0; i < n; ++i)
+        if (status[i] & 2) { out_pts[2 * i] = h[2 * i]; out_pts[2 * i + 1] = h[2 * i + 1]; }
+    return 0;
+}
+
 // ---- extractor -------------------------------------------------------------------------------
 static int fill_det(const slamklt_detect_params* p, int H, int W, int n_cur, DetArgs* a) {
     if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");

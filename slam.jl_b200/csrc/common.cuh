@@ -69,7 +69,7 @@ struct LKLevel {
 struct LKArgs {
     FrameSet A, B;
     int offA, offB;
-    int nl, mode;  // mode 0 = optflow!, 1 = fb_tracking!
+    int nl, mode;  // mode 0 = optflow!, 1 = fb_tracking!, 2 = optical_flow_matching! (prior pass, then full pass)
     LKLevel lv[MAX_LAYERS];
     const double* pts;
     const double* disp_in;  // nullable
@@ -80,6 +80,8 @@ struct LKArgs {
     int iterations, window, levels, pad_;
     double eig_thr, eps, max_dist;
     unsigned long long* counters;  // [0] window px * iterations, [1] iterations
+    const uint8_t* has_prior;      // mode 2: per point, 1 = 3-D keypoint tracked first with disp_in and levels3d
+    int levels3d, pad2_;
 };
 
 struct DetArgs {

@@ -86,18 +86,25 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
     const int total = a.n_frames * a.n_per_frame;
     if (gw >= total) return;
     const int f = gw / a.n_per_frame;
-    const float* fbA = a.A.frame(a.offA + f);
-    const float* fbB = a.B.frame(a.offB + f);
+    const float* const fbA0 = a.A.frame(a.offA + f);
+    const float* const fbB0 = a.B.frame(a.offB + f);
     const double pty = a.pts[2 * (size_t)gw], ptx = a.pts[2 * (size_t)gw + 1];
     double dy = 0.0, dx = 0.0;
     if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
+    // mode 2 = optical_flow_matching! (map_manager.jl:451-564): keypoints with a prior (3-D keypoints) are first tracked with
+    // that prior on levels3d levels; those that fail, and all others, are tracked from a zero displacement on all levels
+    const bool prior_first = a.mode == 2 && a.has_prior && a.has_prior[gw] != 0;
+    if (a.mode == 2 && !prior_first) { dy = 0.0; dx = 0.0; }
+    int levels_cur = prior_first ? a.levels3d : a.levels;
+    bool second_try = false;
 
     const int w = a.window;
-    const int nstage = a.levels + 1 + (a.mode ? 1 : 0);
     unsigned int wpx = 0, nit = 0;
     double qy = pty, qx = ptx;
     bool ok = true;
     uint8_t result = 0;
+    const float* fbA = fbA0;
+    const float* fbB = fbB0;
 
     const int rgp = lane & 7, cgp = lane >> 3;  // patch row group / column group of this lane
     const int pi0 = rgp * PR, pj0 = cgp * PC;   // first window row / column of the patch
@@ -106,9 +113,11 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
     bool pending = false;
     const int srg = lane % RG, scg = lane / RG;  // staging role of this lane: 16-byte row group / column group
 
+retry:
+    const int nstage = levels_cur + 1 + (a.mode ? 1 : 0);
     for (int s = 0; s < nstage; ++s) {
-        const bool back = s > a.levels;
-        const int lvl = back ? 0 : a.levels - s;
+        const bool back = s > levels_cur;
+        const int lvl = back ? 0 : levels_cur - s;
         if (back) {
             qy = pty + dy; qx = ptx + dx;  // tracker.jl:37-46
             if (lane == 0 && a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
@@ -293,6 +302,21 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
         if (lvl > 0) { dy *= 2.0; dx *= 2.0; }
     }
 
+    if (a.mode != 0 && result != 0 && ok) {
+        // tracker.jl:59-66: the back-tracked point must land within max_distance of the original keypoint
+        const double by = qy + dy, bx = qx + dx;
+        const double ey = pty - by, ex = ptx - bx;
+        if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+    }
+    if (prior_first && !second_try && result != 3) {
+        // the prior pass failed: map_manager.jl:531-536 re-queues the keypoint with the 2-D ones (no prior, all levels)
+        second_try = true;
+        levels_cur = a.levels;
+        dy = 0.0; dx = 0.0; qy = pty; qx = ptx;
+        ok = true; result = 0;
+        fbA = fbA0; fbB = fbB0;
+        goto retry;
+    }
     if (pending) {  // never leave with copies in flight
         if (LK_TMA) mbar_wait(bar, parity); else cp_async_wait_all();
     }
@@ -302,17 +326,11 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
             a.status[gw] = ok ? 1 : 0;
         }
     } else if (lane == 0) {
-        if (result == 0) {
-            if (a.out_pts) {
-                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
-                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
-            }
-        } else if (ok) {
-            const double by = qy + dy, bx = qx + dx;
-            const double ey = pty - by, ex = ptx - bx;
-            if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+        if (result == 0 && a.out_pts) {  // forward pass failed; the reference leaves new_keypoints[i] undefined
+            a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+            a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
         }
-        a.status[gw] = result;
+        a.status[gw] = result | ((prior_first && !second_try && result == 3) ? 4 : 0);  // bit2: tracked by the prior pass
     }
     if (lane == 0 && a.counters) {
         atomicAdd(a.counters, (unsigned long long)wpx);

@@ -125,3 +125,36 @@ def test_invalid_arguments(ctx):
         slamklt.fb_tracking(g, g, np.array([[5.0, 5.0]]), window_size=16)
     with pytest.raises(slamklt.SlamKltError):
         g.update(np.zeros((64, 65)))
+
+
+def test_optical_flow_matching_two_pass(ctx):
+    """the tracking part of optical_flow_matching! (map_manager.jl:451-564) in one launch equals the
+    reference's two fb_tracking! calls (3-D keypoints with a prior on 1 level, then failures + 2-D keypoints on 3 levels)."""
+    fr, aff = synth.make_sequence(4100, 2)
+    f = synth.to_f64(fr)
+    rng = np.random.default_rng(8)
+    pts = synth.random_keypoints(12, 1500, 376, 1241, border=2.0)
+    gt = synth.true_flow(aff, 0, 1, pts)
+    is3d = rng.random(len(pts)) < 0.5
+    prior = 0.5 * (gt - pts) + rng.normal(0, 0.4, pts.shape)
+    bad = is3d & (rng.random(len(pts)) < 0.3)          # wrong map points: prior far off => prior pass fails, retried as 2-D
+    prior[bad] += rng.choice([-6.0, 6.0], size=(bad.sum(), 2))
+    o0, o1 = O.LKPyramid(f[0], 3), O.LKPyramid(f[1], 3)
+    o0.update(f[0]); o1.update(f[1])
+    g0, g1 = slamklt.LKPyramid(ctx, f[0], 3), slamklt.LKPyramid(ctx, f[1], 3)
+    g0.update(f[0]); g1.update(f[1])
+    # reference composition
+    exp_pts = np.full_like(pts, np.nan); exp_st = np.zeros(len(pts), bool); exp_3d = np.zeros(len(pts), bool)
+    i3 = np.flatnonzero(is3d)
+    p3, s3, _ = O.fb_tracking(o0, o1, pts[i3], displacement=prior[i3], window_size=9, pyramid_levels=1, max_distance=1.0)
+    exp_pts[i3[s3]] = p3[s3]; exp_st[i3[s3]] = True; exp_3d[i3[s3]] = True
+    i2 = np.concatenate([np.flatnonzero(~is3d), i3[~s3]])
+    p2, s2, _ = O.fb_tracking(o0, o1, pts[i2], window_size=9, pyramid_levels=3, max_distance=1.0)
+    exp_pts[i2[s2]] = p2[s2]; exp_st[i2[s2]] = True
+    got_pts, got_st, got_3d = slamklt.optical_flow_matching(g0, g1, pts, prior, is3d, window_size=9, pyramid_levels=3,
+                                                            pyramid_levels_3d=1, max_distance=1.0)
+    assert np.mean(got_st == exp_st) >= 0.999 and np.mean(got_3d == exp_3d) >= 0.999
+    both = got_st & exp_st & (got_3d == exp_3d)
+    assert both.sum() > 1000 and exp_3d.sum() > 200 and (i3[~s3]).size > 50
+    d = np.abs(got_pts[both] - exp_pts[both]).max(axis=1)
+    assert np.mean(d < 0.01) >= 0.999 and d.max() < 0.02
