@@ -129,9 +129,10 @@ retry:
         const LKLevel& L = a.lv[lvl];
         const int H = L.H, W = L.W, pitch = L.pitch;
         const unsigned pitch4 = (unsigned)L.pitch * 4u;
-        const double inv = 1.0 / (double)(1 << lvl);
+        const double inv = __longlong_as_double((long long)(1023 - lvl) << 52);  // 2^-lvl exactly, no division
         const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);
         int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
+        const bool interior = py - 1 >= w + 6 && H - py >= w + 6 && px - 1 >= w + 6 && W - px >= w + 6;
         bool setup = true;
         double g00 = 0, g01 = 0, g11 = 0;
         double cy = 0.0, cx = 0.0;
@@ -198,16 +199,23 @@ retry:
                     }
                 }
                 const double ga = (double)warp_sum_f2(syy), gc = (double)warp_sum_f2(sxx), gb = (double)warp_sum_f2(syx);
+                // eigenvalue gate (lucas_kanade.jl:38-46): singular values of the symmetric G = [a b; b c] are Q +- R with
+                // Q = |a+c|/2, R = sqrt(((a-c)/2)^2 + b^2) (utils.jl:5-27 with H = 0), so min(S)/area < thr  <=>  |Q - R| < t,
+                // t = thr*area  <=>  R < Q + t  and  R > Q - t: decided on squares, no sqrt / division on the common path
                 const double E = 0.5 * (ga + gc), F = 0.5 * (ga - gc);
-                const double R = sqrt(F * F + gb * gb), Q = fabs(E);
-                const double s1 = Q + R, s2 = fabs(Q - R);
-                const double min_eig = fmin(s1, s2) / (double)(nrows * ncols);
-                if (min_eig < a.eig_thr) { ok = false; break; }
-                const double tol = 1.4901161193847656e-08;
-                if (s2 > tol) {
+                const double R2 = F * F + gb * gb, Q = fabs(E);
+                const double t = a.eig_thr * (double)(nrows * ncols);
+                const double qp = Q + t, qm = Q - t;
+                if (t > 0.0 && R2 < qp * qp && (qm < 0.0 || R2 > qm * qm)) { ok = false; break; }
+                const double tol = 1.4901161193847656e-08;  // sqrt(eps(Float64)), utils.jl:37
+                bool full_rank = t > tol;  // the gate already guarantees min(S) >= t
+                double R = 0.0;
+                if (!full_rank) { R = sqrt(R2); full_rank = fabs(Q - R) > tol; }
+                if (full_rank) {
                     const double id = 1.0 / (ga * gc - gb * gb);
                     g00 = gc * id; g01 = -gb * id; g11 = ga * id;
                 } else {
+                    // rank-deficient (only reachable with eigenvalue_threshold ~ 0): Moore-Penrose via the eigenvectors
                     g00 = g01 = g11 = 0.0;
                     const double l1 = E + (E >= 0 ? R : -R);
                     if (fabs(l1) > tol) {
@@ -223,14 +231,21 @@ retry:
             if (it >= a.iterations) break;
             const double pcy = (double)py + (dy + cy), pcx = (double)px + (dx + cx);
             const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
-            const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
-            if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
-            const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
-            const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
-            if (nup != up || ndown != down || nleft != left || nright != right) {
-                up = nup; down = ndown; left = nleft; right = nright;
-                setup = true;
-                continue;
+            // fast path: the keypoint sits >= w+6 px inside the level and the estimate is within 3 px of it, so the estimate
+            // lies in the image and get_offsets(point, estimate) is (w, w, w, w) as before: nothing to recompute
+            const bool fast = interior && (unsigned)(fy - py + 3) <= 6u && (unsigned)(fx - px + 3) <= 6u;
+            if (!fast) {
+                // floor / ceil as integers serve both lies_in (1 <= pc <= size <=> floor >= 1 && ceil <= size) and get_offsets:
+                // floor(min(w, min(p, pc) - 1)) = min(w, min(p, floor pc) - 1), floor(min(w, H - max(p, pc))) = min(w, H - max(p, ceil pc))
+                const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
+                if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
+                const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
+                const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
+                if (nup != up || ndown != down || nleft != left || nright != right) {
+                    up = nup; down = ndown; left = nleft; right = nright;
+                    setup = true;
+                    continue;
+                }
             }
             const float wy = (float)(pcy - (double)fy), wx = (float)(pcx - (double)fx);
             const int ay = fy - up - 1, ax = fx - left - 1;  // 0-based first tap row / column
@@ -294,8 +309,10 @@ retry:
             const double ffy = g00 * sby + g01 * sbx, ffx = g01 * sby + g11 * sbx;
             if (fabs(ffy) < eps && fabs(ffx) < eps) break;
             cy += ffy; cx += ffx;
-            const double ny = pcy + ffy, nx = pcx + ffx;
-            if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
+            if (!(fast && fabs(ffy) < 2.0 && fabs(ffx) < 2.0)) {  // on the fast path a step below 2 px cannot leave the image
+                const double ny = pcy + ffy, nx = pcx + ffx;
+                if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
+            }
         }
         if (!ok) break;
         dy += cy; dx += cx;
