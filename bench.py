@@ -302,6 +302,24 @@ def main():
     ctx.sync()
     e2e8_s = time.perf_counter() - t0
 
+    # ---------------- per-frame drop-in path (config[0] shape: one frame at a time through the reference-facing calls)
+    single = None
+    if world == 1:
+        pa, pb = slamklt.LKPyramid(ctx, f64[0], LEVELS), slamklt.LKPyramid(ctx, f64[1], LEVELS)
+        kp1k = kpA[0][:1000]
+        ext1k = slamklt.Extractor(1000, 17, (11, 36), 35)
+        for i in range(3):
+            pb.update(f64[1 + i % 2]); slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST)
+        t_upd, t_trk, t_det = [], [], []
+        for i in range(20):
+            t0 = time.perf_counter(); pb.update(f64[1 + i % 2]); t1 = time.perf_counter()
+            r = slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST); t2 = time.perf_counter()
+            slamklt.detect(ctx, ext1k, f64[1], r[0][r[1]]); t3 = time.perf_counter()
+            t_upd.append(t1 - t0); t_trk.append(t2 - t1); t_det.append(t3 - t2)
+        single = {"update_ms": 1e3 * float(np.median(t_upd)), "fb_tracking_1000kp_ms": 1e3 * float(np.median(t_trk)),
+                  "detect_ms": 1e3 * float(np.median(t_det)),
+                  "note": "host wall clock per call, Float64 host image in, results out (synchronous C ABI calls)"}
+
     # ---------------- max over ranks, gather of tracked-keypoint counts
     t_dev = dev_ms / 1e3
     t_e2e, t_e2e8 = e2e_s, e2e8_s
@@ -386,7 +404,7 @@ def main():
             "e2e_u8_host_frames": {"value": e2e8_val, "unit": UNIT, "ms_per_step": 1e3 * t_e2e8 / args.steps},
             "gpu_launches": int(gpu_launches),
             "roofline": roofline, "step_roofline": step_roof, "lk_fp32": lk_roof, "kernels": kernels,
-            "tracked_ok_per_rank": counts, "tracked_fraction": tracked_ok / (N_FRAMES * N_PTS)}
+            "single_frame_calls": single, "tracked_ok_per_rank": counts, "tracked_fraction": tracked_ok / (N_FRAMES * N_PTS)}
 
     # ---------------- CPU baseline on rank 0, N = 1 only
     if rank == 0 and world == 1 and not args.no_cpu:
