@@ -104,3 +104,34 @@ def test_pyramid_copy_clone_swap(ctx, small_seq):
     assert not empty.has_gradients()
     with pytest.raises(slamklt.SlamKltError):
         slamklt.fb_tracking(empty, a, np.array([[30.0, 30.0]]))
+
+
+def test_two_host_threads_share_a_context(ctx, small_seq):
+    """The mapper task calls into the path concurrently with the front-end task (mapper.jl:51-60); calls on one context are
+    serialised by its mutex and must give the same answers as serial calls."""
+    import threading
+    _, f64, _ = small_seq
+    pts = synth.random_keypoints(123, 200, 120, 200, border=3.0)
+    ref_a = slamklt.LKPyramid(ctx, f64[0], 2); ref_b = slamklt.LKPyramid(ctx, f64[2], 2)
+    ref_b.update(f64[1])  # same build path (update!) as the workers
+    ref = slamklt.fb_tracking(ref_a, ref_b, pts, window_size=9, pyramid_levels=2, max_distance=1.0)
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            a = slamklt.LKPyramid(ctx, f64[0], 2)
+            b = slamklt.LKPyramid(ctx, f64[2], 2)
+            for _ in range(10):
+                b.update(f64[1])
+                results[tid] = slamklt.fb_tracking(a, b, pts, window_size=9, pyramid_levels=2, max_distance=1.0)
+                b.update(f64[2])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    assert not errors
+    for tid in range(4):
+        assert np.array_equal(results[tid][1], ref[1])
+        assert np.array_equal(results[tid][0][ref[1]], ref[0][ref[1]])

@@ -1,0 +1,31 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel family on tiny inputs."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import slamklt
+from slamklt import synth
+
+fr, aff = synth.make_sequence(1, 3, H=75, W=131)
+f = synth.to_f64(fr)
+ctx = slamklt.Context(0)
+for levels, shape in ((2, (75, 131)), (1, (33, 47))):
+    a = slamklt.LKPyramid(ctx, f[0][:shape[0], :shape[1]], levels)
+    b = slamklt.LKPyramid(ctx, fr[1][:shape[0], :shape[1]], levels)
+    b.update(f[1][:shape[0], :shape[1]])
+    pts = np.vstack([synth.random_keypoints(3, 40, shape[0], shape[1], border=1.0), [[1.0, 1.0], [shape[0], shape[1]], [shape[0] - 0.5, 2.0]]])
+    for w in (9, 11, 15):
+        slamklt.fb_tracking(a, b, pts, window_size=w, pyramid_levels=levels, max_distance=1.0)
+    slamklt.optflow(np.zeros_like(pts), a, b, pts, slamklt.LucasKanade(pyramid_levels=levels))
+    slamklt.optical_flow_matching(a, b, pts, np.ones_like(pts), np.arange(len(pts)) % 2, pyramid_levels=levels, pyramid_levels_3d=1)
+    a.plane(1, "Syy"); a.plane(0, "Iyy"); a.plane(0, "Ix")
+e = slamklt.Extractor(100, 8, (3, 4), 35)
+slamklt.detect(ctx, e, f[0], np.array([[10.0, 10.0], [60.0, 100.0]]))
+slamklt.detect(ctx, e, fr[0], np.zeros((0, 2)))
+batch = slamklt.StreamBatch(ctx, 75, 131, 2, 2, 50)
+batch.prime(f[0])
+pts = np.stack([synth.random_keypoints(5 + i, 50, 75, 131, border=2.0) for i in range(2)])
+batch.step(slamklt.StreamBatch.pack_frames(f[1:3]), pts, slamklt.LucasKanade(pyramid_levels=2))
+batch.upload(slamklt.StreamBatch.pack_frames(fr[1:3]), pts); batch.process(slamklt.LucasKanade(pyramid_levels=2)); batch.download()
+batch.detect(e)
+batch.close(); ctx.close()
+print("sanitize_small done")
