@@ -824,15 +824,40 @@ static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, 
 
 // Build the pyramids of n_frames frames.  raw != nullptr: level 0 is read from the staged host image (dtype, compact
 // ld = H0) and the layer plane is written on the way; raw == nullptr: the level-0 layer is already in place.
-// Per level: k_cols_all (main) -> { k_rows blur -> k_resize -> next level (main)  ||  k_rows struct/prefix (side stream) }.
+// Schedule (3 streams): main runs the layer chain -- level 0: k_cols_all (conversion + gradients + blur y pass), then per
+// level k_rows blur -> k_resize -> [k_cols_blur of the next level]; the structure planes of level 0 (k_rows prefix) go to
+// side stream B, and the gradient stages of the coarser levels (k_cols_grad + k_rows prefix) to side stream C as soon as
+// their layer exists, so the small coarse-level kernels overlap the layer chain instead of extending it.
 int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx, const void* raw, int dtype, const Hook* hk) {
     int launches = 0;
     char nm[48];
     const bool ctor = mode == SLAMKLT_MODE_CTOR;
     const bool par = ps.parallel && hk == nullptr;  // per-kernel profiling needs a serial stream
-    cudaStream_t sA = ps.main, sB = par ? ps.b : ps.main;
-    cudaEvent_t evB = ps.ev[MAX_LAYERS + 1];
+    cudaStream_t sA = ps.main, sB = par ? ps.b : ps.main, sC = par ? ps.c : ps.main;
+    cudaEvent_t evB = ps.ev[MAX_LAYERS + 1], evC = ps.ev[MAX_LAYERS + 2];
+
+    auto col_args = [&](int l) {
+        const LevelGeom& L = g.lv[l];
+        ColArgs ca{};
+        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
+        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
+        ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems;
+        ca.o_tmp = plane_off(L, DP_TMP);
+        ca.raw = nullptr; ca.raw_ld = g.H0; ca.raw_stride = (size_t)g.H0 * g.W0;
+        return ca;
+    };
+    auto rows_struct = [&](cudaStream_t s, int l, const IirDev& c4) {
+        const LevelGeom& L = g.lv[l];
+        RowArgs ra{};
+        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
+        ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_RYY); ra.plane_elems = L.plane_elems;
+        ra.inv_n = nullptr;
+        snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
+        dispatch_rows(s, ra, c4, 1);
+        launches += 1;
+    };
+
     for (int l = 0; l < g.nl; ++l) {
         const LevelGeom& L = g.lv[l];
         const bool blur = l + 1 < g.nl;
@@ -840,26 +865,36 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
         IirDev c4, c1;
         iir_dev(4.0, K, krow_of(L.W), &c4);  // lucas_kanade.jl:112
         iir_dev(sigma, K, krow_of(L.W), &c1);
-        ColArgs ca{};
-        ca.fs = fs; ca.f0 = f0; ca.n_frames = n_frames; ca.H = L.H; ca.W = L.W; ca.pitch = L.pitch;
-        ca.zero_border = ctor; ca.o_in = plane_off(L, DP_I); ca.o_out0 = plane_off(L, DP_T0);
-        ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems;
+        ColArgs ca = col_args(l);
         ca.inv_n = (ctor && blur) ? inv_ny[l] : nullptr;
-        ca.do_blur = blur; ca.o_tmp = plane_off(L, DP_TMP);
-        const int src = (l == 0 && raw) ? (dtype == SLAMKLT_F64 ? 1 : (dtype == SLAMKLT_F32 ? 2 : 3)) : 0;
-        ca.raw = src ? raw : nullptr; ca.raw_ld = g.H0; ca.raw_stride = (size_t)g.H0 * g.W0;
-        snprintf(nm, sizeof(nm), "k_cols_all_L%d", l); mark(hk, nm);
-        dispatch_cols_all(sA, K, src, ca, c4, c1);
-        launches += 1;
-        if (par) { cudaEventRecord(ps.ev[l], sA); cudaStreamWaitEvent(sB, ps.ev[l], 0); }
-        // x pass of the three structure planes + row prefix (side stream)
-        RowArgs ra{};
-        ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
-        ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_RYY); ra.plane_elems = L.plane_elems;
-        ra.inv_n = nullptr;
-        snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
-        dispatch_rows(sB, ra, c4, 1);
-        launches += 1;
+        ca.do_blur = blur;
+        if (l == 0 || !par) {
+            // fused column kernel on the main stream
+            const int src = (l == 0 && raw) ? (dtype == SLAMKLT_F64 ? 1 : (dtype == SLAMKLT_F32 ? 2 : 3)) : 0;
+            ca.raw = src ? raw : nullptr;
+            snprintf(nm, sizeof(nm), "k_cols_all_L%d", l); mark(hk, nm);
+            dispatch_cols_all(sA, K, src, ca, c4, c1);
+            launches += 1;
+            if (par) { cudaEventRecord(ps.ev[0], sA); cudaStreamWaitEvent(sB, ps.ev[0], 0); }
+            rows_struct(par ? sB : sA, l, c4);
+        } else {
+            // coarser levels: the layer chain only needs the blur y pass; gradients + structure planes run on stream C
+            cudaEventRecord(ps.ev[l], sA);  // layer l exists (k_resize of level l-1 ran on main)
+            cudaStreamWaitEvent(sC, ps.ev[l], 0);
+            ColArgs cg = ca;
+            cg.inv_n = nullptr;
+            snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
+            dispatch_cols(sC, K, true, cg, c4);
+            launches += 1;
+            rows_struct(sC, l, c4);
+            if (blur) {
+                ColArgs cb = ca;
+                cb.o_out0 = plane_off(L, DP_TMP);
+                snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
+                dispatch_cols(sA, K, false, cb, c1);
+                launches += 1;
+            }
+        }
         if (blur) {
             const LevelGeom& N = g.lv[l + 1];
             RowArgs rb{};
@@ -876,7 +911,9 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
     }
     if (par) {
         cudaEventRecord(evB, sB);
+        cudaEventRecord(evC, sC);
         cudaStreamWaitEvent(sA, evB, 0);
+        cudaStreamWaitEvent(sA, evC, 0);
     }
     return launches;
 }
