@@ -183,7 +183,7 @@ struct slamklt_ctx {
     PyrStreams pyr_streams{};            // build DAG: main + two side streams
     cudaStream_t lk_stream = nullptr;    // tracking of chunk k overlaps the build of chunk k+1
     std::vector<cudaEvent_t> pipe_ev;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::mutex mu;
     unsigned long long* d_counters = nullptr;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -227,7 +227,19 @@ struct slamklt_batch {
     DevBuf staging, img64, pts, outp, status;
     std::vector<slamklt_pyr*> views;
     bool primed = false;
+    cudaEvent_t ev_lk_done = nullptr;  // last tracking kernel that read this batch's slots (recorded on the lk stream)
+    bool lk_pending = false;
 };
+
+// a batch whose last tracking kernel is still in flight on the lk stream must be waited for before the compute stream
+// touches its slots, points or result buffers again
+#define BATCH_WAIT_LK(c, b)                                                     \
+    do {                                                                        \
+        if ((b)->lk_pending) {                                                  \
+            CK(cudaStreamWaitEvent((c)->stream, (b)->ev_lk_done, 0));           \
+            (b)->lk_pending = false;                                            \
+        }                                                                       \
+    } while (0)
 
 // LK reads up to 32 window columns without predicates; the last plane of an allocation needs that much slack
 static const size_t ALLOC_SLACK = 34 * 1100;
@@ -328,6 +340,7 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     c->pyr_streams.parallel = getenv("SLAMKLT_SERIAL_BUILD") == nullptr;
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
     *out = c;
@@ -345,7 +358,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_counters);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_join);
     for (auto e : c->pipe_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->d2h_stream);
@@ -362,6 +375,7 @@ int slamklt_ctx_sync(slamklt_ctx* c) {
     if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->lk_stream));
     return 0;
 }
 
@@ -424,6 +438,9 @@ int slamklt_timer_start(slamklt_ctx* c) {
 int slamklt_timer_stop(slamklt_ctx* c, float* ms) {
     if (!c || !ms) return fail(SLAMKLT_E_INVALID, "NULL argument");
     CK(cudaSetDevice(c->device));
+    // tracking kernels may run on the side stream: the stopwatch ends when both streams are done
+    CK(cudaEventRecord(c->ev_join, c->lk_stream));
+    CK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
@@ -584,6 +601,7 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
     if ((which >= 0 || comp >= 0) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    if (p->parent) BATCH_WAIT_LK(c, p->parent);
     const LevelGeom& L = p->g.lv[level];
     std::vector<float> tmp((size_t)L.H * L.W * (comp >= 0 ? 2 : 1));
     if (which >= 0) {
@@ -638,6 +656,8 @@ static int run_lk_single(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr
                          const slamklt_lk_params* p, int mode) {
     if (A->g.H0 != B->g.H0 || A->g.W0 != B->g.W0) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
     if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    if (A->parent) BATCH_WAIT_LK(c, A->parent);
+    if (B->parent) BATCH_WAIT_LK(c, B->parent);
     int r;
     if ((r = c->pts.ensure((size_t)n * 16))) return r;
     if ((r = c->disp.ensure((size_t)n * 16))) return r;
@@ -874,6 +894,7 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     if ((r = b->outp.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
     if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;
     b->views.resize(b->n_slots, nullptr);
+    CK(cudaEventCreateWithFlags(&b->ev_lk_done, cudaEventDisableTiming));
     *out = b;
     return 0;
 }
@@ -884,7 +905,9 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->lk_stream));
     for (auto* v : b->views) delete v;
+    if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
     b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release();
     cudaFree(b->base);
     delete b;
@@ -897,6 +920,7 @@ int slamklt_batch_prime(slamklt_ctx* c, slamklt_batch* b, const void* img, int d
     if (ld < b->g.H0) return fail(SLAMKLT_E_INVALID, "ld < H");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, b);
     int r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, b->g.H0, b->g.W0);
     if (r) return r;
     r = build_frames(c, fs_of(b), 0, 1, b->g, c->staging.p, dtype, sigma, mode, nullptr);
@@ -915,6 +939,7 @@ int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int
     if (n_pts > 0 && !pts) return fail(SLAMKLT_E_INVALID, "pts is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, b);
     int r = upload_frames(c, b->staging, imgs, dtype, ld, frame_stride_bytes, b->n_frames, b->g.H0, b->g.W0);
     if (r) return r;
     if (n_pts > 0) {
@@ -931,6 +956,7 @@ int slamklt_batch_build(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode
     if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, b);
     return build_frames(c, fs_of(b), 1, b->n_frames, b->g, b->staging.p, b->up_dtype, sigma, mode, nullptr);
 }
 
@@ -942,6 +968,7 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     if (b->n_pts == 0) return 0;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, b);
     LKArgs a{};
     a.A = fs_of(b); a.B = fs_of(b); a.offA = 0; a.offB = 1;
     fill_lk_levels(b->g, &a);
@@ -962,6 +989,7 @@ int slamklt_batch_download(slamklt_ctx* c, slamklt_batch* b, double* out_pts, ui
     if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    if (b->lk_pending) { CK(cudaStreamWaitEvent(c->stream, b->ev_lk_done, 0)); b->lk_pending = false; }
     const size_t n = (size_t)b->n_frames * b->n_pts;
     if (n > 0) {
         if (out_pts) CK(cudaMemcpyAsync(out_pts, b->outp.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -1003,6 +1031,10 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     const bool side_lk = !c->prof_on;  // the per-kernel profiler times one serial stream
     cudaStream_t lks = side_lk ? c->lk_stream : c->stream;
     // order the side streams after everything already queued on the compute stream (staging / slot reuse)
+    if (b->lk_pending) {  // the previous tracking kernel of THIS batch still reads its slots / points / result buffers
+        CK(cudaStreamWaitEvent(c->stream, b->ev_lk_done, 0));
+        b->lk_pending = false;
+    }
     CK(cudaEventRecord(evStart, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, evStart, 0));
     if (side_lk) CK(cudaStreamWaitEvent(c->lk_stream, evStart, 0));
@@ -1058,8 +1090,9 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
             }
         }
     }
-    // later work on the compute stream (next step's builds overwrite these slots) is ordered after the last tracking kernel
-    if (n_pts > 0) CK(cudaStreamWaitEvent(c->stream, evLK[nchunks - 1], 0));
+    // Only work that touches THIS batch again has to wait for its tracking kernels (see lk_pending above and
+    // batch_wait_lk): another batch may build on the compute stream while this one is still being tracked.
+    if (n_pts > 0 && side_lk) { CK(cudaEventRecord(b->ev_lk_done, lks)); b->lk_pending = true; }
     return 0;
 }
 
@@ -1128,6 +1161,7 @@ int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, in
     if (r) return r;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, b);
     const double* d_img;
     if (b->up_dtype == SLAMKLT_F64) d_img = (const double*)b->staging.p;
     else {
