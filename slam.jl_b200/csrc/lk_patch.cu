@@ -280,12 +280,13 @@ retry:
             }
             // ---- prepare_linear_system (lucas_kanade.jl:159-173) on this lane's patch
             const float* tb = &sT[ox + pj0][oy + pi0];
-            float by = 0.f, bx = 0.f;
-            float vprev[PR];  // vertical lerps of the previous tap column
+            float byr[PR], bxr[PR];  // one accumulator pair per patch row: PR independent FFMA chains instead of one
+            float vprev[PR];         // vertical lerps of the previous tap column
 #pragma unroll
             for (int i = 0; i < PR; ++i) {
                 const float t0 = tb[i], t1 = tb[i + 1];
                 vprev[i] = fmaf(wy, t1 - t0, t0);
+                byr[i] = 0.f; bxr[i] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < PC; ++j) {
@@ -297,11 +298,14 @@ retry:
                     const float vcur = fmaf(wy, tcol[i + 1] - tcol[i], tcol[i]);
                     const float val = fmaf(wx, vcur - vprev[i], vprev[i]);
                     const float dI = tI[i][j] - val;
-                    by = fmaf(dI, tIy[i][j], by);
-                    bx = fmaf(dI, tIx[i][j], bx);
+                    byr[i] = fmaf(dI, tIy[i][j], byr[i]);
+                    bxr[i] = fmaf(dI, tIx[i][j], bxr[i]);
                     vprev[i] = vcur;
                 }
             }
+            float by = byr[0], bx = bxr[0];
+#pragma unroll
+            for (int i = 1; i < PR; ++i) { by += byr[i]; bx += bxr[i]; }
             const double sby = (double)warp_sum_f2(by), sbx = (double)warp_sum_f2(bx);
             wpx += (unsigned)(nrows * ncols);
             nit += 1;
