@@ -481,13 +481,14 @@ static void shi_tomasi_cell(const double* cell, int ld, int h, int w, double* R,
 #undef CP
     for (int x = 0; x < w; ++x)
         for (int y = 0; y < h; ++y) {
+            /* meancovs: imfilter with the dense kernel (1/9) * ones(3,3): products accumulated tap by tap [3P] */
+            const double k9 = 1.0 / 9.0;
             double a = 0, b = 0, c = 0;
             for (int dx = -1; dx <= 1; ++dx)
                 for (int dy = -1; dy <= 1; ++dy) {
                     size_t i = clampi(y + dy, 0, h - 1) + (size_t)clampi(x + dx, 0, w - 1) * h;
-                    a += gyy[i]; b += gyx[i]; c += gxx[i];
+                    a += k9 * gyy[i]; b += k9 * gyx[i]; c += k9 * gxx[i];
                 }
-            a /= 9.0; b /= 9.0; c /= 9.0;
             R[y + (size_t)x * h] = ((a + c) - sqrt((a - c) * (a - c) + 4.0 * b * b)) / 2.0;
         }
 }

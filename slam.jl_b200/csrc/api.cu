@@ -830,14 +830,11 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_fra
     c->launches += launch_detect(c->stream, a, c->hk());
     CKL();
     prof_end(c);
+    // one copy for the counts and one for the whole [frame][cap][2] block (entries past n_out[f] are unspecified)
     CK(cudaMemcpyAsync(n_out, c->det_n.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cap > 0) CK(cudaMemcpyAsync(out_yx, c->det_out.p, (size_t)n_frames * cap * 16, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (int f = 0; f < n_frames; ++f) {
-        const int n = n_out[f] < cap ? n_out[f] : cap;
-        if (n > 0) CK(cudaMemcpyAsync(out_yx + (size_t)f * cap * 2, (char*)c->det_out.p + (size_t)f * cap * 16, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
-        c->d2h += (uint64_t)n * 16 + 4;
-    }
-    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += (uint64_t)n_frames * (4 + (uint64_t)cap * 16);
     return 0;
 }
 

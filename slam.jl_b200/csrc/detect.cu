@@ -11,20 +11,40 @@
 namespace sk {
 
 constexpr int DET_THREADS = 256;
-constexpr int MAX_NEAR = 1024;  // current points kept in shared memory per cell
+constexpr int MAX_NEAR = 512;  // current points kept in shared memory per cell (more => slow path over the global list)
 
-size_t detect_smem_bytes(int cs, int hw) {
-    const size_t cell = (size_t)cs * cs;
-    const size_t reg = (size_t)(cs + 2 * hw) * (cs + 2 * hw);
-    size_t b = 0;
-    b += 5 * cell * sizeof(double);               // img, gyy, gyx, gxx, R
-    b += (size_t)cs * (cs + 2 * hw) * sizeof(double);  // tmp after the y pass of the mask blur
-    b += reg * sizeof(float);                     // m0
-    b += cell * sizeof(double) + cell * sizeof(int);  // candidates
-    b += MAX_NEAR * 2 * sizeof(int);
-    b += 64 * sizeof(int);
-    return b;
+// Shared-memory plan of one cell (doubles unless noted), identical on host and device:
+//   A: padded plane, image * mask first, response R later            (P*P)
+//   B: three padded product planes gyy, gyx, gxx; during the mask phase the same bytes hold the y-filtered mask
+//      (cs*(cs+2hw) doubles) followed by the binary mask ((cs+2hw)^2 floats)
+//   C: candidates (response double + index int, at most ceil(cs/2)^2 strict maxima); during the mask phase the list of
+//      nearby current points (2*MAX_NEAR ints)
+//   D: 64 ints of scan scratch
+struct DetSmem { size_t oA, oB, oTmp, oM0, oCandR, oCandI, oNear, oMisc, total; };
+__host__ __device__ inline DetSmem det_smem_plan(int cs, int hw) {
+    const size_t P = cs + 2, pad = P * P, rw = cs + 2 * hw;
+    const size_t nc = (size_t)((cs + 1) / 2) * ((cs + 1) / 2);
+    DetSmem m;
+    m.oA = 0;
+    m.oB = pad * 8;
+    m.oTmp = m.oB;
+    m.oM0 = m.oTmp + (size_t)cs * rw * 8;
+    size_t endB = m.oB + 3 * pad * 8;
+    const size_t endMask = m.oM0 + rw * rw * 4;
+    if (endMask > endB) endB = endMask;
+    endB = (endB + 15) & ~(size_t)15;
+    m.oCandR = endB;
+    m.oCandI = m.oCandR + nc * 8;
+    m.oNear = m.oCandR;
+    size_t endC = m.oCandI + nc * 4;
+    const size_t endNear = m.oNear + 2 * (size_t)MAX_NEAR * 4;
+    if (endNear > endC) endC = endNear;
+    m.oMisc = (endC + 15) & ~(size_t)15;
+    m.total = m.oMisc + 64 * 4;
+    return m;
 }
+
+size_t detect_smem_bytes(int cs, int hw) { return det_smem_plan(cs, hw).total; }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -50,6 +70,13 @@ __device__ int block_excl_scan(int v, int* s_warp, int& total) {
     return base + inc - v;
 }
 
+// i -> (y, x) with i = y + x*h, exact for i*h < 2^20 (h <= 64): one multiply and a shift instead of an integer division
+struct DivH {
+    unsigned magic; int h;
+    __device__ DivH(int h_) : magic((1u << 20) / (unsigned)h_ + 1u), h(h_) {}
+    __device__ __forceinline__ void split(int i, int& y, int& x) const { x = (int)(((unsigned)i * magic) >> 20); y = i - x * h; }
+};
+
 __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cs = a.cs, hw = a.hw;
@@ -62,23 +89,29 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
     int* cnt_out = a.cell_cnt + (size_t)f * gridDim.x + cell_id;
     if (h <= 0 || w <= 0) { if (threadIdx.x == 0) *cnt_out = 0; return; }
 
-    const size_t cell = (size_t)cs * cs;
-    double* s_img = (double*)smem_raw;
-    double* s_gyy = s_img + cell;
-    double* s_gyx = s_gyy + cell;
-    double* s_gxx = s_gyx + cell;
-    double* s_R = s_gxx + cell;
-    double* s_tmp = s_R + cell;
-    double* s_candr = s_tmp + (size_t)cs * (cs + 2 * hw);
-    float* s_m0 = (float*)(s_candr + cell);
-    int* s_candi = (int*)(s_m0 + (size_t)(cs + 2 * hw) * (cs + 2 * hw));
-    int* s_near = s_candi + cell;
-    int* s_misc = s_near + 2 * MAX_NEAR;  // [0] near count, [1..8] warp scan scratch
+    // padded planes: element (y, x) of the cell lives at (y+1) + (x+1)*P; the halo carries the replicate border of the
+    // CELL (Images.shi_tomasi runs on the cell sub-image) so that the stencils below need no clamps
+    const int P = cs + 2;
+    const size_t pad = (size_t)P * P;
+    const DetSmem sm = det_smem_plan(cs, hw);
+    double* s_img = (double*)(smem_raw + sm.oA);   // later: the response plane
+    double* s_R = s_img;
+    double* s_gyy = (double*)(smem_raw + sm.oB);
+    double* s_gyx = s_gyy + pad;
+    double* s_gxx = s_gyx + pad;
+    double* s_tmp = (double*)(smem_raw + sm.oTmp);  // mask phase only (aliases the product planes)
+    float* s_m0 = (float*)(smem_raw + sm.oM0);      // mask phase only
+    double* s_candr = (double*)(smem_raw + sm.oCandR);
+    int* s_candi = (int*)(smem_raw + sm.oCandI);
+    int* s_near = (int*)(smem_raw + sm.oNear);      // mask phase only (aliases the candidates)
+    int* s_misc = (int*)(smem_raw + sm.oMisc);      // [0] near count, [1..8] warp scan scratch
 
     const double* img = a.img + (size_t)f * H * W;
     const int tid = threadIdx.x;
+    const DivH dh(h);
+    const int npx = h * w;
 
-    // ---- image * mask (extractor.jl:66-71) ---------------------------------------------------
+    // ---- image * mask (extractor.jl:66-71) into the padded tile ---------------------------------
     const bool masked = a.n_cur > 0;
     if (masked) {
         const double* cur = a.cur + (size_t)f * a.n_cur * 2;
@@ -97,9 +130,11 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         const int n_near = s_misc[0];
         const int rh = h + 2 * hw, rw = w + 2 * hw;
         const int r2 = a.radius * a.radius;
+        const DivH drh(rh);
         // binary mask on the halo region; coordinates clamped to the image (replicate border of the blur)
         for (int i = tid; i < rh * rw; i += DET_THREADS) {
-            const int yy = i % rh, xx = i / rh;
+            int yy, xx;
+            drh.split(i, yy, xx);
             const int Y = clampi(y0 - hw + yy, 0, H - 1) + 1, X = clampi(x0 - hw + xx, 0, W - 1) + 1;  // 1-based
             float m = 1.f;
             if (n_near <= MAX_NEAR) {
@@ -119,76 +154,145 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         if (hw > 0) {
             // y pass -> s_tmp[h][rw]
             for (int i = tid; i < h * rw; i += DET_THREADS) {
-                const int y = i % h, xx = i / h;
+                int y, xx;
+                dh.split(i, y, xx);
+                const float* mp = s_m0 + y + xx * rh;
                 double acc = 0.0;
-                for (int t = 0; t <= 2 * hw; ++t) acc += a.kw[t] * (double)s_m0[(y + t) + xx * rh];
+                for (int t = 0; t <= 2 * hw; ++t) acc += a.kw[t] * (double)mp[t];
                 s_tmp[i] = acc;
             }
             __syncthreads();
-            for (int i = tid; i < h * w; i += DET_THREADS) {
-                const int y = i % h, x = i / h;
+            for (int i = tid; i < npx; i += DET_THREADS) {
+                int y, x;
+                dh.split(i, y, x);
+                const double* tp = s_tmp + y + x * h;
                 double acc = 0.0;
-                for (int t = 0; t <= 2 * hw; ++t) acc += a.kw[t] * s_tmp[y + (x + t) * h];
-                s_img[i] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * acc;
+                for (int t = 0; t <= 2 * hw; ++t) acc += a.kw[t] * tp[t * h];
+                s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * acc;
             }
         } else {
-            for (int i = tid; i < h * w; i += DET_THREADS) {
-                const int y = i % h, x = i / h;
-                s_img[i] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * (double)s_m0[i];
+            for (int i = tid; i < npx; i += DET_THREADS) {
+                int y, x;
+                dh.split(i, y, x);
+                s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * (double)s_m0[i];
             }
         }
     } else {
-        for (int i = tid; i < h * w; i += DET_THREADS) {
-            const int y = i % h, x = i / h;
-            s_img[i] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H];
+        for (int i = tid; i < npx; i += DET_THREADS) {
+            int y, x;
+            dh.split(i, y, x);
+            s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H];
         }
     }
     __syncthreads();
+    // replicate halo of a padded plane: rows first (x in 1..w), then full columns including the corners
+    auto fill_halo = [&](double* pl) {
+        for (int x = tid; x < w; x += DET_THREADS) {
+            pl[0 + (x + 1) * P] = pl[1 + (x + 1) * P];
+            pl[(h + 1) + (x + 1) * P] = pl[h + (x + 1) * P];
+        }
+        __syncthreads();
+        for (int y = tid; y < h + 2; y += DET_THREADS) {
+            pl[y] = pl[y + P];
+            pl[y + (w + 1) * P] = pl[y + w * P];
+        }
+        __syncthreads();
+    };
+    fill_halo(s_img);
 
     // ---- Shi-Tomasi response on the cell sub-image (replicate border at the cell edge) --------
-#define CP(yy, xx) s_img[clampi(yy, 0, h - 1) + clampi(xx, 0, w - 1) * h]
-    for (int i = tid; i < h * w; i += DET_THREADS) {
-        const int y = i % h, x = i / h;
-        const double g_y = ((CP(y + 1, x - 1) - CP(y - 1, x - 1)) + 2.0 * (CP(y + 1, x) - CP(y - 1, x)) + (CP(y + 1, x + 1) - CP(y - 1, x + 1))) / 8.0;
-        const double g_x = ((CP(y - 1, x + 1) - CP(y - 1, x - 1)) + 2.0 * (CP(y, x + 1) - CP(y, x - 1)) + (CP(y + 1, x + 1) - CP(y + 1, x - 1))) / 8.0;
-        s_gyy[i] = g_y * g_y; s_gyx[i] = g_y * g_x; s_gxx[i] = g_x * g_x;
-    }
-#undef CP
-    __syncthreads();
-    for (int i = tid; i < h * w; i += DET_THREADS) {
-        const int y = i % h, x = i / h;
-        double sa = 0.0, sb = 0.0, sc = 0.0;
-        for (int dx = -1; dx <= 1; ++dx)
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int j = clampi(y + dy, 0, h - 1) + clampi(x + dx, 0, w - 1) * h;
-                sa += s_gyy[j]; sb += s_gyx[j]; sc += s_gxx[j];
+    // NPT independent pixels per thread and round are unrolled together: the Float64 chains of one pixel are short on ILP
+    constexpr int NPT = 5;
+    for (int base = 0; base < npx; base += DET_THREADS * NPT) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int i = base + tid + k * DET_THREADS;
+            if (i < npx) {
+                int y, x;
+                dh.split(i, y, x);
+                const double* c = s_img + (y + 1) + (x + 1) * P;  // centre
+                const double mm = c[-1 - P], m0 = c[-P], mp = c[1 - P];   // column x-1: rows y-1, y, y+1
+                const double zm = c[-1], zp = c[1];                         // column x
+                const double pm = c[-1 + P], p0 = c[P], pp = c[1 + P];     // column x+1
+                const double g_y = ((mp - mm) + 2.0 * (zp - zm) + (pp - pm)) / 8.0;
+                const double g_x = ((pm - mm) + 2.0 * (p0 - m0) + (pp - mp)) / 8.0;
+                const int o = (y + 1) + (x + 1) * P;
+                s_gyy[o] = g_y * g_y; s_gyx[o] = g_y * g_x; s_gxx[o] = g_x * g_x;
             }
-        sa /= 9.0; sb /= 9.0; sc /= 9.0;
-        s_R[i] = ((sa + sc) - sqrt((sa - sc) * (sa - sc) + 4.0 * sb * sb)) / 2.0;
+        }
+    }
+    __syncthreads();
+    // the three product planes share the halo fill loops
+    for (int x = tid; x < w; x += DET_THREADS) {
+        const int t = (x + 1) * P;
+        s_gyy[t] = s_gyy[1 + t]; s_gyy[h + 1 + t] = s_gyy[h + t];
+        s_gyx[t] = s_gyx[1 + t]; s_gyx[h + 1 + t] = s_gyx[h + t];
+        s_gxx[t] = s_gxx[1 + t]; s_gxx[h + 1 + t] = s_gxx[h + t];
+    }
+    __syncthreads();
+    for (int y = tid; y < h + 2; y += DET_THREADS) {
+        s_gyy[y] = s_gyy[y + P]; s_gyy[y + (w + 1) * P] = s_gyy[y + w * P];
+        s_gyx[y] = s_gyx[y + P]; s_gyx[y + (w + 1) * P] = s_gyx[y + w * P];
+        s_gxx[y] = s_gxx[y + P]; s_gxx[y + (w + 1) * P] = s_gxx[y + w * P];
+    }
+    // R halo = -inf so that out-of-cell neighbours never block a maximum
+    for (int t = tid; t < 2 * (w + 2) + 2 * h; t += DET_THREADS) {
+        int yy, xx;
+        if (t < w + 2) { yy = 0; xx = t; }
+        else if (t < 2 * (w + 2)) { yy = h + 1; xx = t - (w + 2); }
+        else if (t < 2 * (w + 2) + h) { yy = t - 2 * (w + 2) + 1; xx = 0; }
+        else { yy = t - 2 * (w + 2) - h + 1; xx = w + 1; }
+        s_R[yy + xx * P] = -__longlong_as_double(0x7ff0000000000000LL);
+    }
+    __syncthreads();
+    const double k9 = 1.0 / 9.0;  // the 3x3 mean is imfilter with a (1/9)-valued kernel: products accumulated tap by tap
+    for (int base = 0; base < npx; base += DET_THREADS * NPT) {
+#pragma unroll
+        for (int k = 0; k < NPT; ++k) {
+            const int i = base + tid + k * DET_THREADS;
+            if (i < npx) {
+                int y, x;
+                dh.split(i, y, x);
+                const int o = (y + 1) + (x + 1) * P;
+                double sa = 0.0, sb = 0.0, sc = 0.0;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int j = o + dy + dx * P;
+                        sa += k9 * s_gyy[j]; sb += k9 * s_gyx[j]; sc += k9 * s_gxx[j];
+                    }
+                s_R[o] = ((sa + sc) - sqrt((sa - sc) * (sa - sc) + 4.0 * sb * sb)) / 2.0;
+            }
+        }
     }
     __syncthreads();
 
     // ---- strict 3x3 local maxima, enumerated column-major (findlocalmaxima) -------------------
     int n_cand = 0;
-    for (int base = 0; base < h * w; base += DET_THREADS) {
-        const int i = base + tid;
-        int ismax = 0;
-        if (i < h * w) {
-            const int y = i % h, x = i / h;
-            const double r = s_R[i];
-            ismax = 1;
-            for (int dx = -1; dx <= 1; ++dx)
-                for (int dy = -1; dy <= 1; ++dy) {
-                    if (!dx && !dy) continue;
-                    const int yy = y + dy, xx = x + dx;
-                    if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-                    if (!(s_R[yy + xx * h] < r)) ismax = 0;
-                }
+    {
+        const int PT = (npx + DET_THREADS - 1) / DET_THREADS;  // contiguous pixels per thread => one block scan keeps the order
+        const int i0 = tid * PT, i1 = min(npx, i0 + PT);
+        unsigned mask = 0;  // PT <= 16 for cells up to 64 x 64
+        for (int i = i0; i < i1; ++i) {
+            int y, x;
+            dh.split(i, y, x);
+            const double* c = s_R + (y + 1) + (x + 1) * P;
+            const double r = c[0];
+            const int ismax = (c[-1 - P] < r) & (c[-P] < r) & (c[1 - P] < r) & (c[-1] < r) & (c[1] < r) & (c[-1 + P] < r) & (c[P] < r) & (c[1 + P] < r);
+            mask |= (unsigned)ismax << (i - i0);
         }
         int tot;
-        const int pos = block_excl_scan(ismax, s_misc + 1, tot);
-        if (ismax) { s_candr[n_cand + pos] = s_R[i]; s_candi[n_cand + pos] = i; }
-        n_cand += tot;
+        int pos = block_excl_scan(__popc(mask), s_misc + 1, tot);
+        for (int i = i0; i < i1; ++i)
+            if (mask >> (i - i0) & 1u) {
+                int y, x;
+                dh.split(i, y, x);
+                s_candr[pos] = s_R[(y + 1) + (x + 1) * P];
+                s_candi[pos] = i;
+                ++pos;
+            }
+        n_cand = tot;
     }
     __syncthreads();
 
@@ -210,9 +314,10 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         int tot;
         const int pos = block_excl_scan(sel, s_misc + 1, tot);
         if (sel && n_sel + pos < a.slots) {
-            const int idx = s_candi[i];
-            out[2 * (n_sel + pos)] = (int64_t)(idx % h) + 1 + y0;
-            out[2 * (n_sel + pos) + 1] = (int64_t)(idx / h) + 1 + x0;
+            int y, x;
+            dh.split(s_candi[i], y, x);
+            out[2 * (n_sel + pos)] = (int64_t)y + 1 + y0;
+            out[2 * (n_sel + pos) + 1] = (int64_t)x + 1 + x0;
         }
         n_sel += tot;
     }
