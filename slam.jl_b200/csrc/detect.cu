@@ -16,7 +16,7 @@ constexpr int MAX_NEAR = 512;  // current points kept in shared memory per cell 
 // Shared-memory plan of one cell (doubles unless noted), identical on host and device:
 //   A: padded plane, image * mask first, response R later            (P*P)
 //   B: three padded product planes gyy, gyx, gxx; during the mask phase the same bytes hold the y-filtered mask
-//      (cs*(cs+2hw) doubles) followed by the binary mask ((cs+2hw)^2 floats)
+//      (cs*(cs+2hw) doubles) followed by the binary mask ((cs+2hw)^2 bytes)
 //   C: candidates (response double + index int, at most ceil(cs/2)^2 strict maxima); during the mask phase the list of
 //      nearby current points (2*MAX_NEAR ints)
 //   D: 64 ints of scan scratch
@@ -30,7 +30,7 @@ __host__ __device__ inline DetSmem det_smem_plan(int cs, int hw) {
     m.oTmp = m.oB;
     m.oM0 = m.oTmp + (size_t)cs * rw * 8;
     size_t endB = m.oB + 3 * pad * 8;
-    const size_t endMask = m.oM0 + rw * rw * 4;
+    const size_t endMask = m.oM0 + rw * rw;
     if (endMask > endB) endB = endMask;
     endB = (endB + 15) & ~(size_t)15;
     m.oCandR = endB;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
     double* s_gyx = s_gyy + pad;
     double* s_gxx = s_gyx + pad;
     double* s_tmp = (double*)(smem_raw + sm.oTmp);  // mask phase only (aliases the product planes)
-    float* s_m0 = (float*)(smem_raw + sm.oM0);      // mask phase only
+    unsigned char* s_m0 = (unsigned char*)(smem_raw + sm.oM0);  // mask phase only: binary mask, 1 byte per pixel
     double* s_candr = (double*)(smem_raw + sm.oCandR);
     int* s_candi = (int*)(smem_raw + sm.oCandI);
     int* s_near = (int*)(smem_raw + sm.oNear);      // mask phase only (aliases the candidates)
@@ -132,23 +132,44 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         const int r2 = a.radius * a.radius;
         const DivH drh(rh);
         // binary mask on the halo region; coordinates clamped to the image (replicate border of the blur)
-        for (int i = tid; i < rh * rw; i += DET_THREADS) {
-            int yy, xx;
-            drh.split(i, yy, xx);
-            const int Y = clampi(y0 - hw + yy, 0, H - 1) + 1, X = clampi(x0 - hw + xx, 0, W - 1) + 1;  // 1-based
-            float m = 1.f;
-            if (n_near <= MAX_NEAR) {
-                for (int k = 0; k < n_near; ++k) {
-                    const int dy = Y - s_near[2 * k], dx = X - s_near[2 * k + 1];
-                    if (dy * dy + dx * dx <= r2) { m = 0.f; break; }
-                }
-            } else {
-                for (int k = 0; k < a.n_cur; ++k) {
-                    const int dy = Y - (int)rint(cur[2 * k]), dx = X - (int)rint(cur[2 * k + 1]);
-                    if (dy * dy + dx * dx <= r2) { m = 0.f; break; }
-                }
+        const bool inner = y0 - hw >= 0 && y1 + hw <= H && x0 - hw >= 0 && x1 + hw <= W && n_near <= MAX_NEAR;
+        if (inner) {
+            // no clamping inside the image: rasterise each nearby disc row by row instead of testing every pixel against
+            // every point (get_mask + ImageDraw circle, extractor.jl:116-122)
+            for (int i = tid; i < rh * rw; i += DET_THREADS) s_m0[i] = 1;
+            __syncthreads();
+            const int rows = 2 * a.radius + 1;
+            for (int it = tid; it < n_near * rows; it += DET_THREADS) {
+                const int k = it / rows, dy = it - k * rows - a.radius;
+                const int yy = s_near[2 * k] + dy - 1 - (y0 - hw);  // region row of image row cy + dy (1-based -> 0-based)
+                if (yy < 0 || yy >= rh) continue;
+                const int rem = r2 - dy * dy;
+                int sx = (int)sqrtf((float)rem);
+                while (sx * sx > rem) --sx;
+                while ((sx + 1) * (sx + 1) <= rem) ++sx;
+                const int xc = s_near[2 * k + 1] - 1 - (x0 - hw);
+                const int xa = max(xc - sx, 0), xb = min(xc + sx, rw - 1);
+                for (int xx = xa; xx <= xb; ++xx) s_m0[yy + xx * rh] = 0;
             }
-            s_m0[i] = m;
+        } else {
+            for (int i = tid; i < rh * rw; i += DET_THREADS) {
+                int yy, xx;
+                drh.split(i, yy, xx);
+                const int Y = clampi(y0 - hw + yy, 0, H - 1) + 1, X = clampi(x0 - hw + xx, 0, W - 1) + 1;  // 1-based
+                unsigned char m = 1;
+                if (n_near <= MAX_NEAR) {
+                    for (int k = 0; k < n_near; ++k) {
+                        const int dy = Y - s_near[2 * k], dx = X - s_near[2 * k + 1];
+                        if (dy * dy + dx * dx <= r2) { m = 0; break; }
+                    }
+                } else {
+                    for (int k = 0; k < a.n_cur; ++k) {
+                        const int dy = Y - (int)rint(cur[2 * k]), dx = X - (int)rint(cur[2 * k + 1]);
+                        if (dy * dy + dx * dx <= r2) { m = 0; break; }
+                    }
+                }
+                s_m0[i] = m;
+            }
         }
         __syncthreads();
         if (hw > 0) {
@@ -156,9 +177,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
             for (int i = tid; i < h * rw; i += DET_THREADS) {
                 int y, xx;
                 dh.split(i, y, xx);
-                const float* mp = s_m0 + y + xx * rh;
+                const unsigned char* mp = s_m0 + y + xx * rh;
                 double acc = 0.0;
-                for (int t = 0; t <= 2 * hw; ++t) acc += a.kw[t] * (double)mp[t];
+                for (int t = 0; t <= 2 * hw; ++t) acc += mp[t] ? a.kw[t] : 0.0;  // == kw[t] * mask bit for bit (mask is exactly 0 or 1)
                 s_tmp[i] = acc;
             }
             __syncthreads();
@@ -174,7 +195,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
             for (int i = tid; i < npx; i += DET_THREADS) {
                 int y, x;
                 dh.split(i, y, x);
-                s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * (double)s_m0[i];
+                s_img[(y + 1) + (x + 1) * P] = s_m0[i] ? img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] : img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * 0.0;
             }
         }
     } else {
