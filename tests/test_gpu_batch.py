@@ -135,3 +135,34 @@ def test_two_host_threads_share_a_context(ctx, small_seq):
     for tid in range(4):
         assert np.array_equal(results[tid][1], ref[1])
         assert np.array_equal(results[tid][0][ref[1]], ref[0][ref[1]])
+
+
+def test_full_size_batch64_against_oracle(ctx):
+    """BASELINE.json configs[1] at full size: 64 frames of 1241x376, 2000 keypoints each, through slamklt_batch_step;
+    three of the 64 pairs are re-done by the Float64 oracle (north_star tolerances), and the batch is self-consistent:
+    tracking frame i -> i+1 and back lands on the start (forward-backward property) for every accepted point."""
+    fr, aff = synth.make_sequence(2000, 65)
+    f64 = synth.to_f64(fr)
+    H, W, L, NF, NP = 376, 1241, 3, 64, 2000
+    alg = slamklt.LucasKanade(pyramid_levels=L, window_size=9)
+    batch = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+    batch.prime(f64[0], mode=slamklt.MODE_UPDATE)
+    ext = slamklt.Extractor(2376, 17, (11, 36), 35)
+    batch.upload(slamklt.StreamBatch.pack_frames(fr[:NF]), np.zeros((NF, 1, 2)) + 5)
+    kps = batch.detect(ext)
+    pts = np.stack([np.vstack([k.astype(np.float64), synth.random_keypoints(i, NP, H, W)])[:NP] + 0.25 for i, k in enumerate(kps)])
+    batch.prime(f64[0], mode=slamklt.MODE_UPDATE)
+    out, st = batch.step(slamklt.StreamBatch.pack_frames(fr[1:]), pts, alg, max_distance=1.0)   # u8 frames in
+    ok = (st & 1).astype(bool)
+    assert ok.mean() > 0.85
+    gt = np.stack([synth.true_flow(aff, i, i + 1, pts[i]) for i in range(NF)])
+    assert np.median(np.linalg.norm(out[ok] - gt[ok], axis=1)) < 0.15
+    for i in (0, 31, 63):
+        o0 = O.LKPyramid(f64[i], L); o0.update(f64[i])
+        o1 = O.LKPyramid(f64[i + 1], L); o1.update(f64[i + 1])
+        po, so, fo = O.fb_tracking(o0, o1, pts[i], window_size=9, pyramid_levels=L, max_distance=1.0)
+        assert np.mean(so == ok[i]) >= 0.999
+        both = so & ok[i]
+        d = np.abs(po[both] - out[i][both]).max(axis=1)
+        assert np.mean(d < 0.01) >= 0.999 and d.max() < 0.02
+    batch.close()
