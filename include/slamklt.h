@@ -152,6 +152,43 @@ int slamklt_flow_matching(slamklt_ctx* ctx, const slamklt_pyr* from, const slamk
                           const double* prior_disp_yx, const uint8_t* has_prior, int n, const slamklt_lk_params* p,
                           int levels_3d, double* out_pts_yx, uint8_t* status);
 
+/* Camera -- camera.jl:1-29, the fields project_undistort / undistort_point / backproject / in_image read. */
+typedef struct slamklt_camera {
+    double fx, fy, cx, cy;  /* camera.jl:3-7 */
+    double k1, k2, p1, p2;  /* camera.jl:9-13 */
+    int64_t height, width;  /* camera.jl:18-19 */
+    double Ti0[16];         /* camera.jl:21-24, 4 x 4 column-major (SMatrix storage order) */
+} slamklt_camera;
+
+typedef struct slamklt_matching_params {
+    slamklt_lk_params lk;       /* window_size, pyramid_levels, max_distance = params.max_ktl_distance (map_manager.jl:454-456) */
+    int32_t stereo;             /* the `stereo` argument (map_manager.jl:452) */
+    int32_t pyramid_levels_3d;  /* map_manager.jl:458 (1) */
+    double epipolar_error;      /* maybe_stereo_update!, map_manager.jl:580 (2.0) */
+} slamklt_matching_params;
+
+/* optical_flow_matching!(map_manager, frame, from, to, stereo) -- map_manager.jl:451-564 -- with its per-keypoint geometry
+ * on the device: for every keypoint of `frame` (pixels_yx = kp.pixel, is_3d = kp.is_3d and its map
+ * point exists, world_xyz = get_position(mp), undist_yx = kp.undistorted_pixel, only read in stereo mode)
+ *   1. 3-D keypoints are projected with frame.cw (column-major 4 x 4; stereo: right_cam->Ti0 * cw) through
+ *      project_undistort(cam, .) (frame.jl:478-484, camera.jl:73-85); inside the image (camera.jl:87-95; stereo: the right
+ *      camera's bounds) they get the prior (projection - pixel) / 2^pyramid_levels_3d, outside they are not tracked (bit 3);
+ *   2. tracking as in slamklt_flow_matching (prior pass, retry of the failures together with the 2-D keypoints);
+ *   3. mono: update_keypoint! (frame.jl:252-270): out_pixel = tracked pixel, out_undist = undistort_point(cam, pixel),
+ *      out_position = backproject(cam, undist) as (x, y, 1);
+ *      stereo: maybe_stereo_update! (map_manager.jl:579-590) + update_stereo_keypoint! (frame.jl:272-287): rejected when
+ *      |undist_yx[i].y - undistort_point(right_cam, tracked).y| > epipolar_error (bit 4), else out_pixel = (pixel.y, tracked.x),
+ *      out_undist / out_position through the right camera.
+ * status: bit0 = keypoint updated, bit1 = forward pass of the deciding attempt ok, bit2 = tracked by the prior pass,
+ * bit3 = 3-D keypoint whose projection is outside the image (mono: left untouched, stereo: remove_mappoint_obs!),
+ * bit4 = tracked but rejected by the epipolar gate.  Outputs of keypoints without bit0 are NaN.  The caller keeps the
+ * dictionary bookkeeping: bit0 -> store the three outputs, otherwise remove_obs_from_current_frame! (mono, bit3 clear). */
+int slamklt_optical_flow_matching(slamklt_ctx* ctx, const slamklt_pyr* from, const slamklt_pyr* to, const double* pixels_yx,
+                                  const uint8_t* is_3d, const double* world_xyz, const double* undist_yx, int n,
+                                  const double* cw, const slamklt_camera* cam, const slamklt_camera* right_cam,
+                                  const slamklt_matching_params* p, double* out_pixel_yx, double* out_undist_yx,
+                                  double* out_position_xyz, uint8_t* status);
+
 /* ---- Extractor ------------------------------------------------------------------------- */
 /* detect(e, image, current_points; sigma_mask) -- extractor.jl:63-95.  out_yx: cap pairs of Int64.
  * *n_out receives the number of detected keypoints (no global cap, like the reference). */

@@ -224,6 +224,121 @@ def detect(e: Extractor, image, current_points, sigma_mask=3.0, min_response=1e-
     return out[:n].copy()
 
 
+class Camera:
+    """camera.jl:1-46: intrinsics, distortion, image size and Ti0 (4 x 4, this camera <- camera 0)."""
+
+    def __init__(self, fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, height=0, width=0, Ti0=None):
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        self.k1, self.k2, self.p1, self.p2 = float(k1), float(k2), float(p1), float(p2)
+        self.height, self.width = int(height), int(width)
+        self.Ti0 = np.eye(4) if Ti0 is None else np.array(Ti0, dtype=np.float64).reshape(4, 4)
+
+
+def undistort_pdn_point(c: Camera, py, px):
+    """undistort_pdn_point (camera.jl:106-128) on arrays of pre-divided (y, x); evaluation order of the reference."""
+    sy, sx = py * py, px * px
+    r2 = sy + sx
+    rd = (1.0 + c.k1 * r2) + c.k2 * (r2 * r2)
+    p = py * px
+    dtx = (2 * c.p1) * p + c.p2 * (r2 + 2 * sy)
+    dty = c.p1 * (r2 + 2 * sx) + (2 * c.p2) * p
+    return (rd * py + dty) * c.fy + c.cy, (rd * px + dtx) * c.fx + c.cx
+
+
+def undistort_point(c: Camera, pts_yx):
+    """undistort_point (camera.jl:97-104)."""
+    pts_yx = np.asarray(pts_yx, dtype=np.float64).reshape(-1, 2)
+    y, x = undistort_pdn_point(c, (pts_yx[:, 0] - c.cy) / c.fy, (pts_yx[:, 1] - c.cx) / c.fx)
+    return np.stack([y, x], axis=1)
+
+
+def backproject(c: Camera, pts_yx):
+    """backproject (camera.jl:130-143): (x, y, 1)."""
+    pts_yx = np.asarray(pts_yx, dtype=np.float64).reshape(-1, 2)
+    return np.stack([(pts_yx[:, 1] - c.cx) / c.fx, (pts_yx[:, 0] - c.cy) / c.fy, np.ones(len(pts_yx))], axis=1)
+
+
+def _matmul4(A, B):
+    """SMatrix * SMatrix: every element a left-to-right sum of products (no BLAS, no reassociation)."""
+    out = np.empty((4, 4))
+    for i in range(4):
+        for j in range(4):
+            acc = A[i, 0] * B[0, j]
+            for k in range(1, 4):
+                acc = acc + A[i, k] * B[k, j]
+            out[i, j] = acc
+    return out
+
+
+def project_world_distort(c: Camera, T, world_xyz):
+    """project_world_to_image_distort / ..._right_image_distort (frame.jl:458-484): T * [X;1], then project_undistort
+    (camera.jl:73-85).  T is frame.cw or _matmul4(right_camera.Ti0, frame.cw)."""
+    w = np.asarray(world_xyz, dtype=np.float64).reshape(-1, 3)
+    X, Y, Z = w[:, 0], w[:, 1], w[:, 2]
+    xc = ((T[0, 0] * X + T[0, 1] * Y) + T[0, 2] * Z) + T[0, 3]
+    yc = ((T[1, 0] * X + T[1, 1] * Y) + T[1, 2] * Z) + T[1, 3]
+    zc = ((T[2, 0] * X + T[2, 1] * Y) + T[2, 2] * Z) + T[2, 3]
+    with np.errstate(all="ignore"):
+        y, x = undistort_pdn_point(c, yc / zc, xc / zc)
+    return np.stack([y, x], axis=1)
+
+
+def in_image(c: Camera, pts_yx):
+    """in_image (camera.jl:87-95)."""
+    return (1 <= pts_yx[:, 0]) & (pts_yx[:, 0] <= c.height) & (1 <= pts_yx[:, 1]) & (pts_yx[:, 1] <= c.width)
+
+
+def optical_flow_matching(from_pyr, to_pyr, pixels, is_3d, world, undist, cw, cam: Camera, right_cam: Camera = None,
+                          stereo=False, window_size=9, pyramid_levels=3, max_distance=1.0, pyramid_levels_3d=1,
+                          epipolar_error=2.0):
+    """optical_flow_matching! (map_manager.jl:451-564) on arrays instead of the keypoint / map-point dictionaries, with
+    update_keypoint! (frame.jl:252-270) or maybe_stereo_update! + update_stereo_keypoint! (map_manager.jl:579-590,
+    frame.jl:272-287) applied to the tracked keypoints.  Returns (pixel, undistorted, position, status) with
+    status bit0 updated, bit2 tracked by the prior pass, bit3 projection outside the image, bit4 epipolar reject."""
+    pixels = np.asarray(pixels, dtype=np.float64).reshape(-1, 2)
+    n = len(pixels)
+    is_3d = np.asarray(is_3d).astype(bool)
+    cw = np.asarray(cw, dtype=np.float64).reshape(4, 4)
+    out_pix = np.full((n, 2), np.nan); out_und = np.full((n, 2), np.nan); out_pos = np.full((n, 3), np.nan)
+    status = np.zeros(n, dtype=np.uint8)
+    scale = 1.0 / 2.0 ** pyramid_levels_3d
+    T = _matmul4(right_cam.Ti0, cw) if stereo else cw
+    proj = project_world_distort(cam, T, world)
+    inside = in_image(right_cam if stereo else cam, proj)
+    i3 = np.flatnonzero(is_3d & inside)
+    status[is_3d & ~inside] = 8
+    i2 = np.flatnonzero(~is_3d)
+
+    def update(idx, new_px, prior_pass):
+        if len(idx) == 0:
+            return
+        if not stereo:
+            und = undistort_point(cam, new_px)
+            out_pix[idx], out_und[idx], out_pos[idx] = new_px, und, backproject(cam, und)
+            status[idx] |= 1 | (4 if prior_pass else 0)
+            return
+        rp = undistort_point(right_cam, new_px)
+        good = ~(np.abs(undist[idx, 0] - rp[:, 0]) > epipolar_error)
+        status[idx[~good]] |= 16 | (4 if prior_pass else 0)
+        g = idx[good]
+        corrected = np.stack([pixels[g, 0], new_px[good, 1]], axis=1)
+        und = undistort_point(right_cam, corrected)
+        out_pix[g], out_und[g], out_pos[g] = corrected, und, backproject(right_cam, und)
+        status[g] |= 1 | (4 if prior_pass else 0)
+
+    if len(i3):
+        disp = scale * (proj[i3] - pixels[i3])
+        p3, s3, _ = fb_tracking(from_pyr, to_pyr, pixels[i3], displacement=disp, window_size=window_size,
+                                pyramid_levels=pyramid_levels_3d, max_distance=max_distance)
+        update(i3[s3], p3[s3], True)
+        i2 = np.concatenate([i2, i3[~s3]])
+    if len(i2):
+        p2, s2, _ = fb_tracking(from_pyr, to_pyr, pixels[i2], window_size=window_size, pyramid_levels=pyramid_levels,
+                                max_distance=max_distance)
+        update(i2[s2], p2[s2], False)
+    return out_pix, out_und, out_pos, status
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -56,6 +56,16 @@ class DetectParams(C.Structure):
                 ("min_response", C.c_double)]
 
 
+class CameraC(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("k1", C.c_double),
+                ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double), ("height", C.c_int64), ("width", C.c_int64),
+                ("Ti0", C.c_double * 16)]
+
+
+class MatchingParams(C.Structure):
+    _fields_ = [("lk", LKParams), ("stereo", C.c_int32), ("pyramid_levels_3d", C.c_int32), ("epipolar_error", C.c_double)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("lk_window_iters", C.c_uint64), ("lk_iters", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -63,7 +73,7 @@ class Stats(C.Structure):
 
 def build_library(force: bool = False) -> str:
     """Compile libslamklt.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_CSRC, f) for f in ("api.cu", "pyramid.cu", "lk.cu", "lk_patch.cu", "detect.cu", "common.cuh")]
+    srcs = [os.path.join(_CSRC, f) for f in ("api.cu", "pyramid.cu", "lk.cu", "lk_patch.cu", "detect.cu", "match.cu", "common.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "slamklt.h"))
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
@@ -79,7 +89,7 @@ SYMBOLS = [
     "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_profile", "slamklt_profile_report", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
     "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
-    "slamklt_flow_matching", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
+    "slamklt_flow_matching", "slamklt_optical_flow_matching", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
     "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
     "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
 ]
@@ -114,6 +124,8 @@ def lib():
         L.slamklt_optflow.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), u8p, ip]
         L.slamklt_fb_track.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(LKParams), dp, u8p]
         L.slamklt_flow_matching.argtypes = [vp, vp, vp, dp, dp, u8p, C.c_int, C.POINTER(LKParams), C.c_int, dp, u8p]
+        L.slamklt_optical_flow_matching.argtypes = [vp, vp, vp, dp, u8p, dp, dp, C.c_int, dp, C.POINTER(CameraC), C.POINTER(CameraC),
+                                                    C.POINTER(MatchingParams), dp, dp, dp, u8p]
         L.slamklt_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(DetectParams),
                                      i64p, C.c_int, ip]
         L.slamklt_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -354,6 +366,50 @@ def optical_flow_matching(from_pyramid: LKPyramid, to_pyramid: LKPyramid, pixels
                                     flg.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.byref(p), int(pyramid_levels_3d), _dp(out),
                                     st.ctypes.data_as(C.POINTER(C.c_uint8))))
     return out, (st & 1).astype(bool), ((st >> 2) & 1).astype(bool)
+
+
+class Camera:
+    """Camera (camera.jl:1-46): intrinsics, distortion, image size, Ti0 (4 x 4, this camera <- camera 0)."""
+
+    def __init__(self, fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, height=0, width=0, Ti0=None):
+        self.fx, self.fy, self.cx, self.cy = float(fx), float(fy), float(cx), float(cy)
+        self.k1, self.k2, self.p1, self.p2 = float(k1), float(k2), float(p1), float(p2)
+        self.height, self.width = int(height), int(width)
+        self.Ti0 = np.eye(4) if Ti0 is None else np.array(Ti0, dtype=np.float64).reshape(4, 4)
+
+    def _c(self):
+        t = np.asfortranarray(self.Ti0).ravel(order="F")  # SMatrix storage order
+        return CameraC(self.fx, self.fy, self.cx, self.cy, self.k1, self.k2, self.p1, self.p2, self.height, self.width,
+                       (C.c_double * 16)(*t))
+
+
+def optical_flow_matching_frame(from_pyramid: LKPyramid, to_pyramid: LKPyramid, pixels, is_3d, world, cw, camera: Camera,
+                                right_camera: Camera = None, undistorted=None, stereo=False, window_size=9, pyramid_levels=3,
+                                pyramid_levels_3d=1, max_distance=1.0, epipolar_error=2.0, iterations=30,
+                                eigenvalue_threshold=1e-4, eps=1e-2):
+    """optical_flow_matching!(map_manager, frame, from, to, stereo) (map_manager.jl:451-564) with the per-keypoint geometry on
+    the device: projection of the 3-D keypoints' map points + prior, both tracking passes, and update_keypoint! /
+    maybe_stereo_update! of the tracked ones.  Arrays replace the dictionaries: pixels[i] = kp.pixel, is_3d[i], world[i] =
+    map-point position, undistorted[i] = kp.undistorted_pixel (stereo), cw = frame.cw (4 x 4).
+    Returns (pixel, undistorted_pixel, position, status); status bits as in include/slamklt.h."""
+    pix = np.ascontiguousarray(pixels, dtype=np.float64).reshape(-1, 2)
+    n = len(pix)
+    flg = np.ascontiguousarray(is_3d, dtype=np.uint8).reshape(-1)
+    wor = np.ascontiguousarray(world, dtype=np.float64).reshape(-1, 3)
+    assert len(flg) == n and len(wor) == n
+    und = None if undistorted is None else np.ascontiguousarray(undistorted, dtype=np.float64).reshape(-1, 2)
+    T = np.ascontiguousarray(np.asarray(cw, dtype=np.float64).reshape(4, 4).ravel(order="F"))
+    out_pix = np.full((n, 2), np.nan); out_und = np.full((n, 2), np.nan); out_pos = np.full((n, 3), np.nan)
+    st = np.zeros(n, dtype=np.uint8)
+    mp = MatchingParams(LKParams(iterations, window_size, pyramid_levels, 0, eigenvalue_threshold, eps, float(max_distance)),
+                        1 if stereo else 0, int(pyramid_levels_3d), float(epipolar_error))
+    cam = camera._c()
+    rcam = None if right_camera is None else right_camera._c()
+    _ck(lib().slamklt_optical_flow_matching(
+        from_pyramid.ctx._h, from_pyramid._h, to_pyramid._h, _dp(pix), flg.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(wor),
+        None if und is None else _dp(und), n, _dp(T), C.byref(cam), None if rcam is None else C.byref(rcam), C.byref(mp),
+        _dp(out_pix), _dp(out_und), _dp(out_pos), st.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out_pix, out_und, out_pos, st
 
 
 class Extractor:

@@ -187,7 +187,7 @@ struct slamklt_ctx {
     std::mutex mu;
     unsigned long long* d_counters = nullptr;
     uint64_t launches = 0, h2d = 0, d2h = 0;
-    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur;
+    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match;
     HostBuf h_out, h_status, h_misc;
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
     // per-kernel profiling (off by default)
@@ -352,7 +352,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->norm_cache) cudaFree(kv.second);
-    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur};
+    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
     for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
@@ -780,6 +780,94 @@ int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_py
     const double* h = (const double*)c->h_out.p;
     for (int i = 0; i < n; ++i)
         if (status[i] & 2) { out_pts[2 * i] = h[2 * i]; out_pts[2 * i + 1] = h[2 * i + 1]; }
+    return 0;
+}
+
+static MatchCam cam_dev(const slamklt_camera* c) { return MatchCam{c->fx, c->fy, c->cx, c->cy, c->k1, c->k2, c->p1, c->p2}; }
+
+int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr* B, const double* pix, const uint8_t* is_3d,
+                                  const double* world, const double* undist, int n, const double* cw, const slamklt_camera* cam,
+                                  const slamklt_camera* rcam, const slamklt_matching_params* mp, double* out_pix, double* out_und,
+                                  double* out_pos, uint8_t* status) {
+    if (!c || !A || !B || !mp) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    const slamklt_lk_params* p = &mp->lk;
+    int r = check_lk(p, A->g.nl, B->g.nl);
+    if (r) return r;
+    const int l3 = mp->pyramid_levels_3d;
+    if (l3 < 0 || !(A->g.nl > l3 && B->g.nl > l3)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");
+    if (p->window_size > 11) return fail(SLAMKLT_E_INVALID, "optical_flow_matching supports window_size <= 11");
+    if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
+    if (n == 0) return 0;  // map_manager.jl:536
+    if (!pix || !is_3d || !world || !cw || !cam || !out_pix || !out_und || !out_pos || !status)
+        return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (mp->stereo && (!rcam || !undist)) return fail(SLAMKLT_E_INVALID, "stereo matching needs right_cam and undist_yx");
+    if (A->g.H0 != B->g.H0 || A->g.W0 != B->g.W0) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
+    if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    // device block: [pix 2n | world 3n | undist 2n | disp 2n | tracked 2n | out_pix 2n | out_und 2n | out_pos 3n] doubles, then
+    // [is_3d n | flag n | status n] bytes
+    const size_t N = (size_t)n;
+    if ((r = c->match.ensure(N * 18 * 8 + N * 3))) return r;
+    double* d = (double*)c->match.p;
+    double *d_pix = d, *d_world = d + 2 * N, *d_undist = d + 5 * N, *d_disp = d + 7 * N, *d_trk = d + 9 * N, *d_opix = d + 11 * N,
+           *d_ound = d + 13 * N, *d_opos = d + 15 * N;
+    uint8_t* d_is3d = (uint8_t*)(d + 18 * N);
+    uint8_t *d_flag = d_is3d + N, *d_status = d_flag + N;
+    CK(cudaMemcpyAsync(d_pix, pix, N * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_world, world, N * 24, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_is3d, is_3d, N, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += N * 41;
+    if (mp->stereo) { CK(cudaMemcpyAsync(d_undist, undist, N * 16, cudaMemcpyHostToDevice, c->stream)); c->h2d += N * 16; }
+
+    MatchArgs m{};
+    m.n = n; m.stereo = mp->stereo ? 1 : 0;
+    m.cam = cam_dev(cam);
+    m.rcam = cam_dev(mp->stereo ? rcam : cam);
+    if (mp->stereo) {
+        // Ti0 * cw (frame.jl:464-468: `right_camera.Ti0 * cw * point` associates to the left), each element a left-to-right sum
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) {
+                volatile double acc = rcam->Ti0[i] * cw[4 * j];
+                for (int k = 1; k < 4; ++k) { volatile double t = rcam->Ti0[i + 4 * k] * cw[k + 4 * j]; acc = acc + t; }
+                m.T[i + 4 * j] = acc;
+            }
+        m.bound_h = (double)rcam->height; m.bound_w = (double)rcam->width;
+    } else {
+        for (int k = 0; k < 16; ++k) m.T[k] = cw[k];
+        m.bound_h = (double)cam->height; m.bound_w = (double)cam->width;
+    }
+    m.scale = 1.0 / std::ldexp(1.0, l3);  // map_manager.jl:466
+    m.epipolar = mp->epipolar_error;
+    m.pix = d_pix; m.is_3d = d_is3d; m.world = d_world; m.undist = d_undist; m.flag = d_flag; m.disp = d_disp;
+    m.tracked = d_trk; m.status = d_status; m.out_pix = d_opix; m.out_und = d_ound; m.out_pos = d_opos;
+    mark(c->hk(), "k_match_prior");
+    launch_match_prior(c->stream, m);
+
+    LKArgs a{};
+    a.A = fs_of(A); a.B = fs_of(B); a.offA = 0; a.offB = 0;
+    fill_lk_levels(A->g, &a);
+    a.mode = 2;
+    a.pts = d_pix; a.disp_in = d_disp; a.disp_out = nullptr;
+    a.out_pts = d_trk; a.status = d_status;
+    a.has_prior = d_flag; a.levels3d = l3;
+    a.n_per_frame = n; a.n_frames = 1;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters;
+    mark(c->hk(), "k_lk_matching");
+    if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
+    mark(c->hk(), "k_match_update");
+    launch_match_update(c->stream, m);
+    c->launches += 3;
+    CKL();
+    prof_end(c);
+    CK(cudaMemcpyAsync(out_pix, d_opix, N * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_und, d_ound, N * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_pos, d_opos, N * 24, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status, d_status, N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += N * 57;
     return 0;
 }
 

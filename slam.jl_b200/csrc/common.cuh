@@ -80,7 +80,7 @@ struct LKArgs {
     int iterations, window, levels, pad_;
     double eig_thr, eps, max_dist;
     unsigned long long* counters;  // [0] window px * iterations, [1] iterations
-    const uint8_t* has_prior;      // mode 2: per point, 1 = 3-D keypoint tracked first with disp_in and levels3d
+    const uint8_t* has_prior;      // mode 2: per point, 1 = 3-D keypoint tracked first with disp_in and levels3d, 2 = skip (status 8)
     int levels3d, pad2_;
 };
 
@@ -98,6 +98,27 @@ struct DetArgs {
     int* n_out;         // [frame]
     int cap;
 };
+
+// optical_flow_matching! prologue / epilogue (match.cu)
+struct MatchCam { double fx, fy, cx, cy, k1, k2, p1, p2; };
+struct MatchArgs {
+    int n, stereo;
+    MatchCam cam, rcam;
+    double T[16];            // world -> camera (column-major): cw, or Ti0 * cw in stereo mode
+    double bound_h, bound_w; // image bounds of the camera the projection must fall into
+    double scale, epipolar;
+    const double* pix;       // n x 2 kp.pixel
+    const uint8_t* is_3d;    // n
+    const double* world;     // n x 3 map-point positions
+    const double* undist;    // n x 2 kp.undistorted_pixel (stereo)
+    uint8_t* flag;           // out of the prologue: 0 no prior, 1 prior, 2 projection outside the image
+    double* disp;            // out of the prologue: prior displacement
+    const double* tracked;   // n x 2 result of the tracking kernel
+    uint8_t* status;         // in/out
+    double* out_pix; double* out_und; double* out_pos;
+};
+void launch_match_prior(cudaStream_t s, const MatchArgs& a);
+void launch_match_update(cudaStream_t s, const MatchArgs& a);
 
 // optional per-kernel profiling hook: called with the kernel's name right before each launch
 struct Hook { void (*fn)(void* user, const char* name); void* user; };

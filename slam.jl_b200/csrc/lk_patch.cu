@@ -93,7 +93,18 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
     if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
     // mode 2 = optical_flow_matching! (map_manager.jl:451-564): keypoints with a prior (3-D keypoints) are first tracked with
     // that prior on levels3d levels; those that fail, and all others, are tracked from a zero displacement on all levels
-    const bool prior_first = a.mode == 2 && a.has_prior && a.has_prior[gw] != 0;
+    const uint8_t prior_flag = (a.mode == 2 && a.has_prior) ? a.has_prior[gw] : (uint8_t)0;
+    if (prior_flag == 2) {  // 3-D keypoint whose projection left the image: not tracked at all (map_manager.jl:489-506)
+        if (lane == 0) {
+            a.status[gw] = 8;
+            if (a.out_pts) {
+                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+        return;
+    }
+    const bool prior_first = prior_flag != 0;
     if (a.mode == 2 && !prior_first) { dy = 0.0; dx = 0.0; }
     int levels_cur = prior_first ? a.levels3d : a.levels;
     bool second_try = false;

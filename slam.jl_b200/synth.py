@@ -111,3 +111,49 @@ def random_keypoints(seed: int, n: int, H: int, W: int, border: float = 12.0) ->
     y = rng.uniform(1 + border, H - border, size=n)
     x = rng.uniform(1 + border, W - border, size=n)
     return np.stack([y, x], axis=1)
+
+
+KITTI_CAMERA = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, k1=-0.08, k2=0.015, p1=8e-4, p2=-5e-4,
+                    height=KITTI_H, width=KITTI_W)
+
+
+def matching_scene(seed: int, pixels_yx: np.ndarray, targets_yx: np.ndarray, camera: dict = None, baseline: float = 0.0,
+                   frac_3d: float = 0.5, frac_bad: float = 0.25, frac_outside: float = 0.05, prior_noise: float = 0.6):
+    """Inputs of optical_flow_matching! for keypoints `pixels_yx` whose true positions in the target image are
+    `targets_yx`: a frame pose cw, map-point positions of the 3-D keypoints that project (through the distorting camera,
+    camera.jl:106-128) close to the targets -- some far off (wrong map points) and some outside the image -- and the
+    right camera's Ti0 for a stereo rig with `baseline`.  Returns a dict of arrays."""
+    cam = dict(KITTI_CAMERA if camera is None else camera)
+    rng = np.random.default_rng(seed)
+    n = len(pixels_yx)
+    is_3d = rng.random(n) < frac_3d
+    tgt = targets_yx + rng.normal(0.0, prior_noise, targets_yx.shape)
+    bad = is_3d & (rng.random(n) < frac_bad)
+    tgt[bad] += rng.choice([-14.0, 14.0], size=(int(bad.sum()), 2))
+    outside = is_3d & ~bad & (rng.random(n) < frac_outside)
+    tgt[outside, 1] += rng.choice([-2.0, 2.0], size=int(outside.sum())) * cam["width"]
+    # invert the distortion model by fixed-point iteration: distorted normalised (yd, xd) -> undistorted (yn, xn)
+    yd, xd = (tgt[:, 0] - cam["cy"]) / cam["fy"], (tgt[:, 1] - cam["cx"]) / cam["fx"]
+    yn, xn = yd.copy(), xd.copy()
+    for _ in range(20):
+        r2 = yn * yn + xn * xn
+        rd = 1.0 + cam["k1"] * r2 + cam["k2"] * r2 * r2
+        p = yn * xn
+        dtx = 2 * cam["p1"] * p + cam["p2"] * (r2 + 2 * yn * yn)
+        dty = cam["p1"] * (r2 + 2 * xn * xn) + 2 * cam["p2"] * p
+        yn, xn = (yd - dty) / rd, (xd - dtx) / rd
+    depth = rng.uniform(4.0, 60.0, n)
+    # camera-space point of the camera the target image belongs to (the right one when baseline != 0)
+    pc = np.stack([xn * depth, yn * depth, depth, np.ones(n)], axis=0)
+    th = rng.uniform(-0.3, 0.3, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(th[0]), -np.sin(th[0])], [0, np.sin(th[0]), np.cos(th[0])]])
+    Ry = np.array([[np.cos(th[1]), 0, np.sin(th[1])], [0, 1, 0], [-np.sin(th[1]), 0, np.cos(th[1])]])
+    Rz = np.array([[np.cos(th[2]), -np.sin(th[2]), 0], [np.sin(th[2]), np.cos(th[2]), 0], [0, 0, 1]])
+    cw = np.eye(4)
+    cw[:3, :3] = Rz @ Ry @ Rx
+    cw[:3, 3] = rng.uniform(-3.0, 3.0, 3)
+    Ti0 = np.eye(4)
+    Ti0[0, 3] = -baseline
+    world = (np.linalg.inv(Ti0 @ cw) @ pc)[:3].T.copy()
+    world[~is_3d] = 0.0
+    return dict(is_3d=is_3d, world=world, cw=cw, Ti0=Ti0, camera=cam, bad=bad, outside=outside)

@@ -158,3 +158,78 @@ def test_optical_flow_matching_two_pass(ctx):
     assert both.sum() > 1000 and exp_3d.sum() > 200 and (i3[~s3]).size > 50
     d = np.abs(got_pts[both] - exp_pts[both]).max(axis=1)
     assert np.mean(d < 0.01) >= 0.999 and d.max() < 0.02
+
+
+def _matching_case(ctx, stereo):
+    if stereo:
+        l, r, d = synth.stereo_pair(5200)
+        f = synth.to_f64(np.stack([l, r]))
+        pts = synth.random_keypoints(21, 1500, 376, 1241, border=45.0)
+        dd = d[np.clip(np.rint(pts[:, 0]).astype(int) - 1, 0, 375), np.clip(np.rint(pts[:, 1]).astype(int) - 1, 0, 1240)]
+        gt = pts - np.stack([np.zeros(len(pts)), dd], axis=1)
+    else:
+        fr, aff = synth.make_sequence(5100, 2)
+        f = synth.to_f64(fr)
+        pts = synth.random_keypoints(20, 1500, 376, 1241, border=2.0)
+        gt = synth.true_flow(aff, 0, 1, pts)
+    sc = synth.matching_scene(77 + stereo, pts, gt, baseline=0.54 if stereo else 0.0)
+    o0, o1 = O.LKPyramid(f[0], 3), O.LKPyramid(f[1], 3)
+    o0.update(f[0]); o1.update(f[1])
+    g0, g1 = slamklt.LKPyramid(ctx, f[0], 3), slamklt.LKPyramid(ctx, f[1], 3)
+    g0.update(f[0]); g1.update(f[1])
+    return pts, sc, (o0, o1), (g0, g1)
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_optical_flow_matching_with_geometry(ctx, stereo):
+    """optical_flow_matching! (map_manager.jl:451-564) with projection of the map points, prior, both
+    tracking passes and update_keypoint! / maybe_stereo_update! on the device, against the oracle's restatement."""
+    pts, sc, (o0, o1), (g0, g1) = _matching_case(ctx, stereo)
+    ocam = O.Camera(**sc["camera"]); orc = O.Camera(**sc["camera"], Ti0=sc["Ti0"])
+    gcam = slamklt.Camera(**sc["camera"]); grc = slamklt.Camera(**sc["camera"], Ti0=sc["Ti0"])
+    rng = np.random.default_rng(5)
+    und = O.undistort_point(ocam, pts)
+    if stereo:
+        und[:, 0] += rng.choice([0.0, 0.0, 0.0, 3.5, -3.5], size=len(pts))   # some rows violate the epipolar gate
+    e_pix, e_und, e_pos, e_st = O.optical_flow_matching(o0, o1, pts, sc["is_3d"], sc["world"], und, sc["cw"], ocam, orc,
+                                                        stereo=stereo, window_size=9, pyramid_levels=3, max_distance=1.0)
+    g_pix, g_und, g_pos, g_st = slamklt.optical_flow_matching_frame(
+        g0, g1, pts, sc["is_3d"], sc["world"], sc["cw"], gcam, right_camera=grc if stereo else None,
+        undistorted=und if stereo else None, stereo=stereo, window_size=9, pyramid_levels=3, max_distance=1.0)
+    # the cases the path distinguishes all occur
+    assert (e_st & 4).astype(bool).sum() > 150 and (e_st == 8).sum() > 10 and (e_st & 1).sum() > (600 if stereo else 900)
+    assert np.sum(sc["bad"] & ((e_st & 5) == 1)) > 30            # wrong map point -> prior pass failed -> tracked by the retry
+    if stereo:
+        assert (e_st & 16).astype(bool).sum() > 100
+    assert np.array_equal(e_st == 8, g_st == 8)                   # in-image decision is Float64-exact
+    m = 1 | 4 | 8 | 16
+    assert np.mean((e_st & m) == (g_st & m)) >= 0.999
+    both = ((e_st & m) == (g_st & m)) & ((e_st & 1) == 1)
+    for e, g in ((e_pix, g_pix), (e_und, g_und)):
+        d = np.abs(e[both] - g[both]).max(axis=1)
+        assert np.mean(d < 0.01) >= 0.999 and d.max() < 0.02
+    assert np.abs(e_pos[both] - g_pos[both]).max() < 0.02 / 700
+    assert np.all(np.isnan(g_pix[(g_st & 1) == 0]))
+    # the epilogue arithmetic itself is bit-identical: redo it on the pixels the device tracked
+    cam = orc if stereo else ocam
+    ok = (g_st & 1) == 1
+    u = O.undistort_point(cam, g_pix[ok])
+    assert np.array_equal(u, g_und[ok]) and np.array_equal(O.backproject(cam, u), g_pos[ok])
+    if stereo:
+        assert np.array_equal(g_pix[ok][:, 0], pts[ok][:, 0])      # row taken from the left keypoint
+
+
+def test_optical_flow_matching_geometry_arguments(ctx):
+    pts, sc, _, (g0, g1) = _matching_case(ctx, False)
+    gcam = slamklt.Camera(**sc["camera"])
+    with pytest.raises(slamklt.SlamKltError):   # stereo without the right camera / undistorted pixels
+        slamklt.optical_flow_matching_frame(g0, g1, pts, sc["is_3d"], sc["world"], sc["cw"], gcam, stereo=True)
+    with pytest.raises(slamklt.SlamKltError, match="Not enough layers"):
+        slamklt.optical_flow_matching_frame(g0, g1, pts, sc["is_3d"], sc["world"], sc["cw"], gcam, pyramid_levels=5)
+    out = slamklt.optical_flow_matching_frame(g0, g1, np.zeros((0, 2)), np.zeros(0), np.zeros((0, 3)), sc["cw"], gcam)
+    assert out[0].shape == (0, 2) and out[3].shape == (0,)
+    # no 3-D keypoints at all: identical to plain fb_tracking
+    z = np.zeros(len(pts), bool)
+    pix, und, pos, st = slamklt.optical_flow_matching_frame(g0, g1, pts, z, sc["world"], sc["cw"], gcam, max_distance=1.0)
+    p2, s2, _ = slamklt.fb_tracking(g0, g1, pts, window_size=9, pyramid_levels=3, max_distance=1.0)
+    assert np.array_equal((st & 1).astype(bool), s2) and np.array_equal(pix[s2], p2[s2])
