@@ -21,6 +21,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace sk {
 
@@ -111,6 +112,33 @@ __device__ __forceinline__ void store_col(float* __restrict__ col, int y0, int p
     }
 }
 
+// Row validity at group granularity.  When H is a multiple of G (and K is), a lane's K rows fall into K/G groups that are
+// valid or invalid as a whole, so the K per-row tests `y0 + j < H` collapse into K/G loop-invariant predicates (G = 1 is the
+// general case).  Guard rows (>= H) are zero from the allocation's memset and no kernel ever writes anything else there,
+// so stores of invalid groups are simply skipped.
+template <int K, int G>
+struct RowGroups {
+    bool g[K / G];
+    __device__ __forceinline__ RowGroups(int y0, int H) {
+#pragma unroll
+        for (int i = 0; i < K / G; ++i) g[i] = y0 + i * G < H;
+    }
+    __device__ __forceinline__ bool valid(int j) const { return g[j / G]; }
+};
+
+template <int K, int G>
+__device__ __forceinline__ void store_col_g(float* __restrict__ col, int y0, const RowGroups<K, G>& rg, const float (&x)[K]) {
+    constexpr int V = (G % 4 == 0) ? 4 : 2;
+    static_assert(G % 2 == 0 && K % V == 0, "vector stores need even groups");
+#pragma unroll
+    for (int v = 0; v < K / V; ++v) {
+        if (rg.valid(V * v)) {
+            if constexpr (V == 4) *reinterpret_cast<float4*>(col + y0 + 4 * v) = make_float4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
+            else *reinterpret_cast<float2*>(col + y0 + 2 * v) = make_float2(x[2 * v], x[2 * v + 1]);
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // warp-wide recursive filter of one line held in registers: lane l owns elements [l*K, l*K+K)
 // ----------------------------------------------------------------------------------------------
@@ -124,7 +152,7 @@ __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, 
 // The line is extended to the full 32*K elements with its border value (x[n-1] for replicate, 0 for Fill(0)): the
 // Triggs-Sdika boundary is exactly the constant-extension assumption, so the result on [0, n) is unchanged while
 // every lane becomes a full chunk and no per-element predicate is needed.
-template <int K, int NL>
+template <int K, int NL, int G = 1>
 __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, const int lane, const IirDev& c, const bool zero_border) {
     const int y0 = lane * K;
     const int jl = n - 1 - y0;  // slot of the last element of the line, if it lives in this lane
@@ -136,14 +164,23 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
         float first = __shfl_sync(FULL, x[l][0], 0);
         float lastv = 0.f;
 #pragma unroll
-        for (int j = 0; j < K; ++j)
+        for (int j = G - 1; j < K; j += G)  // n is a multiple of G: the last element closes a group
             if (j == jl) lastv = x[l][j];
         lastv = __shfl_sync(FULL, lastv, ln);
         um[l] = (zero_border ? 0.f : first) * c.inv1ma;
         iplus[l] = zero_border ? 0.f : lastv;
+        if constexpr (G == 1) {
 #pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (j > jl) x[l][j] = iplus[l];  // constant extension past the end of the line
+            for (int j = 0; j < K; ++j)
+                if (j > jl) x[l][j] = iplus[l];  // constant extension past the end of the line
+        } else {
+#pragma unroll
+            for (int i = 0; i < K / G; ++i) {
+                const bool past = i * G > jl;
+#pragma unroll
+                for (int j = i * G; j < i * G + G; ++j) x[l][j] = past ? iplus[l] : x[l][j];
+            }
+        }
     }
     // forward, phase 1: chunk-local pass (lane 0 starts from the true left boundary state)
     float s0[NL], s1[NL], s2[NL];
@@ -328,10 +365,20 @@ __device__ __forceinline__ void load_col_halo(const float* __restrict__ I, int x
 }
 
 // SRC: 0 layer plane (fp32), 1 raw Float64, 2 raw Float32, 3 raw UInt8 (value / 255)
-template <int K, int SRC>
-__device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y0, float (&x)[K]) {
+template <int K, int SRC, int G = 1>
+__device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y0, float (&x)[K],
+                                             const RowGroups<K, G>& rg) {
     if constexpr (SRC == 0) {
         load_col<K>(I + (size_t)xc * a.pitch, y0, a.pitch, x);
+    } else if constexpr (SRC == 1 && G > 1) {
+        // aligned variant (the launcher guarantees raw_ld even): whole groups are valid or not
+        const double* col = reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
+#pragma unroll
+        for (int v = 0; v < K / 2; ++v) {
+            double2 t = make_double2(0.0, 0.0);
+            if (rg.valid(2 * v)) t = __ldg(reinterpret_cast<const double2*>(col + y0 + 2 * v));
+            x[2 * v] = (float)t.x; x[2 * v + 1] = (float)t.y;
+        }
     } else if constexpr (SRC == 1) {
         const double* col = reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
         if ((a.raw_ld & 1) == 0) {  // 16-byte aligned column starts: K is even, so pairs never straddle the end of a valid run
@@ -350,23 +397,23 @@ __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __re
     } else if constexpr (SRC == 2) {
         const float* col = reinterpret_cast<const float*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
 #pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? __ldg(col + y0 + j) : 0.f;
+        for (int j = 0; j < K; ++j) x[j] = rg.valid(j) ? __ldg(col + y0 + j) : 0.f;
     } else {
         const uint8_t* col = reinterpret_cast<const uint8_t*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
 #pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = (y0 + j < a.H) ? (float)((double)__ldg(col + y0 + j) / 255.0) : 0.f;
+        for (int j = 0; j < K; ++j) x[j] = rg.valid(j) ? (float)((double)__ldg(col + y0 + j) / 255.0) : 0.f;
     }
 }
 
-template <int K, int SRC>
+template <int K, int SRC, int G = 1>
 __device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float* __restrict__ I, int f, int xcol, int y0, int lane, bool zb,
-                                                  float (&e)[K + 2]) {
+                                                  float (&e)[K + 2], const RowGroups<K, G>& rg) {
     const int W = a.W, H = a.H;
     float x[K];
     const bool inside = xcol >= 0 && xcol < W;
     if (inside || !zb) {
         const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
-        load_col_any<K, SRC>(a, I, f, xc, y0, x);
+        load_col_any<K, SRC, G>(a, I, f, xc, y0, x, rg);
     } else {
 #pragma unroll
         for (int j = 0; j < K; ++j) x[j] = 0.f;
@@ -381,14 +428,14 @@ __device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float*
     e[K + 1] = dnv;
     if (!zb) {
 #pragma unroll
-        for (int j = 1; j <= K + 1; ++j)
+        for (int j = 1; j <= K + 1; j += G)  // row H opens a group
             if (y0 + j - 1 == H) e[j] = e[j - 1];
     }
 }
 
 // Fused column kernel: [level 0: input conversion + layer store] + Scharr + products + y pass of the sigma=4 filter
 // + [levels < L: y pass of the pyramid blur].  One read of the source column per output column (+2 halo columns per strip).
-template <int K, int SRC>
+template <int K, int SRC, int G>
 __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -398,16 +445,17 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
     const int total = a.n_frames * strips;
     const int y0 = lane * K;
     const bool zb = a.zero_border != 0;
+    const RowGroups<K, G> rg(y0, H);
     for (int w = warp; w < total; w += nwarps) {
         const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
         float* fb = a.fs.frame(a.f0 + f);
         const float* I = fb + a.o_in;
         float em[K + 2], ec[K + 2], ep[K + 2];
-        load_col_halo_any<K, SRC>(a, I, f, xb - 1, y0, lane, zb, em);
-        load_col_halo_any<K, SRC>(a, I, f, xb, y0, lane, zb, ec);
+        load_col_halo_any<K, SRC, G>(a, I, f, xb - 1, y0, lane, zb, em, rg);
+        load_col_halo_any<K, SRC, G>(a, I, f, xb, y0, lane, zb, ec, rg);
         const int xe = min(xb + GRAD_CS, W);
         for (int xcol = xb; xcol < xe; ++xcol) {
-            load_col_halo_any<K, SRC>(a, I, f, xcol + 1, y0, lane, zb, ep);
+            load_col_halo_any<K, SRC, G>(a, I, f, xcol + 1, y0, lane, zb, ep, rg);
             float pp[3][K];
             {
                 float gi[2 * K];
@@ -423,7 +471,9 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
 #pragma unroll
                 for (int v = 0; v < K / 2; ++v) {
                     const int y = y0 + 2 * v;
-                    if (y < pitch) {
+                    if constexpr (G > 1) {
+                        if (rg.valid(2 * v)) *reinterpret_cast<float4*>(og + 2 * y) = make_float4(gi[4 * v], gi[4 * v + 1], gi[4 * v + 2], gi[4 * v + 3]);
+                    } else if (y < pitch) {
                         float4 t;
                         t.x = y < H ? gi[4 * v] : 0.f; t.y = y < H ? gi[4 * v + 1] : 0.f;
                         t.z = y + 1 < H ? gi[4 * v + 2] : 0.f; t.w = y + 1 < H ? gi[4 * v + 3] : 0.f;
@@ -431,24 +481,38 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
                     }
                 }
             }
-            warp_iir_lines<K, 3>(pp, H, lane, c4, false);
+            warp_iir_lines<K, 3, G>(pp, H, lane, c4, false);
             float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
-            store_col<K>(o0, y0, pitch, H, pp[0]);
-            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pp[1]);
-            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pp[2]);
+            if constexpr (G > 1) {
+                store_col_g<K, G>(o0, y0, rg, pp[0]);
+                store_col_g<K, G>(o0 + a.plane_elems, y0, rg, pp[1]);
+                store_col_g<K, G>(o0 + 2 * a.plane_elems, y0, rg, pp[2]);
+            } else {
+                store_col<K>(o0, y0, pitch, H, pp[0]);
+                store_col<K>(o0 + a.plane_elems, y0, pitch, H, pp[1]);
+                store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pp[2]);
+            }
             if (SRC != 0 || a.do_blur) {
                 float bl[1][K];
+                if constexpr (G > 1) {
+                    // rows >= H are never stored and the filter overwrites them with the border value
 #pragma unroll
-                for (int j = 0; j < K; ++j) bl[0][j] = (y0 + j < H) ? ec[j + 1] : 0.f;
-                if (SRC != 0) store_col<K>(fb + a.o_in + (size_t)xcol * pitch, y0, pitch, H, bl[0]);  // the converted layer
+                    for (int j = 0; j < K; ++j) bl[0][j] = ec[j + 1];
+                    if (SRC != 0) store_col_g<K, G>(fb + a.o_in + (size_t)xcol * pitch, y0, rg, bl[0]);  // the converted layer
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) bl[0][j] = (y0 + j < H) ? ec[j + 1] : 0.f;
+                    if (SRC != 0) store_col<K>(fb + a.o_in + (size_t)xcol * pitch, y0, pitch, H, bl[0]);  // the converted layer
+                }
                 if (a.do_blur) {
-                    warp_iir_lines<K, 1>(bl, H, lane, c1, zb);
+                    warp_iir_lines<K, 1, G>(bl, H, lane, c1, zb);
                     if (a.inv_n) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
-                            if (y0 + j < H) bl[0][j] *= __ldg(a.inv_n + y0 + j);
+                            if (rg.valid(j)) bl[0][j] *= __ldg(a.inv_n + y0 + j);
                     }
-                    store_col<K>(fb + a.o_tmp + (size_t)xcol * pitch, y0, pitch, H, bl[0]);
+                    if constexpr (G > 1) store_col_g<K, G>(fb + a.o_tmp + (size_t)xcol * pitch, y0, rg, bl[0]);
+                    else store_col<K>(fb + a.o_tmp + (size_t)xcol * pitch, y0, pitch, H, bl[0]);
                 }
             }
 #pragma unroll
@@ -794,6 +858,16 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int
 
 static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
 
+template <int K, int G>
+static void launch_cols_all_g(cudaStream_t s, int src, int blocks, int threads, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
+    switch (src) {
+        case 0: k_cols_all<K, 0, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
+        case 1: k_cols_all<K, 1, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
+        case 2: k_cols_all<K, 2, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
+        default: k_cols_all<K, 3, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
+    }
+}
+
 template <int K>
 static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
     const int total_warps = a.n_frames * ((a.W + GRAD_CS - 1) / GRAD_CS);
@@ -801,12 +875,12 @@ static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const Iir
     int blocks = (total_warps + wpb - 1) / wpb;
     const int maxb = 148 * 16;
     if (blocks > maxb) blocks = maxb;
-    switch (src) {
-        case 0: k_cols_all<K, 0><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
-        case 1: k_cols_all<K, 1><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
-        case 2: k_cols_all<K, 2><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
-        default: k_cols_all<K, 3><<<blocks, wpb * 32, 0, s>>>(a, c4, c1); break;
-    }
+    // group-aligned variant when the image height is a multiple of the row-group size (4 rows, or 2 when K is not a multiple of 4)
+    constexpr int GA = (K % 4 == 0) ? 4 : 2;
+    const bool aligned = a.H % GA == 0 && (src != 1 || ((a.raw_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.raw) & 15) == 0)) &&
+                         getenv("SLAMKLT_COLS_GENERIC") == nullptr;
+    if (aligned) launch_cols_all_g<K, GA>(s, src, blocks, wpb * 32, a, c4, c1);
+    else launch_cols_all_g<K, 1>(s, src, blocks, wpb * 32, a, c4, c1);
 }
 
 static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
