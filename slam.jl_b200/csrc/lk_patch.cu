@@ -24,6 +24,29 @@ __device__ __forceinline__ float warp_sum_f2(float v) {
     return v;
 }
 
+// Sums of two / three per-lane values over the warp with shared butterfly steps: after the first exchange the lower and
+// upper half-warps carry different quantities, so the remaining steps reduce both at once (7 shuffles instead of 10, 9
+// instead of 15).  Every total is the same butterfly tree as warp_sum_f2 computes => bit-identical results.
+__device__ __forceinline__ void warp_sum2(float a, float b, int lane, float& sa, float& sb) {
+    const bool hi = lane & 16;
+    float v = (hi ? b : a) + __shfl_xor_sync(FULL, hi ? a : b, 16);  // lower half: a-partials, upper half: b-partials
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    sa = __shfl_sync(FULL, v, 0);
+    sb = __shfl_sync(FULL, v, 16);
+}
+__device__ __forceinline__ void warp_sum3(float a, float b, float c, int lane, float& sa, float& sb, float& sc) {
+    const bool hi = lane & 16, q = lane & 8;
+    float v = (hi ? b : a) + __shfl_xor_sync(FULL, hi ? a : b, 16);
+    c += __shfl_xor_sync(FULL, c, 16);
+    v = (q ? c : v) + __shfl_xor_sync(FULL, q ? v : c, 8);  // lanes with bit 3 set now carry c-partials
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    sa = __shfl_sync(FULL, v, 0);
+    sb = __shfl_sync(FULL, v, 16);
+    sc = __shfl_sync(FULL, v, 8);
+}
+
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
@@ -209,7 +232,9 @@ retry:
                         }
                     }
                 }
-                const double ga = (double)warp_sum_f2(syy), gc = (double)warp_sum_f2(sxx), gb = (double)warp_sum_f2(syx);
+                float fa, fc, fb;
+                warp_sum3(syy, sxx, syx, lane, fa, fc, fb);
+                const double ga = (double)fa, gc = (double)fc, gb = (double)fb;
                 // eigenvalue gate (lucas_kanade.jl:38-46): singular values of the symmetric G = [a b; b c] are Q +- R with
                 // Q = |a+c|/2, R = sqrt(((a-c)/2)^2 + b^2) (utils.jl:5-27 with H = 0), so min(S)/area < thr  <=>  |Q - R| < t,
                 // t = thr*area  <=>  R < Q + t  and  R > Q - t: decided on squares, no sqrt / division on the common path
@@ -317,7 +342,9 @@ retry:
             float by = byr[0], bx = bxr[0];
 #pragma unroll
             for (int i = 1; i < PR; ++i) { by += byr[i]; bx += bxr[i]; }
-            const double sby = (double)warp_sum_f2(by), sbx = (double)warp_sum_f2(bx);
+            float fby, fbx;
+            warp_sum2(by, bx, lane, fby, fbx);
+            const double sby = (double)fby, sbx = (double)fbx;
             wpx += (unsigned)(nrows * ncols);
             nit += 1;
             ++it;

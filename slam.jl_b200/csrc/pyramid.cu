@@ -23,6 +23,20 @@
 #include "common.cuh"
 #include <cstdlib>
 
+// experiment knob: software prefetch of the raw Float64 column COLS_PREFETCH_DIST columns ahead (1 = into L2, 2 = into L1)
+#ifndef COLS_PREFETCH
+#define COLS_PREFETCH 0
+#endif
+// raw Float64 columns through a cp.async shared-memory stage, one column ahead (0 = direct __ldg loads).  Measured on B200:
+// 0.280 ms vs 0.269 ms direct -- long-scoreboard stalls drop (3.1 -> 1.0 cycles/instr) but the extra LDS/LDGSTS traffic moves
+// them to the shared-memory pipe (short scoreboard 0.8 -> 1.9, MIO throttle 0.2 -> 0.9), which the scan's shuffles already load.
+#ifndef COLS_STAGE
+#define COLS_STAGE 0
+#endif
+#ifndef COLS_PREFETCH_DIST
+#define COLS_PREFETCH_DIST 2
+#endif
+
 namespace sk {
 
 // ----------------------------------------------------------------------------------------------
@@ -190,7 +204,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     for (int j = 0; j < K; ++j) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+            float u = fmaf(a1, s0[l], fmaf(a2, s1[l], fmaf(a3, s2[l], x[l][j])));  // newest state last: 1 FMA on the recurrence's critical path
             s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
         }
     }
@@ -220,7 +234,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     for (int j = 0; j < K; ++j) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            float u = x[l][j] + a1 * s0[l] + a2 * s1[l] + a3 * s2[l];
+            float u = fmaf(a1, s0[l], fmaf(a2, s1[l], fmaf(a3, s2[l], x[l][j])));  // newest state last: 1 FMA on the recurrence's critical path
             x[l][j] = u;
             s2[l] = s1[l]; s1[l] = s0[l]; s0[l] = u;
         }
@@ -244,7 +258,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     for (int j = K - 1; j >= 0; --j) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l];
+            float v = fmaf(a1, t0[l], fmaf(a2, t1[l], fmaf(a3, t2[l], x[l][j])));
             t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v;
             if (j == K - 1 && lane == 31) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
         }
@@ -274,7 +288,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     for (int j = K - 1; j >= 0; --j) {
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
-            float v = x[l][j] + a1 * t0[l] + a2 * t1[l] + a3 * t2[l];
+            float v = fmaf(a1, t0[l], fmaf(a2, t1[l], fmaf(a3, t2[l], x[l][j])));
             if (j == K - 1 && lane == 31) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
             else { t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
             x[l][j] = v * sc;
@@ -305,13 +319,14 @@ struct ColArgs {
 };
 
 // One warp per (frame, column).
-template <int K>
+template <int K, int G>
 __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = a.n_frames * a.W;
     const int y0 = lane * K;
+    const RowGroups<K, G> rg(y0, a.H);
     for (int w = warp; w < total; w += nwarps) {
         const int f = w / a.W, xcol = w - f * a.W;
         float* fb = a.fs.frame(a.f0 + f);
@@ -319,13 +334,14 @@ __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
         float* out = fb + a.o_out0 + (size_t)xcol * a.pitch;
         float x[1][K];
         load_col<K>(in, y0, a.pitch, x[0]);
-        warp_iir_lines<K, 1>(x, a.H, lane, c, a.zero_border != 0);
+        warp_iir_lines<K, 1, G>(x, a.H, lane, c, a.zero_border != 0);
         if (a.inv_n) {
 #pragma unroll
             for (int j = 0; j < K; ++j)
-                if (y0 + j < a.H) x[0][j] *= __ldg(a.inv_n + y0 + j);
+                if (rg.valid(j)) x[0][j] *= __ldg(a.inv_n + y0 + j);
         }
-        store_col<K>(out, y0, a.pitch, a.H, x[0]);
+        if constexpr (G > 1) store_col_g<K, G>(out, y0, rg, x[0]);
+        else store_col<K>(out, y0, a.pitch, a.H, x[0]);
     }
 }
 
@@ -405,19 +421,9 @@ __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __re
     }
 }
 
-template <int K, int SRC, int G = 1>
-__device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float* __restrict__ I, int f, int xcol, int y0, int lane, bool zb,
-                                                  float (&e)[K + 2], const RowGroups<K, G>& rg) {
-    const int W = a.W, H = a.H;
-    float x[K];
-    const bool inside = xcol >= 0 && xcol < W;
-    if (inside || !zb) {
-        const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
-        load_col_any<K, SRC, G>(a, I, f, xc, y0, x, rg);
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = 0.f;
-    }
+// e[0] = row y0-1, e[1..K] = rows y0..y0+K-1, e[K+1] = row y0+K from the lane's own rows x[] (border rule along y applied here)
+template <int K, int G>
+__device__ __forceinline__ void halo_from_col(const float (&x)[K], int y0, int H, int lane, bool zb, float (&e)[K + 2]) {
     float upv = __shfl_up_sync(FULL, x[K - 1], 1);
     float dnv = __shfl_down_sync(FULL, x[0], 1);
     if (lane == 0) upv = zb ? 0.f : x[0];
@@ -433,6 +439,39 @@ __device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float*
     }
 }
 
+template <int K, int SRC, int G = 1>
+__device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float* __restrict__ I, int f, int xcol, int y0, int lane, bool zb,
+                                                  float (&e)[K + 2], const RowGroups<K, G>& rg) {
+    const int W = a.W, H = a.H;
+    float x[K];
+    const bool inside = xcol >= 0 && xcol < W;
+    if (inside || !zb) {
+        const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
+        load_col_any<K, SRC, G>(a, I, f, xc, y0, x, rg);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) x[j] = 0.f;
+    }
+    halo_from_col<K, G>(x, y0, H, lane, zb, e);
+}
+
+// Raw Float64 columns staged through shared memory with cp.async, one column ahead of the column loop: a lane copies its
+// own K rows (K/2 16-byte pieces) and later reads back only what it copied itself, so no barrier is needed, just
+// cp.async.wait_group.  The lane stride is an odd number of 16-byte units => conflict-free 128-bit shared loads.
+template <int K>
+struct RawStage {
+    static constexpr int U = K / 2;                       // 16-byte units per lane
+    static constexpr int LU = (U % 2 == 0) ? U + 1 : U;   // lane stride in units (odd)
+    static constexpr int STAGE_UNITS = 32 * LU;
+};
+__device__ __forceinline__ void cp_async_cg16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
+    if (wait) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // Fused column kernel: [level 0: input conversion + layer store] + Scharr + products + y pass of the sigma=4 filter
 // + [levels < L: y pass of the pyramid blur].  One read of the source column per output column (+2 halo columns per strip).
 template <int K, int SRC, int G>
@@ -446,16 +485,63 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
     const int y0 = lane * K;
     const bool zb = a.zero_border != 0;
     const RowGroups<K, G> rg(y0, H);
+    constexpr bool STAGED = COLS_STAGE && SRC == 1 && G > 1 && K <= 16;
+    __shared__ __align__(16) double2 sRaw[STAGED ? 4 * 2 * RawStage<K>::STAGE_UNITS : 1];
+    double2* const sMine = sRaw + (threadIdx.x >> 5) * 2 * RawStage<K>::STAGE_UNITS + lane * RawStage<K>::LU;
     for (int w = warp; w < total; w += nwarps) {
         const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
         float* fb = a.fs.frame(a.f0 + f);
         const float* I = fb + a.o_in;
         float em[K + 2], ec[K + 2], ep[K + 2];
+        const int xe = min(xb + GRAD_CS, W);
+        // column c (clamped into the image) -> stage c & 1; issued one iteration before it is consumed
+        auto stage_issue = [&](int c) {
+            if constexpr (STAGED) {
+                if (c >= W) { if (zb) return; c = W - 1; }
+                const double* col = reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)c * a.raw_ld + y0;
+                double2* dst = sMine + (c & 1) * RawStage<K>::STAGE_UNITS;
+#pragma unroll
+                for (int v = 0; v < K / 2; ++v)
+                    if (rg.valid(2 * v)) cp_async_cg16(dst + v, col + 2 * v);
+                cp_async_commit_wait_all(false);
+            }
+        };
+        stage_issue(xb + 1);
         load_col_halo_any<K, SRC, G>(a, I, f, xb - 1, y0, lane, zb, em, rg);
         load_col_halo_any<K, SRC, G>(a, I, f, xb, y0, lane, zb, ec, rg);
-        const int xe = min(xb + GRAD_CS, W);
         for (int xcol = xb; xcol < xe; ++xcol) {
+            if constexpr (STAGED) {
+                float x[K];
+                int c = xcol + 1;
+                cp_async_commit_wait_all(true);
+                if (c >= W && zb) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) x[j] = 0.f;
+                } else {
+                    if (c >= W) c = W - 1;
+                    const double2* src = sMine + (c & 1) * RawStage<K>::STAGE_UNITS;
+#pragma unroll
+                    for (int v = 0; v < K / 2; ++v) {
+                        double2 t = make_double2(0.0, 0.0);
+                        if (rg.valid(2 * v)) t = src[v];
+                        x[2 * v] = (float)t.x; x[2 * v + 1] = (float)t.y;
+                    }
+                }
+                halo_from_col<K, G>(x, y0, H, lane, zb, ep);
+                if (xcol + 1 < xe) stage_issue(xcol + 2);
+            } else {
+#if COLS_PREFETCH
+            if (SRC == 1 && xcol + 1 + COLS_PREFETCH_DIST < W && y0 < H) {
+                const double* pf = reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)(xcol + 1 + COLS_PREFETCH_DIST) * a.raw_ld + y0;
+#if COLS_PREFETCH == 1
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+#else
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+#endif
+            }
+#endif
             load_col_halo_any<K, SRC, G>(a, I, f, xcol + 1, y0, lane, zb, ep, rg);
+            }
             float pp[3][K];
             {
                 float gi[2 * K];
@@ -521,61 +607,6 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(128) k_cols_grad(ColArgs a, IirDev c) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int H = a.H, W = a.W, pitch = a.pitch;
-    const int strips = (W + GRAD_CS - 1) / GRAD_CS;
-    const int total = a.n_frames * strips;
-    const int y0 = lane * K;
-    const bool zb = a.zero_border != 0;
-    for (int w = warp; w < total; w += nwarps) {
-        const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
-        float* fb = a.fs.frame(a.f0 + f);
-        const float* I = fb + a.o_in;
-        float em[K + 2], ec[K + 2], ep[K + 2];
-        load_col_halo<K>(I, xb - 1, W, pitch, H, y0, lane, zb, em);
-        load_col_halo<K>(I, xb, W, pitch, H, y0, lane, zb, ec);
-        const int xe = min(xb + GRAD_CS, W);
-        for (int xcol = xb; xcol < xe; ++xcol) {
-            load_col_halo<K>(I, xcol + 1, W, pitch, H, y0, lane, zb, ep);
-            float pp[3][K];
-            float gi[2 * K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                // centre row index in the halo arrays is j+1
-                const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
-                float gy = s0 * (0.5f * (em[j + 2] - em[j])) + s1 * (0.5f * (ec[j + 2] - ec[j])) + s0 * (0.5f * (ep[j + 2] - ep[j]));
-                float gx = s0 * (0.5f * (ep[j] - em[j])) + s1 * (0.5f * (ep[j + 1] - em[j + 1])) + s0 * (0.5f * (ep[j + 2] - em[j + 2]));
-                gi[2 * j] = gy; gi[2 * j + 1] = gx;
-                pp[0][j] = gy * gy; pp[1][j] = gx * gx; pp[2][j] = gy * gx;
-            }
-            // interleaved gradients: lane owns 2K consecutive floats starting at 2*y0
-            {
-                float* og = fb + a.o_grad + (size_t)xcol * (2 * pitch);
-#pragma unroll
-                for (int v = 0; v < K / 2; ++v) {
-                    const int y = y0 + 2 * v;
-                    if (y < pitch) {
-                        float4 t;
-                        t.x = y < H ? gi[4 * v] : 0.f; t.y = y < H ? gi[4 * v + 1] : 0.f;
-                        t.z = y + 1 < H ? gi[4 * v + 2] : 0.f; t.w = y + 1 < H ? gi[4 * v + 3] : 0.f;
-                        *reinterpret_cast<float4*>(og + 2 * y) = t;
-                    }
-                }
-            }
-            warp_iir_lines<K, 3>(pp, H, lane, c, false);
-            float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
-            store_col<K>(o0, y0, pitch, H, pp[0]);
-            store_col<K>(o0 + a.plane_elems, y0, pitch, H, pp[1]);
-            store_col<K>(o0 + 2 * a.plane_elems, y0, pitch, H, pp[2]);
-#pragma unroll
-            for (int j = 0; j < K + 2; ++j) { em[j] = ec[j]; ec[j] = ep[j]; }
-        }
-    }
-}
 
 // ----------------------------------------------------------------------------------------------
 // dim-2 kernel (along x).  CTA = LR rows x NC chunks of KRt elements; thread (row, chunk) keeps its chunk in registers.
@@ -648,7 +679,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     float s0 = ch == 0 ? um : 0.f, s1 = s0, s2 = s0;
 #pragma unroll
     for (int j = 0; j < KRt; ++j) {
-        float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+        float u = fmaf(a1, s0, fmaf(a2, s1, fmaf(a3, s2, x[j])));
         s2 = s1; s1 = s0; s0 = u;
     }
     sF[ch][0][rl] = s0; sF[ch][1][rl] = s1; sF[ch][2][rl] = s2;
@@ -672,7 +703,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     else { s0 = sF[ch][0][rl]; s1 = sF[ch][1][rl]; s2 = sF[ch][2][rl]; }
 #pragma unroll
     for (int j = 0; j < KRt; ++j) {
-        float u = x[j] + a1 * s0 + a2 * s1 + a3 * s2;
+        float u = fmaf(a1, s0, fmaf(a2, s1, fmaf(a3, s2, x[j])));
         x[j] = u;
         s2 = s1; s1 = s0; s0 = u;
     }
@@ -688,7 +719,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
     for (int j = KRt - 1; j >= 0; --j) {
-        float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2;
+        float v = fmaf(a1, t0, fmaf(a2, t1, fmaf(a3, t2, x[j])));
         t2 = t1; t1 = t0; t0 = v;
         if (j == KRt - 1 && lastc) { t0 = vr0; t1 = vr1; t2 = vr2; }
     }
@@ -713,7 +744,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     const float sc = c.scale;
 #pragma unroll
     for (int j = KRt - 1; j >= 0; --j) {
-        float v = x[j] + a1 * t0 + a2 * t1 + a3 * t2;
+        float v = fmaf(a1, t0, fmaf(a2, t1, fmaf(a3, t2, x[j])));
         if (j == KRt - 1 && lastc) { v = vr0; t0 = vr0; t1 = vr1; t2 = vr2; }
         else { t2 = t1; t1 = t0; t0 = v; }
         x[j] = v * sc;
@@ -810,33 +841,27 @@ int pick_K(int H) {
 }
 
 template <int K>
-static void launch_cols(cudaStream_t s, bool grad, const ColArgs& a, const IirDev& c) {
+static void launch_cols_blur(cudaStream_t s, const ColArgs& a, const IirDev& c) {
     const int maxb = 148 * 16;
-    if (grad) {
-        const int total_warps = a.n_frames * ((a.W + GRAD_CS - 1) / GRAD_CS);
-        const int wpb = 4;
-        int blocks = (total_warps + wpb - 1) / wpb;
-        if (blocks > maxb) blocks = maxb;
-        k_cols_grad<K><<<blocks, wpb * 32, 0, s>>>(a, c);
-    } else {
-        const int total_warps = a.n_frames * a.W;
-        const int wpb = 8;
-        int blocks = (total_warps + wpb - 1) / wpb;
-        if (blocks > maxb) blocks = maxb;
-        k_cols_blur<K><<<blocks, wpb * 32, 0, s>>>(a, c);
-    }
+    const int total_warps = a.n_frames * a.W;
+    const int wpb = 8;
+    int blocks = (total_warps + wpb - 1) / wpb;
+    if (blocks > maxb) blocks = maxb;
+    constexpr int GA = (K % 4 == 0) ? 4 : 2;
+    if (a.H % GA == 0 && getenv("SLAMKLT_COLS_GENERIC") == nullptr) k_cols_blur<K, GA><<<blocks, wpb * 32, 0, s>>>(a, c);
+    else k_cols_blur<K, 1><<<blocks, wpb * 32, 0, s>>>(a, c);
 }
 
-static void dispatch_cols(cudaStream_t s, int K, bool grad, const ColArgs& a, const IirDev& c) {
+static void dispatch_cols_blur(cudaStream_t s, int K, const ColArgs& a, const IirDev& c) {
     switch (K) {
-        case 2: launch_cols<2>(s, grad, a, c); break;
-        case 4: launch_cols<4>(s, grad, a, c); break;
-        case 6: launch_cols<6>(s, grad, a, c); break;
-        case 8: launch_cols<8>(s, grad, a, c); break;
-        case 12: launch_cols<12>(s, grad, a, c); break;
-        case 16: launch_cols<16>(s, grad, a, c); break;
-        case 24: launch_cols<24>(s, grad, a, c); break;
-        case 34: launch_cols<34>(s, grad, a, c); break;
+        case 2: launch_cols_blur<2>(s, a, c); break;
+        case 4: launch_cols_blur<4>(s, a, c); break;
+        case 6: launch_cols_blur<6>(s, a, c); break;
+        case 8: launch_cols_blur<8>(s, a, c); break;
+        case 12: launch_cols_blur<12>(s, a, c); break;
+        case 16: launch_cols_blur<16>(s, a, c); break;
+        case 24: launch_cols_blur<24>(s, a, c); break;
+        case 34: launch_cols_blur<34>(s, a, c); break;
     }
 }
 
@@ -957,15 +982,16 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             cudaStreamWaitEvent(sC, ps.ev[l], 0);
             ColArgs cg = ca;
             cg.inv_n = nullptr;
+            cg.do_blur = 0;  // the fused kernel without its blur half (SRC = 0: nothing to convert)
             snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
-            dispatch_cols(sC, K, true, cg, c4);
+            dispatch_cols_all(sC, K, 0, cg, c4, c1);
             launches += 1;
             rows_struct(sC, l, c4);
             if (blur) {
                 ColArgs cb = ca;
                 cb.o_out0 = plane_off(L, DP_TMP);
                 snprintf(nm, sizeof(nm), "k_cols_blur_L%d", l); mark(hk, nm);
-                dispatch_cols(sA, K, false, cb, c1);
+                dispatch_cols_blur(sA, K, cb, c1);
                 launches += 1;
             }
         }

@@ -48,6 +48,23 @@ def test_pyramid_planes(ctx, seq, mode, shape):
         assert rel_err(a, b) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", ["f64", "u8"])
+def test_column_kernel_variants_bit_identical(ctx, seq, monkeypatch, dtype):
+    """The group-aligned column kernel (row validity per 4-row group, H % 4 == 0) and the general one (per-row predicates,
+    forced with SLAMKLT_COLS_GENERIC) are the same arithmetic: every plane of every level is bit-identical."""
+    img = seq[0][0] if dtype == "f64" else seq[1][0]
+    planes = {}
+    for variant in ("aligned", "generic"):
+        if variant == "generic":
+            monkeypatch.setenv("SLAMKLT_COLS_GENERIC", "1")
+        gp = slamklt.LKPyramid(ctx, img, 3)
+        gp.update(img)
+        planes[variant] = {(l, n): gp.plane(l, n) for l in range(4) for n in ("layer", "Iy", "Ix", "Syy", "Sxx", "Syx")}
+    monkeypatch.delenv("SLAMKLT_COLS_GENERIC")
+    for k, a in planes["aligned"].items():
+        assert np.array_equal(a, planes["generic"][k]), k
+
+
 def _track_both(ctx, f0, f1, pts, levels=3, window=9, max_distance=1.0, disp=None, mode="ctor"):
     o0, o1 = O.LKPyramid(f0, max(levels, 3), mode="ctor"), O.LKPyramid(f1, max(levels, 3), mode="ctor")
     g0, g1 = slamklt.LKPyramid(ctx, f0, max(levels, 3)), slamklt.LKPyramid(ctx, f1, max(levels, 3))
