@@ -402,7 +402,14 @@ bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
     const int total = a.n_frames * a.n_per_frame;
     const int blocks = (total + 3) / 4;
     const int w2 = 2 * a.window + 1;
-    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 128, 0, s>>>(a);
+    // experiment knob: SLAMKLT_LK_PAD_KB adds unused dynamic shared memory per CTA to lower the occupancy (4 -> 3 -> 2 CTAs/SM)
+    static const int pad = [] {
+        const char* e = getenv("SLAMKLT_LK_PAD_KB");
+        const int kb = e ? atoi(e) : 0;
+        if (kb > 0) cudaFuncSetAttribute(k_lk_patch<19, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
+        return kb * 1024;
+    }();
+    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 128, pad, s>>>(a);
     else if (w2 <= 23) k_lk_patch<23, 3, 6><<<blocks, 128, 0, s>>>(a);
     else return false;
     return true;
