@@ -82,12 +82,27 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #ifndef LK_TMA
 #define LK_TMA 0
 #endif
+// warps (= keypoints) per CTA and the occupancy the register allocation is bounded for (65536 / (32 * LK_WPB * LK_MINB) registers);
+// LK_MAXNREG caps the registers directly instead.  Measured on B200 (64 x 2000 keypoints): 128 registers / 16 warps per SM 1.11 ms;
+// uncapped the kernel wants 160 registers; 120 (16 warps) 1.11 ms, 112 (18 warps, 24 B spill) 1.18 ms, 104 (18 warps) 1.25 ms,
+// 96 (20 warps, ~200 B spill) slower still: the spills cost more than the extra warps hide.  Fewer resident warps through
+// SLAMKLT_LK_PAD_KB: 12 warps 1.34 ms, 8 warps 2.01 ms.
+#ifndef LK_WPB
+#define LK_WPB 4
+#endif
+#ifndef LK_MINB
+#define LK_MINB 4
+#endif
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int W2, int PR, int PC>
-__global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
+#ifdef LK_MAXNREG
+__global__ void __maxnreg__(LK_MAXNREG) k_lk_patch(const LKArgs a) {
+#else
+__global__ void __launch_bounds__(32 * LK_WPB, LK_MINB) k_lk_patch(const LKArgs a) {
+#endif
     static_assert(PR * 8 >= W2 && PC * 4 >= W2, "patch grid must cover the window");
     constexpr int RSPAN = PR * 8 + 1, CSPAN = PC * 4 + 1;  // tap rows / columns touched by the lanes
     // tile rows: multiple of 4 (16-byte staging), >= RSPAN + 8, and PC*TR = 8 (mod 32) so that the 8 x 4 lane grid (row
@@ -96,8 +111,8 @@ __global__ void __launch_bounds__(128, 4) k_lk_patch(const LKArgs a) {
     static_assert(TR >= RSPAN + 8 && TR % 4 == 0 && (PC * TR) % 32 == 8 && PR == 3, "tile geometry");
     constexpr int TC = CSPAN + 8;                           // tile columns
     constexpr int RG = TR / 4, CGN = 32 / RG;               // staging: RG row groups per column, CGN columns per instruction
-    __shared__ __align__(16) float sTile[4][TC][TR];
-    __shared__ __align__(8) uint64_t sBar[4];
+    __shared__ __align__(16) float sTile[LK_WPB][TC][TR];
+    __shared__ __align__(8) uint64_t sBar[LK_WPB];
     float (*sT)[TR] = sTile[threadIdx.x >> 5];
     uint64_t* bar = &sBar[threadIdx.x >> 5];
     unsigned parity = 0;
@@ -400,7 +415,7 @@ retry:
 // returns false when this variant does not cover the window size
 bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
     const int total = a.n_frames * a.n_per_frame;
-    const int blocks = (total + 3) / 4;
+    const int blocks = (total + LK_WPB - 1) / LK_WPB;
     const int w2 = 2 * a.window + 1;
     // experiment knob: SLAMKLT_LK_PAD_KB adds unused dynamic shared memory per CTA to lower the occupancy (4 -> 3 -> 2 CTAs/SM)
     static const int pad = [] {
@@ -409,8 +424,8 @@ bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
         if (kb > 0) cudaFuncSetAttribute(k_lk_patch<19, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
         return kb * 1024;
     }();
-    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 128, pad, s>>>(a);
-    else if (w2 <= 23) k_lk_patch<23, 3, 6><<<blocks, 128, 0, s>>>(a);
+    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 32 * LK_WPB, pad, s>>>(a);
+    else if (w2 <= 23) k_lk_patch<23, 3, 6><<<blocks, 32 * LK_WPB, 0, s>>>(a);
     else return false;
     return true;
 }
