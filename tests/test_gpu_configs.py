@@ -233,3 +233,22 @@ def test_optical_flow_matching_geometry_arguments(ctx):
     pix, und, pos, st = slamklt.optical_flow_matching_frame(g0, g1, pts, z, sc["world"], sc["cw"], gcam, max_distance=1.0)
     p2, s2, _ = slamklt.fb_tracking(g0, g1, pts, window_size=9, pyramid_levels=3, max_distance=1.0)
     assert np.array_equal((st & 1).astype(bool), s2) and np.array_equal(pix[s2], p2[s2])
+
+
+def test_matching_against_committed_golden(ctx):
+    """The device call against the committed fixtures tests/golden/oracle_{small,matching}.npz (no oracle involved at run time)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "oracle_small.npz"))
+    m = np.load(os.path.join(here, "golden", "oracle_matching.npz"))
+    c = m["camera"]
+    cam = slamklt.Camera(*c[:8], height=int(c[8]), width=int(c[9]))
+    p0 = slamklt.LKPyramid(ctx, g["img0"], 2)
+    p1 = slamklt.LKPyramid(ctx, g["img1"], 2); p1.update(g["img1"])
+    pix, und, pos, st = slamklt.optical_flow_matching_frame(p0, p1, g["pts"], m["is_3d"], m["world"], m["cw"], cam,
+                                                            window_size=9, pyramid_levels=2, max_distance=1.0)
+    mask = 1 | 4 | 8
+    assert np.array_equal(st & mask, m["status"] & mask)
+    ok = (st & 1) == 1
+    assert np.abs(pix[ok] - m["pix"][ok]).max() < 0.01 and np.abs(und[ok] - m["und"][ok]).max() < 0.01
+    assert np.abs(pos[ok] - m["pos"][ok]).max() < 0.01 / 100
