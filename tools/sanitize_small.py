@@ -8,7 +8,7 @@ from slamklt import synth
 fr, aff = synth.make_sequence(1, 3, H=75, W=131)
 f = synth.to_f64(fr)
 ctx = slamklt.Context(0)
-for levels, shape in ((2, (75, 131)), (1, (33, 47))):
+for levels, shape in ((2, (75, 131)), (1, (33, 47)), (2, (72, 128))):  # the last one takes the group-aligned column kernels
     a = slamklt.LKPyramid(ctx, f[0][:shape[0], :shape[1]], levels)
     b = slamklt.LKPyramid(ctx, fr[1][:shape[0], :shape[1]], levels)
     b.update(f[1][:shape[0], :shape[1]])
@@ -18,6 +18,12 @@ for levels, shape in ((2, (75, 131)), (1, (33, 47))):
     slamklt.optflow(np.zeros_like(pts), a, b, pts, slamklt.LucasKanade(pyramid_levels=levels))
     slamklt.optical_flow_matching(a, b, pts, np.ones_like(pts), np.arange(len(pts)) % 2, pyramid_levels=levels, pyramid_levels_3d=1)
     a.plane(1, "Syy"); a.plane(0, "Iyy"); a.plane(0, "Ix")
+    sc = synth.matching_scene(4, pts, pts + 0.7, camera=dict(synth.KITTI_CAMERA, fx=90.0, fy=90.0, cx=shape[1] / 2, cy=shape[0] / 2,
+                                                              height=shape[0], width=shape[1]), baseline=0.3)
+    cam = slamklt.Camera(**sc["camera"]); rcam = slamklt.Camera(**sc["camera"], Ti0=sc["Ti0"])
+    slamklt.optical_flow_matching_frame(a, b, pts, sc["is_3d"], sc["world"], sc["cw"], cam, pyramid_levels=levels)
+    slamklt.optical_flow_matching_frame(a, b, pts, sc["is_3d"], sc["world"], sc["cw"], cam, right_camera=rcam, undistorted=pts,
+                                        stereo=True, pyramid_levels=levels)
 e = slamklt.Extractor(100, 8, (3, 4), 35)
 slamklt.detect(ctx, e, f[0], np.array([[10.0, 10.0], [60.0, 100.0]]))
 slamklt.detect(ctx, e, fr[0], np.zeros((0, 2)))
