@@ -82,6 +82,15 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 #ifndef LK_TMA
 #define LK_TMA 0
 #endif
+// warp sums with shared butterfly steps (fewer shuffles, one more dependent step) or plain butterflies.  Measured with the
+// packed loop: shared 1.075 ms, plain 1.089 ms (the shared-memory / shuffle pipe is the scarcer resource)
+#ifndef LK_SHARED_SUMS
+#define LK_SHARED_SUMS 1
+#endif
+// packed fp32 arithmetic in the window loop (sm_100 FFMA2 / FADD2 / FMUL2): loop body 144 -> 100 instructions, 1.111 -> 1.075 ms
+#ifndef LK_F32X2
+#define LK_F32X2 1
+#endif
 // warps (= keypoints) per CTA and the occupancy the register allocation is bounded for (65536 / (32 * LK_WPB * LK_MINB) registers);
 // LK_MAXNREG caps the registers directly instead.  Measured on B200 (64 x 2000 keypoints): 128 registers / 16 warps per SM 1.11 ms;
 // uncapped the kernel wants 160 registers; 120 (16 warps) 1.11 ms, 112 (18 warps, 24 B spill) 1.18 ms, 104 (18 warps) 1.25 ms,
@@ -157,7 +166,14 @@ __global__ void __launch_bounds__(32 * LK_WPB, LK_MINB) k_lk_patch(const LKArgs 
 
     const int rgp = lane & 7, cgp = lane >> 3;  // patch row group / column group of this lane
     const int pi0 = rgp * PR, pj0 = cgp * PC;   // first window row / column of the patch
-    float tI[PR][PC], tIy[PR][PC], tIx[PR][PC];
+    // template patch: I in column pairs (2q, 2q+1) as float2 + the odd last column (packed fp32 subtraction), gradients as the
+    // (Iy, Ix) pair the 64-bit load delivers: one packed FMA per pixel accumulates (by, bx) together
+    constexpr int NQT = PC / 2;
+    float2 tIp[PR][NQT];
+    float tIl[PR];
+    float2 tG[PR][PC];
+    (void)tIl;
+#define TI_REF(i, j) (*((j) < 2 * NQT ? (((j) & 1) ? &tIp[i][(j) / 2 < NQT ? (j) / 2 : 0].y : &tIp[i][(j) / 2 < NQT ? (j) / 2 : 0].x) : &tIl[i]))
     int ty0 = 0, tx0 = 0;
     bool pending = false;
     const int srg = lane % RG, scg = lane / RG;  // staging role of this lane: 16-byte row group / column group
@@ -243,12 +259,13 @@ retry:
                             float iv = 0.f;
                             float2 g2 = make_float2(0.f, 0.f);
                             if (okk) { iv = __ldg(cI + i); g2 = __ldg(cG + i); }
-                            tI[i][j] = iv; tIy[i][j] = g2.x; tIx[i][j] = g2.y;
+                            TI_REF(i, j) = iv; tG[i][j] = g2;
                         }
                     }
                 }
                 float fa, fc, fb;
-                warp_sum3(syy, sxx, syx, lane, fa, fc, fb);
+                if (LK_SHARED_SUMS) warp_sum3(syy, sxx, syx, lane, fa, fc, fb);
+                else { fa = warp_sum_f2(syy); fc = warp_sum_f2(sxx); fb = warp_sum_f2(syx); }
                 const double ga = (double)fa, gc = (double)fc, gb = (double)fb;
                 // eigenvalue gate (lucas_kanade.jl:38-46): singular values of the symmetric G = [a b; b c] are Q +- R with
                 // Q = |a+c|/2, R = sqrt(((a-c)/2)^2 + b^2) (utils.jl:5-27 with H = 0), so min(S)/area < thr  <=>  |Q - R| < t,
@@ -331,6 +348,52 @@ retry:
             }
             // ---- prepare_linear_system (lucas_kanade.jl:159-173) on this lane's patch
             const float* tb = &sT[ox + pj0][oy + pi0];
+            float by, bx;
+#if LK_F32X2
+            if constexpr (PC % 2 == 1) {
+                // packed fp32 (FFMA2 / FMUL2 / FADD2 on register pairs): tap columns in pairs (2m, 2m+1), pixels in pairs
+                // (2q, 2q+1) plus the last column alone; bilinear sample as a*(1-w) + b*w so no negated operand is needed
+                constexpr int NP = (PC + 1) / 2, NQ = PC / 2;
+                const float omwy = 1.f - wy, omwx = 1.f - wx;
+                const float2 wy2 = make_float2(wy, wy), omwy2 = make_float2(omwy, omwy);
+                const float2 nwx2 = make_float2(-wx, -wx), nomwx2 = make_float2(-omwx, -omwx);
+                float2 V[PR][NP];
+                {
+                    float2 Tp[NP];
+#pragma unroll
+                    for (int m = 0; m < NP; ++m) Tp[m] = make_float2(tb[(2 * m) * TR], tb[(2 * m + 1) * TR]);
+#pragma unroll
+                    for (int i = 0; i < PR; ++i) {
+#pragma unroll
+                        for (int m = 0; m < NP; ++m) {
+                            const float2 Tn = make_float2(tb[(2 * m) * TR + i + 1], tb[(2 * m + 1) * TR + i + 1]);
+                            V[i][m] = __ffma2_rn(Tn, wy2, __fmul2_rn(Tp[m], omwy2));
+                            Tp[m] = Tn;
+                        }
+                    }
+                }
+                float2 b2[PR];  // (by, bx) per patch row: PR independent packed-FMA chains
+#pragma unroll
+                for (int i = 0; i < PR; ++i) {
+                    b2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float2 A = V[i][q], B = make_float2(V[i][q].y, V[i][q + 1].x);
+                        const float2 nval = __ffma2_rn(B, nwx2, __fmul2_rn(A, nomwx2));
+                        const float2 dI = __fadd2_rn(tIp[i][q], nval);
+                        b2[i] = __ffma2_rn(tG[i][2 * q], make_float2(dI.x, dI.x), b2[i]);
+                        b2[i] = __ffma2_rn(tG[i][2 * q + 1], make_float2(dI.y, dI.y), b2[i]);
+                    }
+                    const float val = fmaf(V[i][NP - 1].y, wx, V[i][NP - 1].x * omwx);
+                    const float dI = tIl[i] - val;
+                    b2[i] = __ffma2_rn(tG[i][PC - 1], make_float2(dI, dI), b2[i]);
+                }
+#pragma unroll
+                for (int i = 1; i < PR; ++i) b2[0] = __fadd2_rn(b2[0], b2[i]);
+                by = b2[0].x; bx = b2[0].y;
+            } else
+#endif
+            {
             float byr[PR], bxr[PR];  // one accumulator pair per patch row: PR independent FFMA chains instead of one
             float vprev[PR];         // vertical lerps of the previous tap column
 #pragma unroll
@@ -348,17 +411,19 @@ retry:
                 for (int i = 0; i < PR; ++i) {
                     const float vcur = fmaf(wy, tcol[i + 1] - tcol[i], tcol[i]);
                     const float val = fmaf(wx, vcur - vprev[i], vprev[i]);
-                    const float dI = tI[i][j] - val;
-                    byr[i] = fmaf(dI, tIy[i][j], byr[i]);
-                    bxr[i] = fmaf(dI, tIx[i][j], bxr[i]);
+                    const float dI = TI_REF(i, j) - val;
+                    byr[i] = fmaf(dI, tG[i][j].x, byr[i]);
+                    bxr[i] = fmaf(dI, tG[i][j].y, bxr[i]);
                     vprev[i] = vcur;
                 }
             }
-            float by = byr[0], bx = bxr[0];
+            by = byr[0]; bx = bxr[0];
 #pragma unroll
             for (int i = 1; i < PR; ++i) { by += byr[i]; bx += bxr[i]; }
+            }
             float fby, fbx;
-            warp_sum2(by, bx, lane, fby, fbx);
+            if (LK_SHARED_SUMS) warp_sum2(by, bx, lane, fby, fbx);
+            else { fby = warp_sum_f2(by); fbx = warp_sum_f2(bx); }
             const double sby = (double)fby, sbx = (double)fbx;
             wpx += (unsigned)(nrows * ncols);
             nit += 1;

@@ -351,35 +351,6 @@ __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
 // plane and the three y-filtered product planes T0 (yy), T1 (xx), T2 (yx).
 constexpr int GRAD_CS = 8;
 
-template <int K>
-__device__ __forceinline__ void load_col_halo(const float* __restrict__ I, int xcol, int W, int pitch, int H, int y0, int lane, bool zb,
-                                              float (&e)[K + 2]) {
-    // e[0] = row y0-1, e[1..K] = rows y0..y0+K-1, e[K+1] = row y0+K; border rule along x and y applied here
-    float x[K];
-    const bool inside = xcol >= 0 && xcol < W;
-    if (inside || !zb) {
-        const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
-        load_col<K>(I + (size_t)xc * pitch, y0, pitch, x);
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = 0.f;
-    }
-    float upv = __shfl_up_sync(FULL, x[K - 1], 1);
-    float dnv = __shfl_down_sync(FULL, x[0], 1);
-    if (lane == 0) upv = zb ? 0.f : x[0];
-    if (lane == 31) dnv = 0.f;
-    e[0] = upv;
-#pragma unroll
-    for (int j = 0; j < K; ++j) e[j + 1] = x[j];
-    e[K + 1] = dnv;
-    if (!zb) {
-        // replicate below the last row: the neighbour of row H-1 is row H-1 itself (rows >= H hold guard zeros)
-#pragma unroll
-        for (int j = 1; j <= K + 1; ++j)
-            if (y0 + j - 1 == H) e[j] = e[j - 1];
-    }
-}
-
 // SRC: 0 layer plane (fp32), 1 raw Float64, 2 raw Float32, 3 raw UInt8 (value / 255)
 template <int K, int SRC, int G = 1>
 __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y0, float (&x)[K],
