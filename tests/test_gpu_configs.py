@@ -252,3 +252,46 @@ def test_matching_against_committed_golden(ctx):
     ok = (st & 1) == 1
     assert np.abs(pix[ok] - m["pix"][ok]).max() < 0.01 and np.abs(und[ok] - m["und"][ok]).max() < 0.01
     assert np.abs(pos[ok] - m["pos"][ok]).max() < 0.01 / 100
+
+
+def test_degenerate_inputs_match_oracle(ctx):
+    """Edge cases the reference path has to survive: keypoints on / outside the image border, priors that throw the estimate out
+    of the image, a texture-less image (eigenvalue gate), a single iteration, pyramid_levels = 0."""
+    fr, aff = synth.make_sequence(6100, 2, H=120, W=160)
+    f = synth.to_f64(fr)
+    H, W = 120, 160
+    pts = np.array([[1.0, 1.0], [H, W], [1.0, W], [H, 1.0], [0.5, 0.5], [H + 3.0, W + 3.0], [-5.0, 40.0], [60.0, W + 0.4],
+                    [2.2, 2.7], [H - 1.1, W - 1.3], [60.0, 80.0], [10.0, 150.0]])
+    pts = np.vstack([pts, synth.random_keypoints(9, 200, H, W, border=0.0)])
+    o0, o1 = O.LKPyramid(f[0], 3), O.LKPyramid(f[1], 3)
+    o0.update(f[0]); o1.update(f[1])
+    g0, g1 = slamklt.LKPyramid(ctx, f[0], 3), slamklt.LKPyramid(ctx, f[1], 3)
+    g0.update(f[0]); g1.update(f[1])
+
+    def same(ro, rg, min_ok=0):
+        (po, so, fo), (pg, sg, fg) = ro, rg
+        assert np.sum(so != sg) <= 1 and np.sum(fo != fg) <= 1
+        both = so & sg
+        assert both.sum() >= min_ok
+        if both.any():
+            assert np.abs(po[both] - pg[both]).max() < 0.02 and np.mean(np.abs(po[both] - pg[both]).max(axis=1) < 0.01) >= 0.99
+
+    for levels in (3, 0):
+        kw = dict(window_size=9, pyramid_levels=levels, max_distance=1.0)
+        same(O.fb_tracking(o0, o1, pts, **kw), slamklt.fb_tracking(g0, g1, pts, **kw), min_ok=20)
+    # priors that push the estimate far outside (coarsest-level scale)
+    rng = np.random.default_rng(0)
+    disp = rng.choice([-40.0, 0.0, 40.0], size=pts.shape)
+    kw = dict(window_size=9, pyramid_levels=2, max_distance=1.0)
+    same(O.fb_tracking(o0, o1, pts, displacement=disp, **kw), slamklt.fb_tracking(g0, g1, pts, displacement=disp, **kw))
+    # a single iteration
+    same(O.fb_tracking(o0, o1, pts, iterations=1, **kw), slamklt.fb_tracking(g0, g1, pts, iterations=1, **kw), min_ok=5)
+    # texture-less images: every point fails the eigenvalue gate in both
+    flat = np.full((H, W), 0.5)
+    of, gf = O.LKPyramid(flat, 3), slamklt.LKPyramid(ctx, flat, 3)
+    of.update(flat); gf.update(flat)
+    ro, rg = O.fb_tracking(of, of, pts, **kw), slamklt.fb_tracking(gf, gf, pts, **kw)
+    assert not ro[1].any() and not rg[1].any() and not rg[2].any()
+    # detect on the flat image finds nothing; on a tiny image with more cells than pixels the grid is clipped
+    e = slamklt.Extractor(500, 5, (4, 5), 35)
+    assert len(slamklt.detect(ctx, e, flat, np.zeros((0, 2)))) == 0 == len(O.detect(O.Extractor(500, 5, (4, 5), 35), flat, np.zeros((0, 2))))
