@@ -329,8 +329,19 @@ def main():
             r = slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST); t2 = time.perf_counter()
             slamklt.detect(ctx, ext1k, f64[1], r[0][r[1]]); t3 = time.perf_counter()
             t_upd.append(t1 - t0); t_trk.append(t2 - t1); t_det.append(t3 - t2)
+        # optical_flow_matching! as one device call: 2000 keypoints, half of them 3-D with a projected prior
+        kp2k = kpA[0][:N_PTS]
+        sc = synth.matching_scene(5, kp2k, synth.true_flow(affs, 0, 1, kp2k))
+        cam = slamklt.Camera(**sc["camera"])
+        t_mat = []
+        for i in range(23):
+            t0 = time.perf_counter()
+            slamklt.optical_flow_matching_frame(pa, pb, kp2k, sc["is_3d"], sc["world"], sc["cw"], cam, window_size=WINDOW,
+                                                pyramid_levels=LEVELS, max_distance=MAX_DIST)
+            if i >= 3:
+                t_mat.append(time.perf_counter() - t0)
         single = {"update_ms": 1e3 * float(np.median(t_upd)), "fb_tracking_1000kp_ms": 1e3 * float(np.median(t_trk)),
-                  "detect_ms": 1e3 * float(np.median(t_det)),
+                  "detect_ms": 1e3 * float(np.median(t_det)), "optical_flow_matching_2000kp_ms": 1e3 * float(np.median(t_mat)),
                   "note": "host wall clock per call, Float64 host image in, results out (synchronous C ABI calls)"}
 
     # ---------------- max over ranks, gather of tracked-keypoint counts
@@ -429,6 +440,19 @@ def main():
                                 "sample": f"{n_pairs} frame pairs of the same batch: update!(pyramid) + fb_tracking!, frames spread over "
                                           f"{cores} threads, best of 3 passes, {t_cpu:.2f}s wall per pass",
                                 "frames_per_s": n_pairs / t_cpu, "tracked_ok": good}
+        # the matching call of the single-frame leg on the CPU path (point loop threaded like lucas_kanade.jl:33)
+        from oracle import oracle as O
+        O.set_threads(cores)
+        o0, o1 = O.LKPyramid(f64[0], LEVELS), O.LKPyramid(f64[1], LEVELS)
+        o0.update(f64[0]); o1.update(f64[1])
+        ocam = O.Camera(**sc["camera"])
+        t_m = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            O.optical_flow_matching(o0, o1, kp2k, sc["is_3d"], sc["world"], None, sc["cw"], ocam, window_size=WINDOW,
+                                    pyramid_levels=LEVELS, max_distance=MAX_DIST)
+            t_m.append(time.perf_counter() - t0)
+        line["cpu_baseline"]["optical_flow_matching_2000kp_ms"] = 1e3 * min(t_m)
     elif rank == 0:
         line["cpu_baseline"] = None
 
