@@ -321,14 +321,24 @@ def main():
         pa, pb = slamklt.LKPyramid(ctx, f64[0], LEVELS), slamklt.LKPyramid(ctx, f64[1], LEVELS)
         kp1k = kpA[0][:1000]
         ext1k = slamklt.Extractor(1000, 17, (11, 36), 35)
+        # images in the layout the Julia caller hands over (column-major), so no host-side transpose is inside the timings
+        fcol = [np.asfortranarray(f64[k]) for k in range(3)]
+        pin = slamklt.PinnedArray((W, H), np.float64)          # the same frame in page-locked memory (slamklt_host_alloc)
+        pin.array[...] = f64[1].T
+        pin_img = pin.array.T                                   # (H, W) view, column-major
+        u8col = np.asfortranarray(frames_u8[1])
         for i in range(3):
-            pb.update(f64[1 + i % 2]); slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST)
-        t_upd, t_trk, t_det = [], [], []
+            pb.update(fcol[1 + i % 2]); slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST)
+        t_upd, t_trk, t_det, t_pin, t_u8 = [], [], [], [], []
         for i in range(20):
-            t0 = time.perf_counter(); pb.update(f64[1 + i % 2]); t1 = time.perf_counter()
+            t0 = time.perf_counter(); pb.update(fcol[1 + i % 2]); t1 = time.perf_counter()
             r = slamklt.fb_tracking(pa, pb, kp1k, window_size=WINDOW, pyramid_levels=LEVELS, max_distance=MAX_DIST); t2 = time.perf_counter()
-            slamklt.detect(ctx, ext1k, f64[1], r[0][r[1]]); t3 = time.perf_counter()
-            t_upd.append(t1 - t0); t_trk.append(t2 - t1); t_det.append(t3 - t2)
+            slamklt.detect(ctx, ext1k, fcol[1], r[0][r[1]]); t3 = time.perf_counter()
+            pb.update(pin_img); t4 = time.perf_counter()
+            pb.update(u8col); t5 = time.perf_counter()
+            t_upd.append(t1 - t0); t_trk.append(t2 - t1); t_det.append(t3 - t2); t_pin.append(t4 - t3); t_u8.append(t5 - t4)
+        pb.update(fcol[1])
+        pin.free()
         # optical_flow_matching! as one device call: 2000 keypoints, half of them 3-D with a projected prior
         kp2k = kpA[0][:N_PTS]
         sc = synth.matching_scene(5, kp2k, synth.true_flow(affs, 0, 1, kp2k))
@@ -342,6 +352,7 @@ def main():
                 t_mat.append(time.perf_counter() - t0)
         single = {"update_ms": 1e3 * float(np.median(t_upd)), "fb_tracking_1000kp_ms": 1e3 * float(np.median(t_trk)),
                   "detect_ms": 1e3 * float(np.median(t_det)), "optical_flow_matching_2000kp_ms": 1e3 * float(np.median(t_mat)),
+                  "update_pinned_f64_ms": 1e3 * float(np.median(t_pin)), "update_u8_ms": 1e3 * float(np.median(t_u8)),
                   "note": "host wall clock per call, Float64 host image in, results out (synchronous C ABI calls)"}
 
     # ---------------- max over ranks, gather of tracked-keypoint counts
