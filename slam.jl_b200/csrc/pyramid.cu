@@ -304,6 +304,7 @@ struct ColArgs {
     int f0, n_frames;
     int H, W, pitch;
     int zero_border;       // blur: NA mode; grad: Fill(0) Scharr border
+    int strip;             // k_cols_all: columns per warp strip
     size_t o_in;           // layer
     size_t o_out0;         // blur: T0;   grad: T0,T1,T2 consecutive
     size_t o_grad;         // grad only: interleaved (Iy, Ix)
@@ -451,7 +452,8 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int H = a.H, W = a.W, pitch = a.pitch;
-    const int strips = (W + GRAD_CS - 1) / GRAD_CS;
+    const int cs = a.strip;  // columns per warp strip (GRAD_CS for large batches, narrower when there are few frames)
+    const int strips = (W + cs - 1) / cs;
     const int total = a.n_frames * strips;
     const int y0 = lane * K;
     const bool zb = a.zero_border != 0;
@@ -460,11 +462,11 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
     __shared__ __align__(16) double2 sRaw[STAGED ? 4 * 2 * RawStage<K>::STAGE_UNITS : 1];
     double2* const sMine = sRaw + (threadIdx.x >> 5) * 2 * RawStage<K>::STAGE_UNITS + lane * RawStage<K>::LU;
     for (int w = warp; w < total; w += nwarps) {
-        const int f = w / strips, xb = (w - f * strips) * GRAD_CS;
+        const int f = w / strips, xb = (w - f * strips) * cs;
         float* fb = a.fs.frame(a.f0 + f);
         const float* I = fb + a.o_in;
         float em[K + 2], ec[K + 2], ep[K + 2];
-        const int xe = min(xb + GRAD_CS, W);
+        const int xe = min(xb + cs, W);
         // column c (clamped into the image) -> stage c & 1; issued one iteration before it is consumed
         auto stage_issue = [&](int c) {
             if constexpr (STAGED) {
@@ -865,8 +867,12 @@ static void launch_cols_all_g(cudaStream_t s, int src, int blocks, int threads, 
 }
 
 template <int K>
-static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
-    const int total_warps = a.n_frames * ((a.W + GRAD_CS - 1) / GRAD_CS);
+static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a_in, const IirDev& c4, const IirDev& c1) {
+    // strip width: GRAD_CS columns amortise the two halo columns; with few frames narrower strips give every SM several warps
+    ColArgs a = a_in;
+    a.strip = GRAD_CS;
+    while (a.strip > 1 && a.n_frames * ((a.W + a.strip - 1) / a.strip) < 148 * 8) a.strip >>= 1;
+    const int total_warps = a.n_frames * ((a.W + a.strip - 1) / a.strip);
     const int wpb = 4;
     int blocks = (total_warps + wpb - 1) / wpb;
     const int maxb = 148 * 16;
