@@ -189,7 +189,20 @@ def main():
         import torch
         import torch.distributed as dist_
         torch.cuda.set_device(local_rank)
-        dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner to stdout when the first communicator is created; stdout carries exactly one JSON
+        # line, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            t = torch.zeros(1, device=torch.device("cuda", local_rank))
+            dist_.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         dist = dist_
 
     ctx = slamklt.Context(local_rank)
