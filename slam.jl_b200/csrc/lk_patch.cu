@@ -95,12 +95,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // LK_MAXNREG caps the registers directly instead.  Measured on B200 (64 x 2000 keypoints): 128 registers / 16 warps per SM 1.11 ms;
 // uncapped the kernel wants 160 registers; 120 (16 warps) 1.11 ms, 112 (18 warps, 24 B spill) 1.18 ms, 104 (18 warps) 1.25 ms,
 // 96 (20 warps, ~200 B spill) slower still: the spills cost more than the extra warps hide.  Fewer resident warps through
-// SLAMKLT_LK_PAD_KB: 12 warps 1.34 ms, 8 warps 2.01 ms.
+// SLAMKLT_LK_PAD_KB: 12 warps 1.34 ms, 8 warps 2.01 ms.  CTA size at 16 warps per SM: 4 / 2 / 1 warps per CTA 1.074 / 1.055 / 0.996 ms --
+// keypoints need very different numbers of iterations, and a CTA keeps its slot until its slowest warp is done, so one-warp CTAs
+// (no barrier is used anywhere in the kernel) keep all 16 warp slots busy.
 #ifndef LK_WPB
-#define LK_WPB 4
+#define LK_WPB 1
 #endif
 #ifndef LK_MINB
-#define LK_MINB 4
+#define LK_MINB (16 / LK_WPB)
 #endif
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
