@@ -185,7 +185,8 @@ struct slamklt_ctx {
     std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_join = nullptr;
     std::mutex mu;
-    unsigned long long* d_counters = nullptr;
+    unsigned long long* d_counters = nullptr;  // [0..1] executed window-iterations / iterations, then the work-counter ring
+    unsigned work_idx = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
     DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match;
     HostBuf h_out, h_status, h_misc;
@@ -198,6 +199,10 @@ struct slamklt_ctx {
     std::map<std::string, std::pair<double, long long>> prof_acc;
     const Hook* hk() const { return prof_on ? &hook : nullptr; }
 };
+
+// work counters of the persistent tracking grid: a ring, one slot per launch (the launcher zeroes the slot on its stream)
+static constexpr int WORK_RING = 1024;
+static unsigned* work_slot(slamklt_ctx* c) { return reinterpret_cast<unsigned*>(c->d_counters + 2) + (c->work_idx++ % WORK_RING); }
 
 static void prof_mark(void* user, const char* name) {
     slamklt_ctx* c = (slamklt_ctx*)user;
@@ -341,8 +346,8 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-    CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    CK(cudaMalloc(&c->d_counters, 2 * sizeof(unsigned long long) + WORK_RING * sizeof(unsigned)));
+    CK(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long) + WORK_RING * sizeof(unsigned), c->stream));
     *out = c;
     return 0;
 }
@@ -681,7 +686,7 @@ static int run_lk_single(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr
     a.n_per_frame = n; a.n_frames = 1;
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-    a.counters = c->d_counters;
+    a.counters = c->d_counters; a.work = work_slot(c);
     c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
     prof_end(c);
@@ -766,7 +771,7 @@ int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_py
     a.n_per_frame = n; a.n_frames = 1;
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-    a.counters = c->d_counters;
+    a.counters = c->d_counters; a.work = work_slot(c);
     mark(c->hk(), "k_lk_matching");
     if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
     c->launches += 1;
@@ -854,7 +859,7 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     a.n_per_frame = n; a.n_frames = 1;
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-    a.counters = c->d_counters;
+    a.counters = c->d_counters; a.work = work_slot(c);
     mark(c->hk(), "k_lk_matching");
     if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
     mark(c->hk(), "k_match_update");
@@ -1063,7 +1068,7 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     a.n_per_frame = b->n_pts; a.n_frames = b->n_frames;
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-    a.counters = c->d_counters;
+    a.counters = c->d_counters; a.work = work_slot(c);
     c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
     prof_end(c);
@@ -1150,7 +1155,7 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     a.mode = 1;
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
-    a.counters = c->d_counters;
+    a.counters = c->d_counters; a.work = work_slot(c);
     a.n_per_frame = n_pts;
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;

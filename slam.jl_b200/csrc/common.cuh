@@ -82,6 +82,7 @@ struct LKArgs {
     unsigned long long* counters;  // [0] window px * iterations, [1] iterations
     const uint8_t* has_prior;      // mode 2: per point, 1 = 3-D keypoint tracked first with disp_in and levels3d, 2 = skip (status 8)
     int levels3d, pad2_;
+    unsigned* work;                // nullable: device counter the persistent grid draws keypoint indices from
 };
 
 struct DetArgs {

@@ -108,32 +108,24 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int W2, int PR, int PC>
-#ifdef LK_MAXNREG
-__global__ void __maxnreg__(LK_MAXNREG) k_lk_patch(const LKArgs a) {
-#else
-__global__ void __launch_bounds__(32 * LK_WPB, LK_MINB) k_lk_patch(const LKArgs a) {
-#endif
-    static_assert(PR * 8 >= W2 && PC * 4 >= W2, "patch grid must cover the window");
-    constexpr int RSPAN = PR * 8 + 1, CSPAN = PC * 4 + 1;  // tap rows / columns touched by the lanes
-    // tile rows: multiple of 4 (16-byte staging), >= RSPAN + 8, and PC*TR = 8 (mod 32) so that the 8 x 4 lane grid (row
-    // stride PR = 3 words, column-group stride PC*TR words) hits 32 distinct banks: TR = 40 for PC = 5, 44 for PC = 6
-    constexpr int TR = PC == 5 ? 40 : 44;
+// tile geometry of the patch kernel: rows a multiple of 4 (16-byte staging), >= RSPAN + 8, and PC*TR = 8 (mod 32) so that the
+// 8 x 4 lane grid (row stride PR = 3 words, column-group stride PC*TR words) hits 32 distinct banks: TR = 40 for PC = 5, 44 for 6
+template <int PR, int PC>
+struct PatchTile {
+    static constexpr int RSPAN = PR * 8 + 1, CSPAN = PC * 4 + 1;  // tap rows / columns touched by the lanes
+    static constexpr int TR = PC == 5 ? 40 : 44;
+    static constexpr int TC = CSPAN + 8;
     static_assert(TR >= RSPAN + 8 && TR % 4 == 0 && (PC * TR) % 32 == 8 && PR == 3, "tile geometry");
-    constexpr int TC = CSPAN + 8;                           // tile columns
-    constexpr int RG = TR / 4, CGN = 32 / RG;               // staging: RG row groups per column, CGN columns per instruction
-    __shared__ __align__(16) float sTile[LK_WPB][TC][TR];
-    __shared__ __align__(8) uint64_t sBar[LK_WPB];
-    float (*sT)[TR] = sTile[threadIdx.x >> 5];
-    uint64_t* bar = &sBar[threadIdx.x >> 5];
-    unsigned parity = 0;
-    if (LK_TMA && (threadIdx.x & 31) == 0) mbar_init(bar, 1);
-    __syncwarp();
+};
 
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int total = a.n_frames * a.n_per_frame;
-    if (gw >= total) return;
+// one keypoint, one warp: all levels of the forward pass, the backward pass and the gates
+template <int W2, int PR, int PC>
+__device__ __forceinline__ void lk_point(const LKArgs& a, const int gw, const int lane, float (*sT)[PatchTile<PR, PC>::TR], uint64_t* bar,
+                                         unsigned& parity) {
+    static_assert(PR * 8 >= W2 && PC * 4 >= W2, "patch grid must cover the window");
+    constexpr int RSPAN = PatchTile<PR, PC>::RSPAN, CSPAN = PatchTile<PR, PC>::CSPAN;
+    constexpr int TR = PatchTile<PR, PC>::TR, TC = PatchTile<PR, PC>::TC;
+    constexpr int RG = TR / 4, CGN = 32 / RG;               // staging: RG row groups per column, CGN columns per instruction
     const int f = gw / a.n_per_frame;
     const float* const fbA0 = a.A.frame(a.offA + f);
     const float* const fbB0 = a.B.frame(a.offB + f);
@@ -479,6 +471,42 @@ retry:
     }
 }
 
+// Kernel: one warp per keypoint.  With a.work != nullptr the grid is persistent (one-warp CTAs filling every SM) and every warp
+// draws keypoint indices from a device counter -- the next index is requested before the current keypoint is processed, so the
+// atomic's latency is hidden; without it CTA i handles keypoints i*LK_WPB .. i*LK_WPB + LK_WPB-1.
+template <int W2, int PR, int PC>
+#ifdef LK_MAXNREG
+__global__ void __maxnreg__(LK_MAXNREG) k_lk_patch(const LKArgs a) {
+#else
+__global__ void __launch_bounds__(32 * LK_WPB, LK_MINB) k_lk_patch(const LKArgs a) {
+#endif
+    constexpr int TR = PatchTile<PR, PC>::TR, TC = PatchTile<PR, PC>::TC;
+    __shared__ __align__(16) float sTile[LK_WPB][TC][TR];
+    __shared__ __align__(8) uint64_t sBar[LK_WPB];
+    float (*sT)[TR] = sTile[threadIdx.x >> 5];
+    uint64_t* bar = &sBar[threadIdx.x >> 5];
+    unsigned parity = 0;
+    if (LK_TMA && (threadIdx.x & 31) == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int total = a.n_frames * a.n_per_frame;
+    if (a.work == nullptr) {
+        const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (gw < total) lk_point<W2, PR, PC>(a, gw, lane, sT, bar, parity);
+        return;
+    }
+    int gw = 0;
+    if (lane == 0) gw = (int)atomicAdd(a.work, 1u);
+    gw = __shfl_sync(FULL, gw, 0);
+    while (gw < total) {
+        int next = 0;
+        if (lane == 0) next = (int)atomicAdd(a.work, 1u);
+        lk_point<W2, PR, PC>(a, gw, lane, sT, bar, parity);
+        __syncwarp();
+        gw = __shfl_sync(FULL, next, 0);
+    }
+}
+
 // returns false when this variant does not cover the window size
 bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
     const int total = a.n_frames * a.n_per_frame;
@@ -491,9 +519,24 @@ bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
         if (kb > 0) cudaFuncSetAttribute(k_lk_patch<19, 3, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
         return kb * 1024;
     }();
-    if (w2 <= 19) k_lk_patch<19, 3, 5><<<blocks, 32 * LK_WPB, pad, s>>>(a);
-    else if (w2 <= 23) k_lk_patch<23, 3, 6><<<blocks, 32 * LK_WPB, 0, s>>>(a);
-    else return false;
+    if (w2 > 23) return false;
+    int grid = blocks;
+    static const bool persistent = getenv("SLAMKLT_LK_STATIC") == nullptr;
+    LKArgs b = a;
+    if (!persistent) b.work = nullptr;
+    if (b.work) {
+        // persistent grid: every warp slot of every SM, keypoints drawn from the counter (zeroed on this stream first)
+        static const int slots = [] {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return sms * LK_MINB;
+        }();
+        if (blocks > slots) { grid = slots; cudaMemsetAsync(b.work, 0, sizeof(unsigned), s); }
+        else b.work = nullptr;  // fewer keypoints than warp slots: one CTA each
+    }
+    if (w2 <= 19) k_lk_patch<19, 3, 5><<<grid, 32 * LK_WPB, pad, s>>>(b);
+    else k_lk_patch<23, 3, 6><<<grid, 32 * LK_WPB, 0, s>>>(b);
     return true;
 }
 
