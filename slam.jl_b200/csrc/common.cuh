@@ -83,6 +83,7 @@ struct LKArgs {
     const uint8_t* has_prior;      // mode 2: per point, 1 = 3-D keypoint tracked first with disp_in and levels3d, 2 = skip (status 8)
     int levels3d, pad2_;
     unsigned* work;                // nullable: device counter the persistent grid draws keypoint indices from
+    int chunk, pad3_;              // keypoints drawn per request
 };
 
 struct DetArgs {

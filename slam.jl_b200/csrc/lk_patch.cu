@@ -495,15 +495,22 @@ __global__ void __launch_bounds__(32 * LK_WPB, LK_MINB) k_lk_patch(const LKArgs 
         if (gw < total) lk_point<W2, PR, PC>(a, gw, lane, sT, bar, parity);
         return;
     }
-    int gw = 0;
-    if (lane == 0) gw = (int)atomicAdd(a.work, 1u);
-    gw = __shfl_sync(FULL, gw, 0);
-    while (gw < total) {
+    // a warp draws `chunk` consecutive keypoints per request (SLAMKLT_LK_CHUNK, default 1).  Measured: 1 / 2 / 4 / 8 keypoints per
+    // request = 0.955 / 0.997 / 1.114 / 1.241 ms -- neighbours in the caller's order are better handled at the same time by
+    // different warps (they meet in L2) than back to back by one warp
+    const unsigned chunk = (unsigned)a.chunk;
+    int base = 0;
+    if (lane == 0) base = (int)atomicAdd(a.work, chunk);
+    base = __shfl_sync(FULL, base, 0);
+    while (base < total) {
         int next = 0;
-        if (lane == 0) next = (int)atomicAdd(a.work, 1u);
-        lk_point<W2, PR, PC>(a, gw, lane, sT, bar, parity);
-        __syncwarp();
-        gw = __shfl_sync(FULL, next, 0);
+        if (lane == 0) next = (int)atomicAdd(a.work, chunk);
+        const int end = min(base + (int)chunk, total);
+        for (int gw = base; gw < end; ++gw) {
+            lk_point<W2, PR, PC>(a, gw, lane, sT, bar, parity);
+            __syncwarp();
+        }
+        base = __shfl_sync(FULL, next, 0);
     }
 }
 
@@ -532,7 +539,9 @@ bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             return sms * LK_MINB;
         }();
-        if (blocks > slots) { grid = slots; cudaMemsetAsync(b.work, 0, sizeof(unsigned), s); }
+        static const int chunk = [] { const char* e = getenv("SLAMKLT_LK_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
+        b.chunk = chunk;
+        if (blocks > slots * chunk) { grid = slots; cudaMemsetAsync(b.work, 0, sizeof(unsigned), s); }
         else b.work = nullptr;  // fewer keypoints than warp slots: one CTA each
     }
     if (w2 <= 19) k_lk_patch<19, 3, 5><<<grid, 32 * LK_WPB, pad, s>>>(b);
