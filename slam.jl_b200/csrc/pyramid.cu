@@ -22,6 +22,8 @@
 
 #include "common.cuh"
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 // experiment knob: software prefetch of the raw Float64 column COLS_PREFETCH_DIST columns ahead (1 = into L2, 2 = into L1)
 #ifndef COLS_PREFETCH
@@ -856,33 +858,67 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int
 
 static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
 
+// Strip width of the fused column kernel.  A strip of cs columns costs about cs + 0.6 column-times (two halo columns that only
+// load); the grid runs in ceil(units / resident warps) rounds and the last round is rarely full, so the width is chosen to
+// minimise rounds * (cs + 0.6): at 64 KITTI frames cs = 8 gives 4.2 -> 5 rounds (84 % full), cs = 7 gives 4.8 -> 5 rounds (96 %).
+// With few frames the same rule picks narrow strips so that every SM gets warps.
+static int pick_strip(int n_frames, int W, int resident_warps) {
+    int best = GRAD_CS;
+    double best_cost = 1e300;
+    for (int cs = 1; cs <= 12; ++cs) {
+        const long long units = (long long)n_frames * ((W + cs - 1) / cs);
+        const long long rounds = (units + resident_warps - 1) / resident_warps;
+        const double cost = (double)rounds * (cs + 0.6);
+        if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = cs; }
+    }
+    return best;
+}
+
+template <typename Kern>
+static int resident_warps_of(Kern kern, int threads) {
+    static std::map<const void*, int> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find((const void*)kern);
+    if (it != cache.end()) return it->second;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+    const int r = sms * (per_sm > 0 ? per_sm : 1) * (threads / 32);
+    cache[(const void*)kern] = r;
+    return r;
+}
+
+template <int K, int SRC, int G>
+static void launch_cols_all_k(cudaStream_t s, ColArgs a, const IirDev& c4, const IirDev& c1) {
+    const int wpb = 4;
+    auto kern = k_cols_all<K, SRC, G>;
+    static const int forced = [] { const char* e = getenv("SLAMKLT_COLS_STRIP"); return e ? atoi(e) : 0; }();
+    a.strip = forced > 0 ? forced : pick_strip(a.n_frames, a.W, resident_warps_of(kern, wpb * 32));
+    const int total_warps = a.n_frames * ((a.W + a.strip - 1) / a.strip);
+    const int blocks = (total_warps + wpb - 1) / wpb;  // one strip per warp; the hardware hands CTAs to SMs as slots free up
+    kern<<<blocks, wpb * 32, 0, s>>>(a, c4, c1);
+}
+
 template <int K, int G>
-static void launch_cols_all_g(cudaStream_t s, int src, int blocks, int threads, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
+static void launch_cols_all_g(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
     switch (src) {
-        case 0: k_cols_all<K, 0, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
-        case 1: k_cols_all<K, 1, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
-        case 2: k_cols_all<K, 2, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
-        default: k_cols_all<K, 3, G><<<blocks, threads, 0, s>>>(a, c4, c1); break;
+        case 0: launch_cols_all_k<K, 0, G>(s, a, c4, c1); break;
+        case 1: launch_cols_all_k<K, 1, G>(s, a, c4, c1); break;
+        case 2: launch_cols_all_k<K, 2, G>(s, a, c4, c1); break;
+        default: launch_cols_all_k<K, 3, G>(s, a, c4, c1); break;
     }
 }
 
 template <int K>
-static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a_in, const IirDev& c4, const IirDev& c1) {
-    // strip width: GRAD_CS columns amortise the two halo columns; with few frames narrower strips give every SM several warps
-    ColArgs a = a_in;
-    a.strip = GRAD_CS;
-    while (a.strip > 1 && a.n_frames * ((a.W + a.strip - 1) / a.strip) < 148 * 8) a.strip >>= 1;
-    const int total_warps = a.n_frames * ((a.W + a.strip - 1) / a.strip);
-    const int wpb = 4;
-    int blocks = (total_warps + wpb - 1) / wpb;
-    const int maxb = 148 * 16;
-    if (blocks > maxb) blocks = maxb;
+static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
     // group-aligned variant when the image height is a multiple of the row-group size (4 rows, or 2 when K is not a multiple of 4)
     constexpr int GA = (K % 4 == 0) ? 4 : 2;
     const bool aligned = a.H % GA == 0 && (src != 1 || ((a.raw_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.raw) & 15) == 0)) &&
                          getenv("SLAMKLT_COLS_GENERIC") == nullptr;
-    if (aligned) launch_cols_all_g<K, GA>(s, src, blocks, wpb * 32, a, c4, c1);
-    else launch_cols_all_g<K, 1>(s, src, blocks, wpb * 32, a, c4, c1);
+    if (aligned) launch_cols_all_g<K, GA>(s, src, a, c4, c1);
+    else launch_cols_all_g<K, 1>(s, src, a, c4, c1);
 }
 
 static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
