@@ -1017,8 +1017,11 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
             dispatch_rows(sA, rb, c1, 0);
             snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
-            dim3 grid((N.H + 127) / 128, N.W, n_frames);
-            k_resize<<<grid, 128, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
+            // block = an even share of the output column rounded up to whole warps (188 rows -> 2 x 96 threads, not 128 + 60)
+            const int nby = (N.H + 127) / 128;
+            const int rthreads = (((N.H + nby - 1) / nby) + 31) / 32 * 32;
+            dim3 grid(nby, N.W, n_frames);
+            k_resize<<<grid, rthreads, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
             launches += 2;
         }
     }
