@@ -537,7 +537,11 @@ bool launch_lk_patch(cudaStream_t s, const LKArgs& a) {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            return sms * LK_MINB;
+            // SLAMKLT_LK_SLOTS: resident one-warp CTAs per SM of the persistent grid (default: all 16 the registers allow);
+            // fewer leave room for the next batch's pyramid kernels to run next to the tracking kernel
+            const char* e = getenv("SLAMKLT_LK_SLOTS");
+            const int per_sm = e ? atoi(e) : LK_MINB;
+            return sms * (per_sm >= 1 && per_sm <= LK_MINB ? per_sm : LK_MINB);
         }();
         static const int chunk = [] { const char* e = getenv("SLAMKLT_LK_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();
         b.chunk = chunk;
