@@ -24,6 +24,9 @@ for levels, shape in ((2, (75, 131)), (1, (33, 47)), (2, (72, 128))):  # the las
     slamklt.optical_flow_matching_frame(a, b, pts, sc["is_3d"], sc["world"], sc["cw"], cam, pyramid_levels=levels)
     slamklt.optical_flow_matching_frame(a, b, pts, sc["is_3d"], sc["world"], sc["cw"], cam, right_camera=rcam, undistorted=pts,
                                         stereo=True, pyramid_levels=levels)
+# more keypoints than warp slots (148 x 16): the tracking kernel runs as a persistent grid drawing indices from the work counter
+many = synth.random_keypoints(11, 3000, 72, 128, border=1.0)
+slamklt.fb_tracking(a, b, many, window_size=9, pyramid_levels=2, max_distance=1.0)
 e = slamklt.Extractor(100, 8, (3, 4), 35)
 slamklt.detect(ctx, e, f[0], np.array([[10.0, 10.0], [60.0, 100.0]]))
 slamklt.detect(ctx, e, fr[0], np.zeros((0, 2)))
