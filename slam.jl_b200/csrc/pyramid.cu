@@ -783,9 +783,10 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
 // ----------------------------------------------------------------------------------------------
 // bilinear decimation to ceil(size/2)  (pyramid.jl:120-121,132-133; [3P] imresize!)
 // ----------------------------------------------------------------------------------------------
+constexpr int RESIZE_CPB = 8;  // output columns per CTA
+
 __global__ void k_resize(FrameSet fs, int f0, size_t o_in, int Hi, int Wi, int pin, size_t o_out, int Ho, int Wo, int pout) {
     const int f = blockIdx.z;
-    const int j = blockIdx.y;  // output column (0-based)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Ho) return;
     float* fb = fs.frame(f0 + f);
@@ -793,15 +794,22 @@ __global__ void k_resize(FrameSet fs, int f0, size_t o_in, int Hi, int Wi, int p
     float* out = fb + o_out;
     // 1-based source coordinate sf*(i1 - 0.5) + 0.5 with i1 = i+1; computed in double like the reference
     const double sy = (double)Hi / (double)Ho, sx = (double)Wi / (double)Wo;
-    const double ry = sy * ((double)i + 0.5) + 0.5, rx = sx * ((double)j + 0.5) + 0.5;
-    int iy = (int)floor(ry), ix = (int)floor(rx);
+    const double ry = sy * ((double)i + 0.5) + 0.5;
+    int iy = (int)floor(ry);
     iy = min(max(iy, 1), Hi - 1);
-    ix = min(max(ix, 1), Wi - 1);
-    const float wy = (float)(ry - iy), wx = (float)(rx - ix);
-    const float* p = in + (iy - 1) + (size_t)(ix - 1) * pin;
-    const float c0 = (1.f - wy) * p[0] + wy * p[1];
-    const float c1 = (1.f - wy) * p[pin] + wy * p[pin + 1];
-    out[i + (size_t)j * pout] = (1.f - wx) * c0 + wx * c1;
+    const float wy = (float)(ry - iy);
+    // a CTA walks RESIZE_CPB output columns: eight times fewer, eight times longer CTAs than one column each
+    const int j0 = blockIdx.y * RESIZE_CPB, j1 = min(j0 + RESIZE_CPB, Wo);
+    for (int j = j0; j < j1; ++j) {
+        const double rx = sx * ((double)j + 0.5) + 0.5;
+        int ix = (int)floor(rx);
+        ix = min(max(ix, 1), Wi - 1);
+        const float wx = (float)(rx - ix);
+        const float* p = in + (iy - 1) + (size_t)(ix - 1) * pin;
+        const float c0 = (1.f - wy) * p[0] + wy * p[1];
+        const float c1 = (1.f - wy) * p[pin] + wy * p[pin + 1];
+        out[i + (size_t)j * pout] = (1.f - wx) * c0 + wx * c1;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1020,7 +1028,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             // block = an even share of the output column rounded up to whole warps (188 rows -> 2 x 96 threads, not 128 + 60)
             const int nby = (N.H + 127) / 128;
             const int rthreads = (((N.H + nby - 1) / nby) + 31) / 32 * 32;
-            dim3 grid(nby, N.W, n_frames);
+            dim3 grid(nby, (N.W + RESIZE_CPB - 1) / RESIZE_CPB, n_frames);
             k_resize<<<grid, rthreads, 0, sA>>>(fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
             launches += 2;
         }
