@@ -849,6 +849,8 @@ static void dispatch_cols_blur(cudaStream_t s, int K, const ColArgs& a, const Ii
 }
 
 static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int mode) {
+    // 16 rows per CTA, two CTAs per SM; 32 rows per CTA (one 1024-thread CTA per SM, 128-byte row segments) measured slower:
+    // prefix kernel of level 0 0.231 vs 0.176 ms
     if (a.W <= 32 * 40) {
         dim3 grid((a.H + 15) / 16, a.nplanes, a.n_frames);
         const int NC = (a.W + 39) / 40;
