@@ -12,6 +12,10 @@ parity tests read like calls into the reference:
     fb_tracking!(prev, cur, keypoints; ...)     tracker.jl:70      -> fb_tracking(prev, cur, keypoints, ...)
     Extractor(max_points, radius, grid, cell)   extractor.jl:21    -> Extractor(...)
     detect(e, image, current_points)            extractor.jl:63    -> detect(ctx, e, image, current_points)
+    optical_flow_matching!(mm, frame, from, to, stereo)  map_manager.jl:451 -> optical_flow_matching_frame(from, to, pixels, is_3d,
+                                                                           world, cw, camera, ...)  (arrays instead of dictionaries)
+    Camera(fx, fy, cx, cy, k1, k2, p1, p2, h, w; Ti0)   camera.jl:31      -> Camera(...)
+    preprocess! + klt_tracking! over many frames         front_end.jl:454  -> StreamBatch(ctx, H, W, levels, n_frames, max_points)
 
 Everything below is ctypes plumbing over the C ABI declared in include/slamklt.h.  There is NO CPU path:
 if the CUDA library is missing or no B200 is visible, construction fails loudly.
