@@ -334,13 +334,19 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     CK(cudaSetDevice(device));
     slamklt_ctx* c = new slamklt_ctx();
     c->device = device;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // stream priorities: pyramid-build streams above the tracking stream, so that the next batch's build kernels take the CTA
+    // slots the tracking kernel frees at its tail first (measured: step 1.664 -> 1.654 ms; SLAMKLT_NO_PRIO=1 turns it off)
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const bool prio = getenv("SLAMKLT_NO_PRIO") == nullptr;
+    const int p_build = prio ? prio_hi : 0, p_lk = prio ? prio_lo : 0;
+    CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, p_build));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     c->pyr_streams.main = c->stream;
-    CK(cudaStreamCreateWithFlags(&c->lk_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->pyr_streams.b, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->pyr_streams.c, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&c->lk_stream, cudaStreamNonBlocking, p_lk));
+    CK(cudaStreamCreateWithPriority(&c->pyr_streams.b, cudaStreamNonBlocking, p_build));
+    CK(cudaStreamCreateWithPriority(&c->pyr_streams.c, cudaStreamNonBlocking, p_build));
     for (auto& e : c->pyr_streams.ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     c->pyr_streams.parallel = getenv("SLAMKLT_SERIAL_BUILD") == nullptr;
     CK(cudaEventCreate(&c->ev0));
