@@ -77,7 +77,7 @@ class Stats(C.Structure):
 
 def build_library(force: bool = False) -> str:
     """Compile libslamklt.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_CSRC, f) for f in ("api.cu", "pyramid.cu", "lk.cu", "lk_patch.cu", "detect.cu", "match.cu", "common.cuh")]
+    srcs = [os.path.join(_CSRC, f) for f in ("api.cu", "pyramid.cu", "lk.cu", "lk_patch.cu", "lk_tma.cu", "detect.cu", "match.cu", "common.cuh")]
     srcs.append(os.path.join(_HERE, "..", "include", "slamklt.h"))
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:

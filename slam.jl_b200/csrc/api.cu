@@ -188,7 +188,7 @@ struct slamklt_ctx {
     unsigned long long* d_counters = nullptr;  // [0..1] executed window-iterations / iterations, then the work-counter ring
     unsigned work_idx = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
-    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match;
+    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match, gtab;
     HostBuf h_out, h_status, h_misc;
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
     // per-kernel profiling (off by default)
@@ -217,6 +217,7 @@ static void prof_end(slamklt_ctx* c) { if (c->prof_on) prof_mark(c, "<end>"); }
 struct slamklt_pyr {
     PyrGeom g;
     float* base = nullptr;
+    void* d_maps = nullptr;  // device array of per-level tensor maps over `base` (lk_tma.cu); views use their batch's
     bool owns = false;
     bool built = false;
     int mode = 0;
@@ -229,7 +230,8 @@ struct slamklt_batch {
     float* base = nullptr;
     int n_frames = 0, n_slots = 0, slot0 = 0, max_pts = 0, n_pts = 0;
     int up_dtype = -1, up_ld = 0;
-    DevBuf staging, img64, pts, outp, status;
+    void* d_maps = nullptr;  // device array of per-level tensor maps over the slot ring
+    DevBuf staging, img64, pts, outp, status, gtab;
     std::vector<slamklt_pyr*> views;
     bool primed = false;
     cudaEvent_t ev_lk_done = nullptr;  // last tracking kernel that read this batch's slots (recorded on the lk stream)
@@ -280,7 +282,38 @@ static float* pyr_frame_base(const slamklt_pyr* p) {
     }
     return p->base;
 }
-static FrameSet fs_of(const slamklt_pyr* p) { return FrameSet{pyr_frame_base(p), p->g.frame_elems, 1, 0}; }
+static FrameSet fs_of(const slamklt_pyr* p) {
+    if (p->parent) {
+        const slamklt_batch* b = p->parent;
+        return FrameSet{b->base, b->g.frame_elems, b->n_slots, (b->slot0 + p->logical_slot) % b->n_slots};
+    }
+    return FrameSet{p->base, p->g.frame_elems, 1, 0};
+}
+static const void* maps_of(const slamklt_pyr* p) { return p->parent ? p->parent->d_maps : p->d_maps; }
+
+// tensor maps of a frame ring for the TMA-staged tracking kernel, uploaded to 64-byte aligned device memory
+static int make_maps(slamklt_ctx* c, const PyrGeom& g, float* base, int n_slots, void** d_maps) {
+    std::vector<unsigned char> host(lk_tma_level_bytes() * MAX_LAYERS + 64);
+    unsigned char* hp = (unsigned char*)(((uintptr_t)host.data() + 63) & ~(uintptr_t)63);
+    char err[200];
+    if (lk_tma_encode(g, base, n_slots, hp, err, sizeof(err))) return fail(SLAMKLT_E_CUDA, "%s", err);
+    if (!*d_maps) CK(cudaMalloc(d_maps, lk_tma_level_bytes() * MAX_LAYERS));
+    CK(cudaMemcpyAsync(*d_maps, hp, lk_tma_level_bytes() * MAX_LAYERS, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // `host` goes out of scope
+    return 0;
+}
+
+// table of first-set-up structure tensors for the tracking kernel (SLAMKLT_LK_GTAB=0 computes them in the tracking warps)
+static int set_gtab(DevBuf& buf, LKArgs* a) {
+    static const bool on = !(getenv("SLAMKLT_LK_GTAB") && getenv("SLAMKLT_LK_GTAB")[0] == '0');
+    a->gtab = nullptr; a->gtab_levels = 0;
+    if (!on || !a->mapsA || !a->mapsB || 2 * a->window + 1 > 19) return 0;
+    const int nlv = std::max(a->levels, a->mode == 2 ? a->levels3d : 0) + 1;
+    int r = buf.ensure((size_t)a->n_frames * a->n_per_frame * nlv * 32);
+    if (r) return r;
+    a->gtab = buf.p; a->gtab_levels = nlv;
+    return 0;
+}
 static FrameSet fs_of(const slamklt_batch* b) { return FrameSet{b->base, b->g.frame_elems, b->n_slots, b->slot0}; }
 
 static int get_norms(slamklt_ctx* c, const PyrGeom& g, double sigma, const float** ny, const float** nx) {
@@ -361,9 +394,11 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
 int slamklt_ctx_destroy(slamklt_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    // every stream of the context may still use the buffers freed below
+    cudaStream_t all[] = {c->stream, c->lk_stream, c->copy_stream, c->d2h_stream, c->pyr_streams.b, c->pyr_streams.c};
+    for (cudaStream_t st : all) if (st) cudaStreamSynchronize(st);
     for (auto& kv : c->norm_cache) cudaFree(kv.second);
-    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match};
+    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match, &c->gtab};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
     for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
@@ -472,6 +507,8 @@ int slamklt_pyr_create(slamklt_ctx* c, int H, int W, int levels, slamklt_pyr** o
     if (e != cudaSuccess) { delete p; return fail(SLAMKLT_E_CUDA, "cudaMalloc pyramid failed: %s", cudaGetErrorString(e)); }
     cudaMemsetAsync(p->base, 0, (g.frame_elems + ALLOC_SLACK) * sizeof(float), c->stream);
     p->owns = true;
+    r = make_maps(c, g, p->base, 1, &p->d_maps);
+    if (r) { cudaFree(p->base); delete p; return r; }
     *out = p;
     return 0;
 }
@@ -484,6 +521,7 @@ int slamklt_pyr_destroy(slamklt_ctx* c, slamklt_pyr* p) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     if (p->owns && p->base) cudaFree(p->base);
+    if (p->d_maps) cudaFree(p->d_maps);
     delete p;
     return 0;
 }
@@ -544,7 +582,10 @@ int slamklt_pyr_copy(slamklt_ctx* c, slamklt_pyr* dst, const slamklt_pyr* src) {
     if (dst->g.H0 != src->g.H0 || dst->g.W0 != src->g.W0 || dst->g.nl != src->g.nl) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(dst->base, src->base, src->g.frame_elems * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    // batch slot views keep no base pointer of their own, and their batch may still be read by a tracking kernel on the lk stream
+    if (src->parent) BATCH_WAIT_LK(c, src->parent);
+    if (dst->parent) BATCH_WAIT_LK(c, dst->parent);
+    CK(cudaMemcpyAsync(pyr_frame_base(dst), pyr_frame_base(src), src->g.frame_elems * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     dst->built = src->built; dst->mode = src->mode;
     return 0;
 }
@@ -568,6 +609,7 @@ int slamklt_pyr_swap(slamklt_ctx* c, slamklt_pyr* a, slamklt_pyr* b) {
     if (a->g.H0 != b->g.H0 || a->g.W0 != b->g.W0 || a->g.nl != b->g.nl) return fail(SLAMKLT_E_INVALID, "pyramid shapes differ");
     std::lock_guard<std::mutex> lk(c->mu);
     std::swap(a->base, b->base);
+    std::swap(a->d_maps, b->d_maps);
     std::swap(a->built, b->built);
     std::swap(a->mode, b->mode);
     std::swap(a->owns, b->owns);
@@ -693,6 +735,8 @@ static int run_lk_single(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_pyr
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters; a.work = work_slot(c);
+    a.mapsA = maps_of(A); a.mapsB = maps_of(B);
+    if ((r = set_gtab(c->gtab, &a))) return r;
     c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
     prof_end(c);
@@ -758,6 +802,8 @@ int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_py
     if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    if (A->parent) BATCH_WAIT_LK(c, A->parent);
+    if (B->parent) BATCH_WAIT_LK(c, B->parent);
     if ((r = c->pts.ensure((size_t)n * 16))) return r;
     if ((r = c->disp.ensure((size_t)n * 16))) return r;
     if ((r = c->outp.ensure((size_t)n * 16))) return r;
@@ -778,9 +824,9 @@ int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_py
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters; a.work = work_slot(c);
-    mark(c->hk(), "k_lk_matching");
-    if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
-    c->launches += 1;
+    a.mapsA = maps_of(A); a.mapsB = maps_of(B);
+    if ((r = set_gtab(c->gtab, &a))) return r;
+    c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
     prof_end(c);
     if ((r = c->h_out.ensure((size_t)n * 16))) return r;
@@ -816,6 +862,8 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     if (!A->built || !B->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
+    if (A->parent) BATCH_WAIT_LK(c, A->parent);
+    if (B->parent) BATCH_WAIT_LK(c, B->parent);
     // device block: [pix 2n | world 3n | undist 2n | disp 2n | tracked 2n | out_pix 2n | out_und 2n | out_pos 3n] doubles, then
     // [is_3d n | flag n | status n] bytes
     const size_t N = (size_t)n;
@@ -866,11 +914,12 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters; a.work = work_slot(c);
-    mark(c->hk(), "k_lk_matching");
-    if (!launch_lk_patch(c->stream, a)) return fail(SLAMKLT_E_INVALID, "window_size not supported");
+    a.mapsA = maps_of(A); a.mapsB = maps_of(B);
+    if ((r = set_gtab(c->gtab, &a))) return r;
+    c->launches += launch_lk(c->stream, a, c->hk());
     mark(c->hk(), "k_match_update");
     launch_match_update(c->stream, m);
-    c->launches += 3;
+    c->launches += 2;
     CKL();
     prof_end(c);
     CK(cudaMemcpyAsync(out_pix, d_opix, N * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -991,6 +1040,7 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;
     b->views.resize(b->n_slots, nullptr);
     CK(cudaEventCreateWithFlags(&b->ev_lk_done, cudaEventDisableTiming));
+    if ((r = make_maps(c, g, b->base, b->n_slots, &b->d_maps))) return r;
     *out = b;
     return 0;
 }
@@ -1004,7 +1054,8 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     CK(cudaStreamSynchronize(c->lk_stream));
     for (auto* v : b->views) delete v;
     if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
-    b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release();
+    b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
+    if (b->d_maps) cudaFree(b->d_maps);
     cudaFree(b->base);
     delete b;
     return 0;
@@ -1075,6 +1126,8 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters; a.work = work_slot(c);
+    a.mapsA = b->d_maps; a.mapsB = b->d_maps;
+    if ((r = set_gtab(b->gtab, &a))) return r;
     c->launches += launch_lk(c->stream, a, c->hk());
     CKL();
     prof_end(c);
@@ -1163,6 +1216,10 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
     a.counters = c->d_counters; a.work = work_slot(c);
     a.n_per_frame = n_pts;
+    a.mapsA = b->d_maps; a.mapsB = b->d_maps;
+    a.n_frames = nf;
+    if ((r = set_gtab(b->gtab, &a))) return r;
+    char* const gtab0 = (char*)a.gtab;
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
         const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
@@ -1174,6 +1231,8 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
             a.pts = (const double*)b->pts.p + (size_t)f0 * n_pts * 2;
             a.out_pts = (double*)b->outp.p + (size_t)f0 * n_pts * 2;
             a.status = (uint8_t*)b->status.p + (size_t)f0 * n_pts;
+            if (gtab0) a.gtab = gtab0 + (size_t)f0 * n_pts * a.gtab_levels * 32;
+            if (nchunks > 1) a.work = work_slot(c);  // chunks may overlap on the lk stream's tail: one counter each
             c->launches += launch_lk(lks, a, c->hk());
             CKL();
             prof_end(c);

@@ -43,11 +43,8 @@ struct FrameSet {
     size_t frame_elems;
     int n_slots;
     int slot0;
-    __host__ __device__ float* frame(int f) const {
-        int s = slot0 + f;
-        s = s % n_slots;
-        return base + (size_t)s * frame_elems;
-    }
+    __host__ __device__ int slot(int f) const { return (slot0 + f) % n_slots; }  // physical slot of logical frame f
+    __host__ __device__ float* frame(int f) const { return base + (size_t)slot(f) * frame_elems; }
 };
 
 __host__ __device__ inline size_t plane_off(const LevelGeom& g, int plane) { return g.off + (size_t)plane * g.plane_elems; }
@@ -84,6 +81,13 @@ struct LKArgs {
     int levels3d, pad2_;
     unsigned* work;                // nullable: device counter the persistent grid draws keypoint indices from
     int chunk, pad3_;              // keypoints drawn per request
+    // TMA-staged kernel (lk_tma.cu): device arrays of per-level tensor maps (LKTmaLevel[MAX_LAYERS]) over the frame rings A and B;
+    // nullptr selects the cp.async kernel of lk_patch.cu
+    const void* mapsA;
+    const void* mapsB;
+    // optional table of first-set-up structure tensors, [keypoint][gtab_levels] entries of 32 bytes, filled by k_lk_gprep
+    void* gtab;
+    int gtab_levels, pad4_;
 };
 
 struct DetArgs {
@@ -138,6 +142,11 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
 bool launch_lk_patch(cudaStream_t s, const LKArgs& a);  // patch-mapped variant (lk_patch.cu), windows up to 23 x 23
+bool launch_lk_tma(cudaStream_t s, const LKArgs& a);    // TMA-staged patch variant (lk_tma.cu), windows up to 19 x 19
+// Tensor maps of one frame ring for the TMA-staged tracking kernel: fills MAX_LAYERS * lk_tma_level_bytes() bytes at host_out
+// (to be copied to 64-byte aligned device memory).  Returns 0, or -1 with a message in err.
+size_t lk_tma_level_bytes();
+int lk_tma_encode(const PyrGeom& g, float* base, int n_slots, void* host_out, char* err, size_t errcap);
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);
 

@@ -225,8 +225,11 @@ int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     const int wpb = (wpb_env >= 1 && wpb_env <= 4) ? wpb_env : 4;
     const int blocks = (total + wpb - 1) / wpb;
     const int w2 = 2 * a.window + 1;
-    static const bool use_rows = getenv("SLAMKLT_LK_VARIANT") && getenv("SLAMKLT_LK_VARIANT")[0] == 'r';  // A/B knob
-    if (!use_rows && launch_lk_patch(s, a)) return 1;
+    // A/B knob: 'r' = row-per-lane kernel (lk.cu), 'p' = cp.async patch kernel (lk_patch.cu); default = TMA-staged patch kernel
+    // (lk_tma.cu) where it covers the window, then the cp.async patch kernel, then the row kernel
+    static const char variant = getenv("SLAMKLT_LK_VARIANT") ? getenv("SLAMKLT_LK_VARIANT")[0] : 't';
+    if (variant == 't' && launch_lk_tma(s, a)) return a.gtab ? 2 : 1;
+    if (variant != 'r' && launch_lk_patch(s, a)) return 1;
     if (w2 <= 19) k_lk<19><<<blocks, wpb * 32, 0, s>>>(a);
     else if (w2 <= 23) k_lk<23><<<blocks, wpb * 32, 0, s>>>(a);
     else k_lk<31><<<blocks, wpb * 32, 0, s>>>(a);

@@ -295,7 +295,8 @@ retry:
             const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
             // fast path: the keypoint sits >= w+6 px inside the level and the estimate is within 3 px of it, so the estimate
             // lies in the image and get_offsets(point, estimate) is (w, w, w, w) as before: nothing to recompute
-            const bool fast = interior && (unsigned)(fy - py + 3) <= 6u && (unsigned)(fx - px + 3) <= 6u;
+            // (the window must still be the unclipped one: an earlier far-off estimate may have clipped it)
+            const bool fast = interior && nrows == 2 * w + 1 && ncols == 2 * w + 1 && (unsigned)(fy - py + 3) <= 6u && (unsigned)(fx - px + 3) <= 6u;
             if (!fast) {
                 // floor / ceil as integers serve both lies_in (1 <= pc <= size <=> floor >= 1 && ceil <= size) and get_offsets:
                 // floor(min(w, min(p, pc) - 1)) = min(w, min(p, floor pc) - 1), floor(min(w, H - max(p, pc))) = min(w, H - max(p, ceil pc))
