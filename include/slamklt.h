@@ -60,6 +60,12 @@ extern "C" {
 #define SLAMKLT_PLANE_SXX 7
 #define SLAMKLT_PLANE_SYX 8
 #define SLAMKLT_PLANE_BLUR 9 /* LKCache.gaussian_filtered (levels 0..L-1) */
+/* The device keeps the smoothed products as exclusive prefix sums along x (fp32, H_l x (W_l + 1), column 0 = 0) instead of the
+ * reference's 2-D integral images (lucas_kanade.jl:131-138); these three return exactly the planes the tracking kernel reads,
+ * so out must hold H_l * (W_l + 1) doubles.  A window's row sum is R[y, c1 + 1] - R[y, c0] (0-based columns c0..c1). */
+#define SLAMKLT_PLANE_RYY 10
+#define SLAMKLT_PLANE_RXX 11
+#define SLAMKLT_PLANE_RYX 12
 
 typedef struct slamklt_ctx slamklt_ctx;
 typedef struct slamklt_pyr slamklt_pyr;

@@ -37,7 +37,8 @@ LIB_PATH = os.environ.get("SLAMKLT_LIB", os.path.join(_CSRC, "libslamklt.so"))  
 
 F64, F32, U8 = 0, 1, 2
 MODE_UPDATE, MODE_CTOR = 0, 1
-PLANES = {"layer": 0, "Iy": 1, "Ix": 2, "Iyy": 3, "Ixx": 4, "Iyx": 5, "Syy": 6, "Sxx": 7, "Syx": 8, "blur": 9}
+PLANES = {"layer": 0, "Iy": 1, "Ix": 2, "Iyy": 3, "Ixx": 4, "Iyx": 5, "Syy": 6, "Sxx": 7, "Syx": 8, "blur": 9,
+          "Ryy": 10, "Rxx": 11, "Ryx": 12}  # R*: the device's row-prefix planes, (H, W + 1)
 
 E_INVALID, E_CUDA, E_LAYERS, E_NODEVICE, E_CAPACITY = -1, -2, -3, -4, -5
 
@@ -291,9 +292,10 @@ class LKPyramid:
         return H.value, W.value
 
     def plane(self, level: int, name: str) -> np.ndarray:
-        """lk.layers[level+1], lk.Iy[level+1], ... as Float64 (H_l, W_l)."""
+        """lk.layers[level+1], lk.Iy[level+1], ... as Float64 (H_l, W_l); the device's own row-prefix planes "Ryy" / "Rxx" /
+        "Ryx" (exclusive prefix sums along x of the smoothed products, what the tracking kernel reads) as (H_l, W_l + 1)."""
         H, W = self.level_shape(level)
-        out = np.empty((H, W), dtype=np.float64, order="F")
+        out = np.empty((H, W + (1 if name in ("Ryy", "Rxx", "Ryx") else 0)), dtype=np.float64, order="F")
         _ck(lib().slamklt_pyr_download(self.ctx._h, self._h, level, PLANES[name], _dp(out)))
         return out
 

@@ -309,7 +309,7 @@ static int set_gtab(DevBuf& buf, LKArgs* a) {
     a->gtab = nullptr; a->gtab_levels = 0;
     if (!on || !a->mapsA || !a->mapsB || 2 * a->window + 1 > 19) return 0;
     const int nlv = std::max(a->levels, a->mode == 2 ? a->levels3d : 0) + 1;
-    int r = buf.ensure((size_t)a->n_frames * a->n_per_frame * nlv * 32);
+    int r = buf.ensure((size_t)a->n_frames * a->n_per_frame * nlv * 16);
     if (r) return r;
     a->gtab = buf.p; a->gtab_levels = nlv;
     return 0;
@@ -637,7 +637,7 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
     if (!c || !p || !out) return fail(SLAMKLT_E_INVALID, "NULL argument");
     if (level < 0 || level >= p->g.nl) return fail(SLAMKLT_E_INVALID, "level %d out of range", level);
     int dp = DP_I, which = -1, comp = -1;  // which: smoothed product plane to recompute; comp: component of the gradient plane
-    bool sat = false;
+    bool sat = false, prefix = false;  // prefix: raw device row-prefix plane, W + 1 columns
     switch (plane) {
         case SLAMKLT_PLANE_LAYER: dp = DP_I; break;
         case SLAMKLT_PLANE_IY: dp = DP_GRAD; comp = 0; break;
@@ -649,14 +649,18 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
         case SLAMKLT_PLANE_SXX: which = 1; break;
         case SLAMKLT_PLANE_SYX: which = 2; break;
         case SLAMKLT_PLANE_BLUR: dp = DP_BLUR; break;
+        case SLAMKLT_PLANE_RYY: dp = DP_RYY; prefix = true; break;
+        case SLAMKLT_PLANE_RXX: dp = DP_RXX; prefix = true; break;
+        case SLAMKLT_PLANE_RYX: dp = DP_RYX; prefix = true; break;
         default: return fail(SLAMKLT_E_INVALID, "unknown plane %d", plane);
     }
-    if ((which >= 0 || comp >= 0) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    if ((which >= 0 || comp >= 0 || prefix) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     if (p->parent) BATCH_WAIT_LK(c, p->parent);
     const LevelGeom& L = p->g.lv[level];
-    std::vector<float> tmp((size_t)L.H * L.W * (comp >= 0 ? 2 : 1));
+    const int ncol = L.W + (prefix ? 1 : 0);
+    std::vector<float> tmp((size_t)L.H * ncol * (comp >= 0 ? 2 : 1));
     if (which >= 0) {
         // the pyramid keeps only the row-prefix form of the smoothed planes; rebuild the plain plane from the y-filtered scratch
         c->launches += launch_smoothed_plane(c->stream, fs_of(p), 0, p->g, level, which, c->hk());
@@ -666,10 +670,10 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
     }
     const float* src = pyr_frame_base(p) + plane_off(L, dp);
     const size_t rowb = (size_t)L.H * sizeof(float) * (comp >= 0 ? 2 : 1), pitchb = (size_t)L.pitch * sizeof(float) * (comp >= 0 ? 2 : 1);
-    CK(cudaMemcpy2DAsync(tmp.data(), rowb, src, pitchb, rowb, L.W, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(tmp.data(), rowb, src, pitchb, rowb, ncol, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->d2h += tmp.size() * sizeof(float);
-    const size_t npx = (size_t)L.H * L.W;
+    const size_t npx = (size_t)L.H * ncol;
     if (comp >= 0) for (size_t i = 0; i < npx; ++i) out[i] = (double)tmp[2 * i + comp];
     else for (size_t i = 0; i < npx; ++i) out[i] = (double)tmp[i];
     if (sat) {  // integral_image!, lucas_kanade.jl:131-138, in Float64 on the host (parity access only)
@@ -1231,7 +1235,7 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
             a.pts = (const double*)b->pts.p + (size_t)f0 * n_pts * 2;
             a.out_pts = (double*)b->outp.p + (size_t)f0 * n_pts * 2;
             a.status = (uint8_t*)b->status.p + (size_t)f0 * n_pts;
-            if (gtab0) a.gtab = gtab0 + (size_t)f0 * n_pts * a.gtab_levels * 32;
+            if (gtab0) a.gtab = gtab0 + (size_t)f0 * n_pts * a.gtab_levels * 16;
             if (nchunks > 1) a.work = work_slot(c);  // chunks may overlap on the lk stream's tail: one counter each
             c->launches += launch_lk(lks, a, c->hk());
             CKL();

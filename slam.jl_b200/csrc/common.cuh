@@ -85,7 +85,7 @@ struct LKArgs {
     // nullptr selects the cp.async kernel of lk_patch.cu
     const void* mapsA;
     const void* mapsB;
-    // optional table of first-set-up structure tensors, [keypoint][gtab_levels] entries of 32 bytes, filled by k_lk_gprep
+    // optional table of first-set-up structure tensors, [keypoint][gtab_levels] entries of 16 bytes, filled by k_lk_gprep
     void* gtab;
     int gtab_levels, pad4_;
 };

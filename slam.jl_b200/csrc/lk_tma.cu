@@ -176,8 +176,8 @@ __device__ __forceinline__ bool g_inverse(double ga, double gc, double gb, doubl
 // ---- G table pre-pass -----------------------------------------------------------------------------------------------------
 // One entry per (keypoint, level): the structure tensor of the window get_offsets(p, p) (lucas_kanade.jl:34-46) depends only on the
 // keypoint and the level, so it is computed once by an 8-lane group (lane = window rows r, r+8, r+16) instead of by all 32 lanes
-// of the tracking warp at every level.  Entry: g00, g01, g11 and a flag (1 = gate passed, 0 = failed / window empty).
-struct __align__(32) GEntry { double g00, g01, g11; long long ok; };
+// of the tracking warp at every level.  Entry: g00, g01, g11 of G^-1 (fp32) and a flag (1 = gate passed, 0 = failed / window empty).
+typedef float4 GEntry;  // g00, g01, g11 of G^-1 rounded to fp32, w = 1 when the gate passed
 
 __global__ void __launch_bounds__(128) k_lk_gprep(const LKArgs a, GEntry* __restrict__ tab) {
     const int sub = threadIdx.x & 7;
@@ -214,10 +214,9 @@ __global__ void __launch_bounds__(128) k_lk_gprep(const LKArgs a, GEntry* __rest
         syx += __shfl_xor_sync(FULL, syx, o);
     }
     if (sub == 0) {
-        GEntry e;
-        e.g00 = e.g01 = e.g11 = 0.0; e.ok = 0;
-        if (valid && g_inverse((double)syy, (double)sxx, (double)syx, a.eig_thr * (double)(nrows * ncols), e.g00, e.g01, e.g11)) e.ok = 1;
-        tab[item] = e;
+        double g00 = 0.0, g01 = 0.0, g11 = 0.0;
+        const bool pass = valid && g_inverse((double)syy, (double)sxx, (double)syx, a.eig_thr * (double)(nrows * ncols), g00, g01, g11);
+        tab[item] = make_float4((float)g00, (float)g01, (float)g11, pass ? 1.f : 0.f);
     }
 }
 
@@ -228,14 +227,29 @@ struct __align__(128) LKTmaSmem {
     float sT[T::TC][T::TR];
     __align__(128) float sI[T::AC][T::AR];
     __align__(128) float2 sG[T::AC][T::AR];
-    __align__(16) double dsave[2];  // displacement at the start of the current level (optflow! keeps it when the level fails)
-    uint64_t barT;
+    __align__(16) float2 sZ[4 * T::AR + 1];  // zeros at every offset j*AR the gradient loads use: patch rows outside the window read here
+    __align__(16) double q[2];               // forward result (the backward pass starts from it; the distance gate needs it again)
+    int dsave[4];                            // displacement at the start of the current level (optflow! keeps it when the level fails)
+    __align__(8) uint64_t barT;
     uint64_t barA;
 };
 
-// one keypoint, one warp: all levels of the forward pass, the backward pass and the gates
-template <int W2, int PR, int PC>
-__device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, const int lane, LKTmaSmem<W2, PR, PC>& sm, unsigned& parT, unsigned& parA) {
+// Position bookkeeping.  The reference keeps d and c as Float64 vectors; the kernel keeps the current estimate of a level as an
+// integer pixel plus an fp32 fraction in [0, 1): floor / ceil / bilinear weights / tile offsets then need no Float64 arithmetic
+// inside the iteration, and the fraction's resolution (6e-8 px) is far below the fp32 noise of the window sums that drive it.
+// Between levels the displacement is doubled exactly (integer part and fraction separately).
+__device__ __forceinline__ void split_d(double d, int& di, float& df) {
+    di = __double2int_rd(d);
+    df = (float)(d - (double)di);
+    if (df >= 1.f) { di += 1; df = 0.f; }  // the rounding of the fraction can reach 1
+}
+__device__ __forceinline__ double join_d(int di, float df) { return (double)di + (double)df; }
+
+// one keypoint, one warp: all levels of the forward pass, the backward pass and the gates.  MODE (= a.mode) is a template parameter
+// so that the forward-backward kernel carries none of optflow!'s or optical_flow_matching!'s bookkeeping
+template <int W2, int PR, int PC, int MODE>
+__device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, const int lane, LKTmaSmem<W2, PR, PC>& sm, unsigned& parT, unsigned& parA,
+                                             const double2 pt0, const int next_raw, int& next, double2& pt_next) {
     using T = TmaTile<W2, PR, PC>;
     constexpr int TR = T::TR, TC = T::TC, AR = T::AR;
     const int f = gw / a.n_per_frame;
@@ -248,11 +262,9 @@ __device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, cons
 #define LKT_MAPS_A (reinterpret_cast<const LKTmaLevel*>(swapped ? a.mapsB : a.mapsA))
 #define LKT_MAPS_B (reinterpret_cast<const LKTmaLevel*>(swapped ? a.mapsA : a.mapsB))
 #define LKT_FB_A (swapped ? a.B.base + (size_t)slot_second * a.B.frame_elems : a.A.base + (size_t)slot_first * a.A.frame_elems)
-    double dy = 0.0, dx = 0.0;
-    if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
     // mode 2 = optical_flow_matching! (map_manager.jl:451-564): keypoints with a prior (3-D keypoints) are first tracked with
     // that prior on levels3d levels; those that fail, and all others, are tracked from a zero displacement on all levels
-    const uint8_t prior_flag = (a.mode == 2 && a.has_prior) ? a.has_prior[gw] : (uint8_t)0;
+    const uint8_t prior_flag = (MODE == 2 && a.has_prior) ? a.has_prior[gw] : (uint8_t)0;
     if (prior_flag == 2) {  // 3-D keypoint whose projection left the image: not tracked at all (map_manager.jl:489-506)
         if (lane == 0) {
             a.status[gw] = 8;
@@ -263,17 +275,28 @@ __device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, cons
         }
         return;
     }
-    const bool prior_first = prior_flag != 0;
-    if (a.mode == 2 && !prior_first) { dy = 0.0; dx = 0.0; }
+    const bool prior_first = MODE == 2 && prior_flag != 0;
     int levels_cur = prior_first ? a.levels3d : a.levels;
     bool second_try = false;
-    const GEntry* gtab = reinterpret_cast<const GEntry*>(a.gtab);
+    const float4* gtab = reinterpret_cast<const float4*>(a.gtab);
+    float4 gnext = make_float4(0.f, 0.f, 0.f, 0.f);  // table entry of the next stage, requested one stage ahead (or at the keypoint's start)
+    if (LKT_PF_G && gtab) gnext = __ldg(gtab + ((size_t)gw * a.gtab_levels + levels_cur));
 
     const int w = a.window;
     unsigned int wpx = 0, nit = 0;
-    double qy = a.pts[2 * (size_t)gw], qx = a.pts[2 * (size_t)gw + 1];
     bool ok = true;
     uint8_t result = 0;
+    int diy = 0, dix = 0;      // displacement at the scale of the current level: integer part ...
+    float dfy = 0.f, dfx = 0.f;  // ... and fraction in [0, 1)
+    int iy0, ix0;              // floor of the point the templates are centred on (keypoint; forward result on the backward pass)
+    {
+        const double2 pt = pt0;  // requested while the previous keypoint was still being tracked
+        iy0 = __double2int_rd(pt.x); ix0 = __double2int_rd(pt.y);
+        if (a.disp_in && !(MODE == 2 && !prior_first)) {
+            const double2 d0 = *reinterpret_cast<const double2*>(a.disp_in + 2 * (size_t)gw);
+            split_d(d0.x, diy, dfy); split_d(d0.y, dix, dfx);
+        }
+    }
 
     const int rgp = lane & 7, cgp = lane >> 3;                      // patch row group / column group of this lane
     const int pi0 = rgp * PR, pj0 = cgp * PC;                       // first window row / column of the patch
@@ -285,53 +308,78 @@ __device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, cons
     float2 tIp[PR][NQT];
     float tIl[PR];
     float2 tG[PR][PC];
-    float2 rm[PR];  // row weights: 1 for window rows, 0 for patch rows beyond the (clipped) window
-    int ty0 = 0, tx0 = 0;
-    bool pendT = false, pendA = false;  // a target / template load is in flight on barT / barA
-    int tmpl_stage = -1;                // stage whose template has been requested (or sits in shared memory)
-    const float* const tI0 = &sm.sI[pj0][pi0s];
-    const float2* const tG0 = &sm.sG[pj0][pi0s];
-    const float* const tT0 = &sm.sT[pj0][pi0s];
+    bool pendA = false;   // a template load is in flight on barA
+    int tmpl_stage = -1;  // stage whose template has been requested (or sits in shared memory)
+    const float* const tT0 = &sm.sT[pj0][pi0s];  // this lane's first tap in a tile whose first tap row / column is (0, 0)
 
 retry:
-    const int nstage = levels_cur + 1 + (a.mode ? 1 : 0);
+    const int nstage = levels_cur + 1 + (MODE ? 1 : 0);
     for (int s = 0; s < nstage; ++s) {
         const bool back = s > levels_cur;
         const int lvl = back ? 0 : levels_cur - s;
         if (back) {
-            qy += dy; qx += dx;  // tracker.jl:37-46
-            if (lane == 0 && a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
+            // tracker.jl:37-46: the backward pass starts from the forward result with the negated displacement
+            const double2 pt = *reinterpret_cast<const double2*>(a.pts + 2 * (size_t)gw);
+            const double qy = pt.x + join_d(diy, dfy), qx = pt.y + join_d(dix, dfx);
+            if (lane == 0) {
+                sm.q[0] = qy; sm.q[1] = qx;
+                if (a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
+            }
             result = 2;
-            dy = -dy; dx = -dx;
+            iy0 = __double2int_rd(qy); ix0 = __double2int_rd(qx);
+            if (dfy > 0.f) { diy = -diy - 1; dfy = 1.f - dfy; } else diy = -diy;
+            if (dfx > 0.f) { dix = -dix - 1; dfx = 1.f - dfx; } else dix = -dix;
+            if (dfy >= 1.f) { diy += 1; dfy = 0.f; }
+            if (dfx >= 1.f) { dix += 1; dfx = 0.f; }
             swapped = true;
         }
-        const LKLevel& L = a.lv[lvl];
-        const int H = L.H, W = L.W, pitch = L.pitch;
-        const double inv = __longlong_as_double((long long)(1023 - lvl) << 52);  // 2^-lvl exactly, no division
-        const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);
-        int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
-        const bool interior = py - 1 >= w + 6 && H - py >= w + 6 && px - 1 >= w + 6 && W - px >= w + 6;
-        bool setup = true, first_setup = true;
-        double g00 = 0, g01 = 0, g11 = 0;
-        int it = 0;  // dy, dx run along with the iterations (they hold d + c of lucas_kanade.jl:50-90)
-        if (a.mode == 0 && lane == 0) { sm.dsave[0] = dy; sm.dsave[1] = dx; }
-        {
-            // request the target tile around the first iteration's position now: its latency overlaps the set-up below
-            const int fy0 = __double2int_rd((double)py + dy), fx0 = __double2int_rd((double)px + dx);
-            ty0 = (fy0 - up - 1 - T::MY) & ~3;  // the innermost TMA coordinate must be a multiple of 16 bytes (tools/tma_probe.cu)
-            tx0 = fx0 - left - 1 - T::MX;
-            if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; }  // (only after an early exit left a load in flight)
-            __syncwarp();
-            if (lane == 0) {
-                fence_async_smem();
-                mbar_expect(&sm.barT, T::T_BYTES);
-                tma_box(&sm.sT[0][0], &LKT_MAPS_B[lvl].tgt, ty0, tx0, LKT_SLOT_B, &sm.barT);
-            }
-            pendT = true;
+        if (LKT_PF_PT && next < 0 && (back || (MODE == 0 && s == levels_cur))) {
+            // the work counter's answer has long arrived: broadcast it and request the next keypoint's coordinates, so that the
+            // next keypoint does not start with two dependent global round trips
+            next = __shfl_sync(FULL, next_raw, 0);
+            if (next < a.n_frames * a.n_per_frame) pt_next = __ldg(reinterpret_cast<const double2*>(a.pts + 2 * (size_t)next));
         }
+        const float eps = back ? 1e-2f : (float)a.eps;
+        const int H = a.lv[lvl].H, W = a.lv[lvl].W;
+        const int py = iy0 >> lvl, px = ix0 >> lvl;  // floor(p / 2^lvl) (lucas_kanade.jl:197): floor(floor(p) / 2^lvl)
+        if (MODE == 0 && lane == 0) { sm.dsave[0] = diy; sm.dsave[1] = __float_as_int(dfy); sm.dsave[2] = dix; sm.dsave[3] = __float_as_int(dfx); }
+        if (!((unsigned)(py - 1) < (unsigned)H && (unsigned)(px - 1) < (unsigned)W)) { ok = false; break; }  // empty window
+        int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
+        int fy = py + diy, fx = px + dix;  // the estimate is (fy + wy, fx + wx)
+        float wy = dfy, wx = dfx;
+        // ---- target tile around the first iteration's position: its latency overlaps the set-up below
+        int ty0 = (fy - up - 1 - T::MY) & ~3;  // the innermost TMA coordinate must be a multiple of 16 bytes (tools/tma_probe.cu)
+        int tx0 = fx - left - 1 - T::MX;
+        __syncwarp();
+        if (lane == 0) {
+            fence_async_smem();
+            mbar_expect(&sm.barT, T::T_BYTES);
+            tma_box(&sm.sT[0][0], &LKT_MAPS_B[lvl].tgt, ty0, tx0, LKT_SLOT_B, &sm.barT);
+        }
+        bool pendT = true;
+        bool setup = true, first_setup = true;
+        float g00 = 0.f, g01 = 0.f, g11 = 0.f;
+        int it = 0, it_mark = 0;
+        // fast-path box of the integer estimate: inside it the staged tile covers every tap and get_offsets(p, estimate) equals
+        // the current offsets, so the estimate lies in the image and nothing has to be recomputed (see the slow path below)
+        // The box also carries the tile: first tap (fy - up - 1 - ty0, fx - left - 1 - tx0) within [0, TR - RSPAN] x [0, TC - CSPAN].
+        int bylo = 0x40000000, byspan = 0, bxlo = 0x40000000, bxspan = 0;  // empty
+        bool orig_offsets = true;
+        const float* tbase = tT0;
+        auto make_box = [&]() {
+            // get_offsets(p, pc) keeps the offsets of get_offsets(p, p) while floor(pc) >= min(p, w + 1) and
+            // ceil(pc) <= max(p, size - w) (lucas_kanade.jl:199-208); a window that was re-clipped has no such box
+            const int ty_lo = ty0 + up + 1, tx_lo = tx0 + left + 1;
+            const int ylo = max(min(py, w + 1), ty_lo), yhi = min(max(py, H - w) - 1, ty_lo + (TR - T::RSPAN));
+            const int xlo = max(min(px, w + 1), tx_lo), xhi = min(max(px, W - w) - 1, tx_lo + (TC - T::CSPAN));
+            const bool some = orig_offsets && yhi >= ylo && xhi >= xlo;
+            bylo = some ? ylo : 0x40000000; byspan = some ? yhi - ylo : 0;
+            bxlo = some ? xlo : 0x40000000; bxspan = some ? xhi - xlo : 0;
+            tbase = tT0 - (tx_lo * TR + ty_lo);
+        };
         while (true) {
-            const int nrows = up + down + 1, ncols = left + right + 1;
             if (setup) {
+                const int nrows = up + down + 1, ncols = left + right + 1;
                 const int r0 = py - up, c0 = px - left;
                 if (nrows < 1 || ncols < 1 || r0 < 1 || c0 < 1 || py + down > H || px + right > W) { ok = false; break; }
                 // ---- template tiles: requested one level ahead on the forward pass, otherwise now
@@ -348,112 +396,116 @@ retry:
                     pendA = true;
                     tmpl_stage = s;
                 }
-                // ---- G: table entry of (keypoint, level) on a level's first set-up, else from the row prefix planes (lane = row)
+                // ---- G^-1: table entry of (keypoint, level) on a level's first set-up, else from the row prefix planes (lane = row)
                 bool gate_ok;
-                if (first_setup && !back && gtab) {
-                    const GEntry* e = gtab + ((size_t)gw * a.gtab_levels + lvl);
-                    const double2 v0 = __ldg(reinterpret_cast<const double2*>(e));
-                    const double2 v1 = __ldg(reinterpret_cast<const double2*>(e) + 1);
-                    g00 = v0.x; g01 = v0.y; g11 = v1.x;
-                    gate_ok = __double_as_longlong(v1.y) != 0;
+                float ra0 = 0.f, ra1 = 0.f, rb0 = 0.f, rb1 = 0.f, rc0 = 0.f, rc1 = 0.f;
+                const bool from_table = first_setup && !back && gtab;
+                if (from_table) {
+                    if (!LKT_PF_G) gnext = __ldg(gtab + ((size_t)gw * a.gtab_levels + lvl));
+                    g00 = gnext.x; g01 = gnext.y; g11 = gnext.z;
+                    gate_ok = gnext.w != 0.f;
+                    if (LKT_PF_G && s < levels_cur) gnext = __ldg(gtab + ((size_t)gw * a.gtab_levels + lvl - 1));
                 } else {
-                    float syy, sxx, syx;
-                    {
-                        const float* colA = LKT_FB_A + (size_t)(r0 - 1 + min(lane, nrows - 1));
-                        const size_t lo = (size_t)(c0 - 1) * pitch, hi = (size_t)(px + right) * pitch;
-                        syy = __ldg(colA + L.oRyy + hi) - __ldg(colA + L.oRyy + lo);
-                        sxx = __ldg(colA + L.oRxx + hi) - __ldg(colA + L.oRxx + lo);
-                        syx = __ldg(colA + L.oRyx + hi) - __ldg(colA + L.oRyx + lo);
-                        if (lane >= nrows) { syy = 0.f; sxx = 0.f; syx = 0.f; }
-                    }
-                    float fa, fc, fb;
-                    wsum3(syy, sxx, syx, lane, fa, fc, fb);
-                    gate_ok = g_inverse((double)fa, (double)fc, (double)fb, a.eig_thr * (double)(nrows * ncols), g00, g01, g11);
+                    // request the six prefix values of this lane's row now; they are reduced after the template has been read
+                    const LKLevel& L = a.lv[lvl];
+                    const float* colA = LKT_FB_A + (size_t)(r0 - 1 + min(lane, nrows - 1));
+                    const size_t lo = (size_t)(c0 - 1) * L.pitch, hi = (size_t)(px + right) * L.pitch;
+                    ra1 = __ldg(colA + L.oRyy + hi); ra0 = __ldg(colA + L.oRyy + lo);
+                    rb1 = __ldg(colA + L.oRxx + hi); rb0 = __ldg(colA + L.oRxx + lo);
+                    rc1 = __ldg(colA + L.oRyx + hi); rc0 = __ldg(colA + L.oRyx + lo);
+                    gate_ok = true;
                 }
-                // ---- template patch of this lane into registers
+                // ---- template patch of this lane into registers; patch rows beyond the window read zero gradients
                 mbar_wait_par(&sm.barA, parA); parA ^= 1;
                 pendA = false;
-                const float* const tI = tI0 + ((r0 - 1) & 3);
-                const float2* const tGp = tG0 + ((r0 - 1) & 3);
+                {
+                    const int skip = (r0 - 1) & 3;
+                    const float* const tI = &sm.sI[pj0][pi0s] + skip;
+                    const float2* const tGp = &sm.sG[pj0][pi0s] + skip;
 #pragma unroll
-                for (int i = 0; i < PR; ++i) {
-                    const float m = (pi0 + i < nrows) ? 1.f : 0.f;
-                    rm[i] = make_float2(m, m);
+                    for (int i = 0; i < PR; ++i) {
+                        const float2* const gr = (pi0 + i < nrows) ? tGp + i : &sm.sZ[0];
 #pragma unroll
-                    for (int q = 0; q < NQT; ++q) tIp[i][q] = make_float2(tI[(2 * q) * AR + i], tI[(2 * q + 1) * AR + i]);
-                    tIl[i] = tI[(PC - 1) * AR + i];
+                        for (int q = 0; q < NQT; ++q) tIp[i][q] = make_float2(tI[(2 * q) * AR + i], tI[(2 * q + 1) * AR + i]);
+                        tIl[i] = tI[(PC - 1) * AR + i];
 #pragma unroll
-                    for (int j = 0; j < PC; ++j) tG[i][j] = tGp[j * AR + i];
+                        for (int j = 0; j < PC; ++j) tG[i][j] = gr[j * AR];
+                    }
+                    if (ncols < T::GC) {  // clipped (or smaller) window: gradient columns beyond it carry real data, zero them
+#pragma unroll
+                        for (int j = 0; j < PC; ++j)
+                            if (pj0 + j >= ncols) {
+#pragma unroll
+                                for (int i = 0; i < PR; ++i) tG[i][j] = make_float2(0.f, 0.f);
+                            }
+                    }
                 }
-                if (ncols < T::GC) {  // clipped (or smaller) window: gradient columns beyond it carry real data, zero them
-#pragma unroll
-                    for (int j = 0; j < PC; ++j)
-                        if (pj0 + j >= ncols) {
-#pragma unroll
-                            for (int i = 0; i < PR; ++i) tG[i][j] = make_float2(0.f, 0.f);
-                        }
+                if (!from_table) {
+                    float syy = ra1 - ra0, sxx = rb1 - rb0, syx = rc1 - rc0;
+                    if (lane >= nrows) { syy = 0.f; sxx = 0.f; syx = 0.f; }
+                    float fa, fc, fb;
+                    wsum3(syy, sxx, syx, lane, fa, fc, fb);
+                    double d00, d01, d11;
+                    gate_ok = g_inverse((double)fa, (double)fc, (double)fb, a.eig_thr * (double)(nrows * ncols), d00, d01, d11);
+                    g00 = (float)d00; g01 = (float)d01; g11 = (float)d11;
                 }
                 if (!gate_ok) { ok = false; break; }
                 // ---- request the next forward level's template: it depends only on the keypoint
                 if (first_setup && !back && s < levels_cur) {
-                    const int nl = lvl - 1;
-                    const double ninv = __longlong_as_double((long long)(1023 - nl) << 52);
-                    const int npy = (int)floor(qy * ninv), npx = (int)floor(qx * ninv);
+                    const int npy = iy0 >> (lvl - 1), npx = ix0 >> (lvl - 1);
                     const int nr0 = npy - min(w, npy - 1), nc0 = npx - min(w, npx - 1);
                     __syncwarp();
                     if (lane == 0) {
                         fence_async_smem();
                         mbar_expect(&sm.barA, T::I_BYTES + T::G_BYTES);
                         const int ra = (nr0 - 1) & ~3;
-                        tma_box(&sm.sI[0][0], &LKT_MAPS_A[nl].ti, ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
-                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[nl].tg, 2 * ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
+                        tma_box(&sm.sI[0][0], &LKT_MAPS_A[lvl - 1].ti, ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
+                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[lvl - 1].tg, 2 * ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
                     }
                     pendA = true;
                     tmpl_stage = s + 1;
                 }
+                orig_offsets = first_setup;
+                make_box();
+                if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; pendT = false; }
                 setup = false; first_setup = false;
             }
-            if (it >= a.iterations) break;
-            const double pcy = (double)py + dy, pcx = (double)px + dx;
-            const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
-            // fast path: the keypoint sits >= w+6 px inside the level, its window is unclipped and the estimate is within 3 px of
-            // it, so the estimate lies in the image and get_offsets(point, estimate) is (w, w, w, w) as before: nothing to recompute
-            const bool fast = interior && nrows == 2 * w + 1 && ncols == 2 * w + 1 && (unsigned)(fy - py + 3) <= 6u && (unsigned)(fx - px + 3) <= 6u;
-            if (!fast) {
-                // floor / ceil as integers serve both lies_in (1 <= pc <= size <=> floor >= 1 && ceil <= size) and get_offsets:
+            if (it >= a.iterations) {
+                // the last step was applied: lucas_kanade.jl:89 still requires the new estimate to lie in the level
+                if (it > 0 && !(fy >= 1 && fy + (wy > 0.f) <= H && fx >= 1 && fx + (wx > 0.f) <= W)) ok = false;
+                break;
+            }
+            if (!((unsigned)(fy - bylo) <= (unsigned)byspan && (unsigned)(fx - bxlo) <= (unsigned)bxspan)) {
+                // exact path: lies_in (1 <= pc <= size  <=>  floor >= 1 && ceil <= size) and get_offsets on floor / ceil:
                 // floor(min(w, min(p, pc) - 1)) = min(w, min(p, floor pc) - 1), floor(min(w, H - max(p, pc))) = min(w, H - max(p, ceil pc))
-                const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
+                const int cyi = fy + (wy > 0.f ? 1 : 0), cxi = fx + (wx > 0.f ? 1 : 0);
                 if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
                 const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
                 const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
                 if (nup != up || ndown != down || nleft != left || nright != right) {
+                    wpx += (unsigned)((up + down + 1) * (left + right + 1) * (it - it_mark)); it_mark = it;
                     up = nup; down = ndown; left = nleft; right = nright;
                     setup = true;
                     continue;
                 }
-            }
-            const float wy = (float)(pcy - (double)fy), wx = (float)(pcx - (double)fx);
-            const int ay = fy - up - 1, ax = fx - left - 1;  // 0-based first tap row / column
-            int oy = ay - ty0, ox = ax - tx0;
-            if (oy < 0 || oy + T::RSPAN > TR || ox < 0 || ox + T::CSPAN > TC) {
-                // the estimate walked out of the staged tile (or the window was re-clipped): stage again around it
-                if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; }
-                __syncwarp();
-                ty0 = (ay - T::MY) & ~3;
-                tx0 = ax - T::MX;
-                oy = ay - ty0; ox = T::MX;
-                if (lane == 0) {
-                    fence_async_smem();
-                    mbar_expect(&sm.barT, T::T_BYTES);
-                    tma_box(&sm.sT[0][0], &LKT_MAPS_B[lvl].tgt, ty0, tx0, LKT_SLOT_B, &sm.barT);
+                if (!((unsigned)(fy - up - 1 - ty0) <= (unsigned)(TR - T::RSPAN) && (unsigned)(fx - left - 1 - tx0) <= (unsigned)(TC - T::CSPAN))) {
+                    // the estimate walked out of the staged tile (or the window was re-clipped): stage again around it
+                    __syncwarp();
+                    ty0 = (fy - up - 1 - T::MY) & ~3;
+                    tx0 = fx - left - 1 - T::MX;
+                    if (lane == 0) {
+                        fence_async_smem();
+                        mbar_expect(&sm.barT, T::T_BYTES);
+                        tma_box(&sm.sT[0][0], &LKT_MAPS_B[lvl].tgt, ty0, tx0, LKT_SLOT_B, &sm.barT);
+                    }
+                    make_box();
+                    mbar_wait_par(&sm.barT, parT); parT ^= 1;
                 }
-                pendT = true;
             }
-            if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; pendT = false; }
             // ---- prepare_linear_system (lucas_kanade.jl:159-173) on this lane's patch
-            const float* tb = tT0 + (ox * TR + oy);
             float by, bx;
             {
+                const float* tb = tbase + (fx * TR + fy);
                 // packed fp32 (FFMA2 / FMUL2 / FADD2 on register pairs): tap columns in pairs (2m, 2m+1), pixels in pairs
                 // (2q, 2q+1) plus the last column alone; bilinear sample as a*(1-w) + b*w so no negated operand is needed
                 constexpr int NP = (PC + 1) / 2, NQ = PC / 2;
@@ -491,53 +543,67 @@ retry:
                     const float dI = tIl[i] - val;
                     b2[i] = __ffma2_rn(tG[i][PC - 1], make_float2(dI, dI), b2[i]);
                 }
-                float2 acc = __fmul2_rn(b2[0], rm[0]);
 #pragma unroll
-                for (int i = 1; i < PR; ++i) acc = __ffma2_rn(b2[i], rm[i], acc);
-                by = acc.x; bx = acc.y;
+                for (int i = 1; i < PR; ++i) b2[0] = __fadd2_rn(b2[0], b2[i]);
+                by = b2[0].x; bx = b2[0].y;
             }
-            float fby, fbx;
-            wsum2(by, bx, lane, fby, fbx);
-            const double sby = (double)fby, sbx = (double)fbx;
-            wpx += (unsigned)(nrows * ncols);
-            nit += 1;
+            float sby, sbx;
+            wsum2(by, bx, lane, sby, sbx);
             ++it;
-            const double ffy = g00 * sby + g01 * sbx, ffx = g01 * sby + g11 * sbx;
-            const double eps = back ? 1e-2 : a.eps;
-            if (fabs(ffy) < eps && fabs(ffx) < eps) break;
-            dy += ffy; dx += ffx;
-            if (!(fast && fabs(ffy) < 2.0 && fabs(ffx) < 2.0)) {  // on the fast path a step below 2 px cannot leave the image
-                const double ny = pcy + ffy, nx = pcx + ffx;
-                if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
+            // compute_flow_vector (lucas_kanade.jl:175-187): f = G^-1 b, in fp32 like the sums it is made of
+            const float ffy = fmaf(g01, sbx, g00 * sby), ffx = fmaf(g11, sbx, g01 * sby);
+            if (fabsf(ffy) < eps && fabsf(ffx) < eps) break;  // converged: the step is not applied (lucas_kanade.jl:80-83)
+            {
+                const float ny = wy + ffy, nx = wx + ffx;
+                const float ky = floorf(ny), kx = floorf(nx);
+                fy += (int)ky; fx += (int)kx;
+                wy = ny - ky; wx = nx - kx;
             }
         }
+        wpx += (unsigned)((up + down + 1) * (left + right + 1) * (it - it_mark));
+        nit += (unsigned)it;
+        if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; }  // early exit with the target tile still in flight
         if (!ok) break;
-        if (lvl > 0) { dy *= 2.0; dx *= 2.0; }
+        diy = fy - py; dix = fx - px; dfy = wy; dfx = wx;
+        if (lvl > 0) {  // the next level's coordinates are twice as fine (lucas_kanade.jl:96)
+            const int ky = dfy >= 0.5f, kx = dfx >= 0.5f;
+            diy = 2 * diy + ky; dfy = 2.f * dfy - (float)ky;
+            dix = 2 * dix + kx; dfx = 2.f * dfx - (float)kx;
+        }
     }
 
-    if (a.mode != 0 && result != 0 && ok) {
+    if (MODE != 0 && result != 0 && ok) {
         // tracker.jl:59-66: the back-tracked point must land within max_distance of the original keypoint
-        const double by = qy + dy, bx = qx + dx;
-        const double ey = a.pts[2 * (size_t)gw] - by, ex = a.pts[2 * (size_t)gw + 1] - bx;
+        __syncwarp();
+        const double2 pt = *reinterpret_cast<const double2*>(a.pts + 2 * (size_t)gw);
+        const double by = sm.q[0] + join_d(diy, dfy), bx = sm.q[1] + join_d(dix, dfx);
+        const double ey = pt.x - by, ex = pt.y - bx;
         if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
     }
     if (prior_first && !second_try && result != 3) {
         // the prior pass failed: map_manager.jl:531-536 re-queues the keypoint with the 2-D ones (no prior, all levels)
         second_try = true;
         levels_cur = a.levels;
-        dy = 0.0; dx = 0.0; qy = a.pts[2 * (size_t)gw]; qx = a.pts[2 * (size_t)gw + 1];
+        diy = 0; dix = 0; dfy = 0.f; dfx = 0.f;
+        {
+            const double2 pt = *reinterpret_cast<const double2*>(a.pts + 2 * (size_t)gw);
+            iy0 = __double2int_rd(pt.x); ix0 = __double2int_rd(pt.y);
+        }
         ok = true; result = 0;
         swapped = false;
         tmpl_stage = -1;
+        if (LKT_PF_G && gtab) gnext = __ldg(gtab + ((size_t)gw * a.gtab_levels + levels_cur));
+        __syncwarp();
         goto retry;
     }
     // never leave with copies in flight (early exits only: a completed keypoint has consumed everything it requested)
-    if (pendT) { mbar_wait_par(&sm.barT, parT); parT ^= 1; }
     if (pendA) { mbar_wait_par(&sm.barA, parA); parA ^= 1; }
-    if (a.mode == 0) {
+    if (MODE == 0) {
         if (lane == 0) {
-            if (!ok) { dy = sm.dsave[0]; dx = sm.dsave[1]; }  // a failed level leaves d[n] as it was (lucas_kanade.jl:43,53,67,89)
-            if (a.disp_out) { a.disp_out[2 * (size_t)gw] = dy; a.disp_out[2 * (size_t)gw + 1] = dx; }
+            if (!ok) {  // a failed level leaves d[n] as it was (lucas_kanade.jl:43,53,67,89)
+                diy = sm.dsave[0]; dfy = __int_as_float(sm.dsave[1]); dix = sm.dsave[2]; dfx = __int_as_float(sm.dsave[3]);
+            }
+            if (a.disp_out) { a.disp_out[2 * (size_t)gw] = join_d(diy, dfy); a.disp_out[2 * (size_t)gw + 1] = join_d(dix, dfx); }
             a.status[gw] = ok ? 1 : 0;
         }
     } else if (lane == 0) {
@@ -553,19 +619,34 @@ retry:
     }
 }
 
+// resident one-warp CTAs per SM the register allocation is bounded for.  Measured on B200 (64 x 2000 keypoints, forward-backward
+// kernel): 16 (110 registers) 0.840 ms, 18 (94 registers, no spills; shared memory allows 18) 0.806 ms.  A 24-row target tile
+// (LKT_TR=24, 9.5 KB of shared memory) reaches 21-24 CTAs but re-stages so often that it loses: 0.976 ms at 16, 0.885 ms at 24.
+// The optflow! / optical_flow_matching! instantiations carry more state and keep the 128-register bound.
 #ifndef LKT_MINB
-#define LKT_MINB 16
+#define LKT_MINB 18
+#endif
+// latency experiments: G-table entry requested one stage ahead (LKT_PF_G) / next keypoint's coordinates requested during the
+// last stage of the current one (LKT_PF_PT).  Measured on B200 (forward-backward kernel, 18 CTAs per SM): neither 0.810 ms, table
+// entry ahead 0.811 ms, coordinates ahead 0.815 ms, both 0.822 ms -- with 18 warps per SM the kernel is bound by instruction
+// issue, not by these round trips, and the extra live registers cost more than the hidden latency returns.  Both off.
+#ifndef LKT_PF_G
+#define LKT_PF_G 0
+#endif
+#ifndef LKT_PF_PT
+#define LKT_PF_PT 0
 #endif
 
-// Kernel: one warp (= one CTA) per keypoint.  With a.work != nullptr the grid is persistent (one-warp CTAs filling every SM) and
-// every warp draws keypoint indices from a device counter -- the next index is requested before the current keypoint is
-// processed, so the atomic's latency is hidden; without it CTA i handles keypoint i.
-template <int W2, int PR, int PC>
-__global__ void __launch_bounds__(32, LKT_MINB) k_lk_tma(const LKArgs a) {
+// Kernel: one warp (= one CTA) per keypoint; the grid is persistent (one-warp CTAs filling every SM, or one per keypoint when there
+// are fewer keypoints than warp slots) and every warp draws keypoint indices from a device counter -- the next index is requested
+// before the current keypoint is processed, so the atomic's latency is hidden.
+template <int W2, int PR, int PC, int MODE>
+__global__ void __launch_bounds__(32, MODE == 1 ? LKT_MINB : 16) k_lk_tma(const LKArgs a) {
     __shared__ LKTmaSmem<W2, PR, PC> sm;
     const int lane = threadIdx.x;
-    // the gradient tile's columns beyond the box are never written by the TMA: zero the tile once
+    // the gradient tile's columns beyond the box are never written by the TMA, nor is the zero row: clear them once
     for (int i = lane; i < TmaTile<W2, PR, PC>::AC * TmaTile<W2, PR, PC>::AR; i += 32) (&sm.sG[0][0])[i] = make_float2(0.f, 0.f);
+    for (int i = lane; i < 4 * TmaTile<W2, PR, PC>::AR + 1; i += 32) sm.sZ[i] = make_float2(0.f, 0.f);
     if (lane == 0) {
         mbar_init1(&sm.barT);
         mbar_init1(&sm.barA);
@@ -574,20 +655,24 @@ __global__ void __launch_bounds__(32, LKT_MINB) k_lk_tma(const LKArgs a) {
     __syncwarp();
     unsigned parT = 0, parA = 0;
     const int total = a.n_frames * a.n_per_frame;
-    if (a.work == nullptr) {
-        const int gw = blockIdx.x;
-        if (gw < total) lk_point_tma<W2, PR, PC>(a, gw, lane, sm, parT, parA);
-        return;
-    }
     int base = 0;
     if (lane == 0) base = (int)atomicAdd(a.work, 1u);
     base = __shfl_sync(FULL, base, 0);
+    double2 pt = make_double2(0.0, 0.0);
+    if (base < total) pt = __ldg(reinterpret_cast<const double2*>(a.pts + 2 * (size_t)base));
     while (base < total) {
-        int next = 0;
-        if (lane == 0) next = (int)atomicAdd(a.work, 1u);
-        lk_point_tma<W2, PR, PC>(a, base, lane, sm, parT, parA);
+        int next_raw = 0;
+        if (lane == 0) next_raw = (int)atomicAdd(a.work, 1u);
+        int next = -1;
+        double2 pt_next = make_double2(0.0, 0.0);
+        lk_point_tma<W2, PR, PC, MODE>(a, base, lane, sm, parT, parA, pt, next_raw, next, pt_next);
         __syncwarp();
-        base = __shfl_sync(FULL, next, 0);
+        if (next < 0) {  // the keypoint ended early (failed before its last stage): fetch the next one here
+            next = __shfl_sync(FULL, next_raw, 0);
+            if (next < total) pt_next = __ldg(reinterpret_cast<const double2*>(a.pts + 2 * (size_t)next));
+        }
+        base = next;
+        pt = pt_next;
     }
 }
 
@@ -600,32 +685,29 @@ static int launch_lk_gprep(cudaStream_t s, const LKArgs& a) {
     return 1;
 }
 
-// returns false when this variant does not cover the request (window size, or no tensor maps)
+// returns false when this variant does not cover the request (window size, or no tensor maps / work counter)
 bool launch_lk_tma(cudaStream_t s, const LKArgs& a) {
     const int total = a.n_frames * a.n_per_frame;
     const int w2 = 2 * a.window + 1;
-    if (w2 > 19 || !a.mapsA || !a.mapsB) return false;
-    auto kern = k_lk_tma<19, 3, 5>;
-    static const int slots = [&] {
+    if (w2 > 19 || !a.mapsA || !a.mapsB || !a.work || a.mode < 0 || a.mode > 2) return false;
+    static const int slots = [] {
         int dev = 0, sms = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, 0);
+        cudaFuncSetAttribute(k_lk_tma<19, 3, 5, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_lk_tma<19, 3, 5, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_lk_tma<19, 3, 5, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lk_tma<19, 3, 5, 1>, 32, 0);
         const char* e = getenv("SLAMKLT_LK_SLOTS");  // experiment knob: resident one-warp CTAs per SM of the persistent grid
         const int want = e ? atoi(e) : per_sm;
         return sms * (want >= 1 && want <= per_sm ? want : per_sm);
     }();
-    LKArgs b = a;
-    static const bool persistent = getenv("SLAMKLT_LK_STATIC") == nullptr;
-    if (!persistent) b.work = nullptr;
-    int grid = total;
-    if (b.work) {
-        if (total > slots) { grid = slots; cudaMemsetAsync(b.work, 0, sizeof(unsigned), s); }
-        else b.work = nullptr;  // fewer keypoints than warp slots: one CTA each
-    }
-    if (b.gtab) launch_lk_gprep(s, b);
-    kern<<<grid, 32, 0, s>>>(b);
+    const int grid = total < slots ? total : slots;
+    cudaMemsetAsync(a.work, 0, sizeof(unsigned), s);
+    if (a.gtab) launch_lk_gprep(s, a);
+    if (a.mode == 0) k_lk_tma<19, 3, 5, 0><<<grid, 32, 0, s>>>(a);
+    else if (a.mode == 1) k_lk_tma<19, 3, 5, 1><<<grid, 32, 0, s>>>(a);
+    else k_lk_tma<19, 3, 5, 2><<<grid, 32, 0, s>>>(a);
     return true;
 }
 
