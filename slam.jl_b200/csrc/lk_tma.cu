@@ -35,6 +35,16 @@ namespace sk {
 #ifndef LKT_MX
 #define LKT_MX 4
 #endif
+// latency experiments: G-table entry requested one stage ahead (LKT_PF_G) / next keypoint's coordinates requested during the
+// last stage of the current one (LKT_PF_PT).  Measured on B200 (forward-backward kernel, 18 CTAs per SM): neither 0.810 ms, table
+// entry ahead 0.811 ms, coordinates ahead 0.815 ms, both 0.822 ms -- with 18 warps per SM the kernel is bound by instruction
+// issue, not by these round trips, and the extra live registers cost more than the hidden latency returns.  Both off.
+#ifndef LKT_PF_G
+#define LKT_PF_G 0
+#endif
+#ifndef LKT_PF_PT
+#define LKT_PF_PT 0
+#endif
 
 template <int W2, int PR, int PC>
 struct TmaTile {
@@ -625,16 +635,6 @@ retry:
 // The optflow! / optical_flow_matching! instantiations carry more state and keep the 128-register bound.
 #ifndef LKT_MINB
 #define LKT_MINB 18
-#endif
-// latency experiments: G-table entry requested one stage ahead (LKT_PF_G) / next keypoint's coordinates requested during the
-// last stage of the current one (LKT_PF_PT).  Measured on B200 (forward-backward kernel, 18 CTAs per SM): neither 0.810 ms, table
-// entry ahead 0.811 ms, coordinates ahead 0.815 ms, both 0.822 ms -- with 18 warps per SM the kernel is bound by instruction
-// issue, not by these round trips, and the extra live registers cost more than the hidden latency returns.  Both off.
-#ifndef LKT_PF_G
-#define LKT_PF_G 0
-#endif
-#ifndef LKT_PF_PT
-#define LKT_PF_PT 0
 #endif
 
 // Kernel: one warp (= one CTA) per keypoint; the grid is persistent (one-warp CTAs filling every SM, or one per keypoint when there
