@@ -231,6 +231,8 @@ struct slamklt_batch {
     int n_frames = 0, n_slots = 0, slot0 = 0, max_pts = 0, n_pts = 0;
     int up_dtype = -1, up_ld = 0;
     void* d_maps = nullptr;  // device array of per-level tensor maps over the slot ring
+    TScratch ts{};           // scratch ring of the y-filtered product planes (kept in L2 by an access-policy window)
+    int build_group = 0;     // frames per build group (0: whole batch at once, planes inside the frame blocks)
     DevBuf staging, img64, pts, outp, status, gtab;
     std::vector<slamklt_pyr*> views;
     bool primed = false;
@@ -290,6 +292,31 @@ static FrameSet fs_of(const slamklt_pyr* p) {
     return FrameSet{p->base, p->g.frame_elems, 1, 0};
 }
 static const void* maps_of(const slamklt_pyr* p) { return p->parent ? p->parent->d_maps : p->d_maps; }
+
+// Keep a scratch buffer resident in L2: persisting set-aside sized for it + an access-policy window on the streams whose kernels
+// touch it (the build's main stream and the coarse-level side stream).  Best effort: without it the ring still works, its
+// lines just compete with the streaming traffic.  SLAMKLT_NO_L2_WINDOW=1 turns it off.
+static void set_l2_window(slamklt_ctx* c, void* base, size_t bytes) {
+    if (getenv("SLAMKLT_NO_L2_WINDOW")) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    const size_t set_aside = std::min((size_t)max_persist, bytes + (bytes >> 3));
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.base_ptr = base;
+    av.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+    av.accessPolicyWindow.hitRatio = bytes <= set_aside ? 1.0f : (float)((double)set_aside / (double)bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStream_t ss[] = {c->stream, c->pyr_streams.c};
+    for (cudaStream_t st : ss)
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    if (getenv("SLAMKLT_VERBOSE"))
+        fprintf(stderr, "[slamklt] L2 window: %.1f MB ring, set-aside %.1f MB (max %.1f MB), window max %.1f MB\n", bytes / 1e6, set_aside / 1e6,
+                max_persist / 1e6, max_window / 1e6);
+}
 
 // tensor maps of a frame ring for the TMA-staged tracking kernel, uploaded to 64-byte aligned device memory
 static int make_maps(slamklt_ctx* c, const PyrGeom& g, float* base, int n_slots, void** d_maps) {
@@ -542,7 +569,7 @@ static int upload_frames(slamklt_ctx* c, DevBuf& staging, const void* img, int d
 }
 
 static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const PyrGeom& g, const void* staged, int dtype, double sigma, int mode,
-                        double* img64) {
+                        double* img64, const TScratch* ts = nullptr, int group = 0) {
     if (!(sigma > 0)) return fail(SLAMKLT_E_INVALID, "sigma must be positive");
     const float* ny[MAX_LAYERS] = {nullptr};
     const float* nx[MAX_LAYERS] = {nullptr};
@@ -555,8 +582,20 @@ static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const
         CKL();
     }
     // level 0 is converted on the fly by the fused column kernel (no separate conversion pass)
-    c->launches += launch_pyramid(c->pyr_streams, fs, f0, n_frames, g, sigma, mode, ny, nx, staged, dtype, c->hk());
-    CKL();
+    if (ts && ts->base && group > 0) {
+        // groups of a few frames: the scratch ring is rewritten by every group and stays in L2; the side streams rejoin the
+        // main stream after the last group only, so the small coarse-level kernels of one group overlap the next group
+        const size_t fbytes = (size_t)g.H0 * g.W0 * dtype_size(dtype);
+        for (int g0 = 0; g0 < n_frames; g0 += group) {
+            const int n = std::min(group, n_frames - g0);
+            const void* raw = staged ? (const char*)staged + (size_t)g0 * fbytes : nullptr;
+            c->launches += launch_pyramid(c->pyr_streams, fs, f0 + g0, n, g, sigma, mode, ny, nx, raw, dtype, c->hk(), ts, g0 + n >= n_frames);
+            CKL();
+        }
+    } else {
+        c->launches += launch_pyramid(c->pyr_streams, fs, f0, n_frames, g, sigma, mode, ny, nx, staged, dtype, c->hk());
+        CKL();
+    }
     prof_end(c);
     return 0;
 }
@@ -655,6 +694,9 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
         default: return fail(SLAMKLT_E_INVALID, "unknown plane %d", plane);
     }
     if ((which >= 0 || comp >= 0 || prefix) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    if (which >= 0 && p->parent && p->parent->ts.base)
+        return fail(SLAMKLT_E_INVALID, "the smoothed product planes of a batch slot are not retained (the batch builds them through a scratch ring); "
+                                       "build a standalone pyramid to inspect them");
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     if (p->parent) BATCH_WAIT_LK(c, p->parent);
@@ -1045,6 +1087,26 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     b->views.resize(b->n_slots, nullptr);
     CK(cudaEventCreateWithFlags(&b->ev_lk_done, cudaEventDisableTiming));
     if ((r = make_maps(c, g, b->base, b->n_slots, &b->d_maps))) return r;
+    // Scratch ring for the y-filtered product planes: SLAMKLT_BUILD_GROUP frames per build group (default 0 = off).  Measured on
+    // B200 (64 KITTI frames, ncu --cache-control none): with groups of 8 and the L2 window the T planes never reach HBM (DRAM
+    // traffic of a build 2.46 -> 1.73 GB) but the build gets slower, 0.75 -> 1.45 ms: 128 launches instead of 16, and a group's
+    // column kernel is a single 84 %-full round of warps (55 us for 8 frames against 32 us for its share of the 64-frame launch).
+    {
+        static const int want = [] { const char* e = getenv("SLAMKLT_BUILD_GROUP"); return e ? atoi(e) : 0; }();
+        if (want > 0 && n_frames >= 2 * want) {
+            size_t off = 0;
+            for (int l = 0; l < g.nl; ++l) { b->ts.off[l] = off; off += 3 * g.lv[l].plane_elems; }
+            b->ts.stride = off; b->ts.ring = want;
+            const size_t bytes = off * want * sizeof(float);
+            cudaError_t e2 = cudaMalloc(&b->ts.base, bytes + ALLOC_SLACK * sizeof(float));
+            if (e2 != cudaSuccess) { b->ts.base = nullptr; cudaGetLastError(); }
+            else {
+                cudaMemsetAsync(b->ts.base, 0, bytes + ALLOC_SLACK * sizeof(float), c->stream);
+                b->build_group = want;
+                set_l2_window(c, b->ts.base, bytes);
+            }
+        }
+    }
     *out = b;
     return 0;
 }
@@ -1060,6 +1122,7 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
     b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
     if (b->d_maps) cudaFree(b->d_maps);
+    if (b->ts.base) cudaFree(b->ts.base);
     cudaFree(b->base);
     delete b;
     return 0;
@@ -1108,7 +1171,7 @@ int slamklt_batch_build(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
-    return build_frames(c, fs_of(b), 1, b->n_frames, b->g, b->staging.p, b->up_dtype, sigma, mode, nullptr);
+    return build_frames(c, fs_of(b), 1, b->n_frames, b->g, b->staging.p, b->up_dtype, sigma, mode, nullptr, &b->ts, b->build_group);
 }
 
 int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_params* p) {
@@ -1228,7 +1291,7 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
         const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
         const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
         if (imgs) CK(cudaStreamWaitEvent(c->stream, evH2D[k], 0));
-        if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr))) return r;
+        if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr, &b->ts, b->build_group))) return r;
         if (n_pts > 0) {
             if (side_lk) { CK(cudaEventRecord(evBuilt[k], c->stream)); CK(cudaStreamWaitEvent(lks, evBuilt[k], 0)); }
             a.offA = f0; a.offB = f0 + 1; a.n_frames = n;

@@ -126,6 +126,18 @@ struct MatchArgs {
 void launch_match_prior(cudaStream_t s, const MatchArgs& a);
 void launch_match_update(cudaStream_t s, const MatchArgs& a);
 
+// Scratch ring for the y-filtered product planes T0..T2 (the only consumer is the x pass that follows): when a batch is built in
+// groups of a few frames, the planes of frame f live in slot f % ring of a small separate buffer instead of inside the frame
+// block, so every group rewrites the same addresses and -- with an L2 access-policy window over the buffer -- the planes are
+// produced and consumed in L2 without ever reaching HBM.  base == nullptr: the planes inside the frame block are used.
+struct TScratch {
+    float* base;
+    size_t stride;            // floats per ring slot (all levels)
+    int ring;                 // slots
+    int pad_;
+    size_t off[MAX_LAYERS];   // float offset of level l's three planes inside a slot
+};
+
 // optional per-kernel profiling hook: called with the kernel's name right before each launch
 struct Hook { void (*fn)(void* user, const char* name); void* user; };
 inline void mark(const Hook* h, const char* name) { if (h && h->fn) h->fn(h->user, name); }
@@ -138,7 +150,8 @@ int launch_convert(cudaStream_t s, const void* src, int dtype, int ld, size_t sr
 struct PyrStreams { cudaStream_t main, b, c; cudaEvent_t ev[MAX_LAYERS + 3]; bool parallel; };
 int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
                    const float* const* inv_ny, const float* const* inv_nx /* per level device arrays, CTOR mode only */,
-                   const void* raw /* staged host image(s) or nullptr */, int dtype, const Hook* hk);
+                   const void* raw /* staged host image(s) or nullptr */, int dtype, const Hook* hk,
+                   const TScratch* ts = nullptr /* T planes in a scratch ring */, bool join = true /* side streams rejoin main */);
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk);
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk);
 bool launch_lk_patch(cudaStream_t s, const LKArgs& a);  // patch-mapped variant (lk_patch.cu), windows up to 23 x 23

@@ -319,6 +319,10 @@ struct ColArgs {
     size_t raw_stride;     // elements per frame
     int do_blur;
     size_t o_tmp;          // y-filtered blur output
+    // T planes in a scratch ring (TScratch) instead of at o_out0 inside the frame
+    float* t_base;
+    size_t t_stride, o_t;
+    int t_ring;
 };
 
 // One warp per (frame, column).
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c
                 }
             }
             warp_iir_lines<K, 3, G>(pp, H, lane, c4, false);
-            float* o0 = fb + a.o_out0 + (size_t)xcol * pitch;
+            float* o0 = (a.t_base ? a.t_base + (size_t)((a.f0 + f) % a.t_ring) * a.t_stride + a.o_t : fb + a.o_out0) + (size_t)xcol * pitch;
             if constexpr (G > 1) {
                 store_col_g<K, G>(o0, y0, rg, pp[0]);
                 store_col_g<K, G>(o0 + a.plane_elems, y0, rg, pp[1]);
@@ -595,6 +599,10 @@ struct RowArgs {
     int zero_border;
     size_t o_in0, o_out0, plane_elems;  // nplanes consecutive input planes -> nplanes consecutive output planes
     const float* inv_n;                 // NA mode: 1/nx[x]
+    // input planes in a scratch ring (TScratch) instead of at o_in0 inside the frame
+    const float* t_base;
+    size_t t_stride, o_t;
+    int t_ring;
 };
 
 // base + k columns as one IMAD.WIDE.U32 (u32 x u32 + u64)
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     const bool chok = ch < NC;  // the block is rounded up to whole warps
     const bool rowok = r < a.H && chok;
     float* fb = a.fs.frame(a.f0 + f);
-    const float* in = fb + a.o_in0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
+    const float* in = (a.t_base ? a.t_base + (size_t)((a.f0 + f) % a.t_ring) * a.t_stride + a.o_t : fb + a.o_in0) + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     float* out = fb + a.o_out0 + (size_t)plane * a.plane_elems + (rowok ? r : 0);
     const int x0 = chok ? ch * KRt : 0;
     const int n = a.W;
@@ -951,7 +959,8 @@ static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, 
 // side stream B, and the gradient stages of the coarser levels (k_cols_grad + k_rows prefix) to side stream C as soon as
 // their layer exists, so the small coarse-level kernels overlap the layer chain instead of extending it.
 int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, const PyrGeom& g, double sigma, int mode,
-                   const float* const* inv_ny, const float* const* inv_nx, const void* raw, int dtype, const Hook* hk) {
+                   const float* const* inv_ny, const float* const* inv_nx, const void* raw, int dtype, const Hook* hk, const TScratch* ts,
+                   bool join) {
     int launches = 0;
     char nm[48];
     const bool ctor = mode == SLAMKLT_MODE_CTOR;
@@ -967,6 +976,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
         ca.o_grad = plane_off(L, DP_GRAD); ca.plane_elems = L.plane_elems;
         ca.o_tmp = plane_off(L, DP_TMP);
         ca.raw = nullptr; ca.raw_ld = g.H0; ca.raw_stride = (size_t)g.H0 * g.W0;
+        if (ts && ts->base) { ca.t_base = ts->base; ca.t_stride = ts->stride; ca.t_ring = ts->ring; ca.o_t = ts->off[l]; }
         return ca;
     };
     auto rows_struct = [&](cudaStream_t s, int l, const IirDev& c4) {
@@ -975,6 +985,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
         ra.fs = fs; ra.f0 = f0; ra.n_frames = n_frames; ra.H = L.H; ra.W = L.W; ra.pitch = L.pitch; ra.nplanes = 3;
         ra.zero_border = 0; ra.o_in0 = plane_off(L, DP_T0); ra.o_out0 = plane_off(L, DP_RYY); ra.plane_elems = L.plane_elems;
         ra.inv_n = nullptr;
+        if (ts && ts->base) { ra.t_base = ts->base; ra.t_stride = ts->stride; ra.t_ring = ts->ring; ra.o_t = ts->off[l]; }
         snprintf(nm, sizeof(nm), "k_rows_struct_L%d", l); mark(hk, nm);
         dispatch_rows(s, ra, c4, 1);
         launches += 1;
@@ -997,8 +1008,11 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             snprintf(nm, sizeof(nm), "k_cols_all_L%d", l); mark(hk, nm);
             dispatch_cols_all(sA, K, src, ca, c4, c1);
             launches += 1;
-            if (par) { cudaEventRecord(ps.ev[0], sA); cudaStreamWaitEvent(sB, ps.ev[0], 0); }
-            rows_struct(par ? sB : sA, l, c4);
+            // with a scratch ring the x pass follows on the same stream: the next group's column kernel (also on this stream)
+            // overwrites the ring slots, and the planes are still hot in L2
+            const bool ring = ts && ts->base;
+            if (par && !ring) { cudaEventRecord(ps.ev[0], sA); cudaStreamWaitEvent(sB, ps.ev[0], 0); }
+            rows_struct(par && !ring ? sB : sA, l, c4);
         } else {
             // coarser levels: the layer chain only needs the blur y pass; gradients + structure planes run on stream C
             cudaEventRecord(ps.ev[l], sA);  // layer l exists (k_resize of level l-1 ran on main)
@@ -1035,7 +1049,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             launches += 2;
         }
     }
-    if (par) {
+    if (par && join) {
         cudaEventRecord(evB, sB);
         cudaEventRecord(evC, sC);
         cudaStreamWaitEvent(sA, evB, 0);
