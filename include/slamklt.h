@@ -217,6 +217,10 @@ int slamklt_batch_upload(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, i
 /* device-side work only: build all n_frames pyramids, then forward-backward track every pair */
 int slamklt_batch_build(slamklt_ctx* ctx, slamklt_batch* b, double sigma, int mode);
 int slamklt_batch_track(slamklt_ctx* ctx, slamklt_batch* b, const slamklt_lk_params* p);
+/* stereo matching of two batches of equal shape -- optical_flow_matching!(..., kf.left_pyramid, right_pyramid, true) of
+ * mapper.jl:51-60 for n_frames keyframes at once: pair i tracks the points uploaded to `to` (they live on `from`'s frame i)
+ * from frame i of `from` (left) to frame i of `to` (right); results are fetched with slamklt_batch_download(to, ...) */
+int slamklt_batch_track_cross(slamklt_ctx* ctx, slamklt_batch* from, slamklt_batch* to, const slamklt_lk_params* p);
 /* build + track of the uploaded frames in one asynchronous call (device-resident step) */
 int slamklt_batch_process(slamklt_ctx* ctx, slamklt_batch* b, double sigma, int mode, const slamklt_lk_params* p);
 /* async D2H of n_frames x n_pts x 2 tracked points and n_frames x n_pts status bytes, then stream sync */

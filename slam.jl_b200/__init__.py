@@ -95,7 +95,7 @@ SYMBOLS = [
     "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
     "slamklt_flow_matching", "slamklt_optical_flow_matching", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
-    "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
+    "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_track_cross", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
     "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
 ]
 
@@ -139,6 +139,7 @@ def lib():
         L.slamklt_batch_upload.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_size_t, dp, C.c_int]
         L.slamklt_batch_build.argtypes = [vp, vp, C.c_double, C.c_int]
         L.slamklt_batch_track.argtypes = [vp, vp, C.POINTER(LKParams)]
+        L.slamklt_batch_track_cross.argtypes = [vp, vp, vp, C.POINTER(LKParams)]
         L.slamklt_batch_process.argtypes = [vp, vp, C.c_double, C.c_int, C.POINTER(LKParams)]
         L.slamklt_batch_download.argtypes = [vp, vp, dp, u8p]
         L.slamklt_batch_rotate.argtypes = [vp, vp]
@@ -500,6 +501,12 @@ class StreamBatch:
     def track(self, alg: LucasKanade, max_distance=1.0):
         p = alg._c(max_distance)
         _ck(lib().slamklt_batch_track(self.ctx._h, self._h, C.byref(p)))
+
+    def track_cross(self, to: "StreamBatch", alg: LucasKanade, max_distance=1.0):
+        """Stereo matching of two batches (mapper.jl:51-60 for n_frames keyframes at once): pair i tracks the points uploaded to
+        `to` from frame i of this batch (left) to frame i of `to` (right); fetch the results with to.download()."""
+        p = alg._c(max_distance)
+        _ck(lib().slamklt_batch_track_cross(self.ctx._h, self._h, to._h, C.byref(p)))
 
     def process(self, alg: LucasKanade, max_distance=1.0, sigma=1.0, mode=MODE_UPDATE):
         """build + track of the uploaded frames in one asynchronous, internally pipelined call."""

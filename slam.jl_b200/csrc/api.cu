@@ -1201,6 +1201,37 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     return 0;
 }
 
+// Stereo matching of two batches (mapper.jl:51-60 for n_frames keyframes at once): pair i tracks `to`'s uploaded points from
+// frame i of `from` to frame i of `to`; results land in `to`'s result buffers (slamklt_batch_download(to, ...)).
+int slamklt_batch_track_cross(slamklt_ctx* c, slamklt_batch* from, slamklt_batch* to, const slamklt_lk_params* p) {
+    if (!c || !from || !to) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    int r = check_lk(p, from->g.nl, to->g.nl);
+    if (r) return r;
+    if (from->g.H0 != to->g.H0 || from->g.W0 != to->g.W0 || from->g.nl != to->g.nl || from->n_frames != to->n_frames)
+        return fail(SLAMKLT_E_INVALID, "batch shapes differ");
+    if (to->n_pts == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    BATCH_WAIT_LK(c, from);
+    BATCH_WAIT_LK(c, to);
+    LKArgs a{};
+    a.A = fs_of(from); a.B = fs_of(to); a.offA = 1; a.offB = 1;
+    fill_lk_levels(to->g, &a);
+    a.mode = 1;
+    a.pts = (const double*)to->pts.p; a.disp_in = nullptr; a.disp_out = nullptr;
+    a.out_pts = (double*)to->outp.p; a.status = (uint8_t*)to->status.p;
+    a.n_per_frame = to->n_pts; a.n_frames = to->n_frames;
+    a.iterations = p->iterations; a.window = p->window_size; a.levels = p->pyramid_levels;
+    a.eig_thr = p->eigenvalue_threshold; a.eps = p->epsilon; a.max_dist = p->max_distance;
+    a.counters = c->d_counters; a.work = work_slot(c);
+    a.mapsA = from->d_maps; a.mapsB = to->d_maps;
+    if ((r = set_gtab(to->gtab, &a))) return r;
+    c->launches += launch_lk(c->stream, a, c->hk());
+    CKL();
+    prof_end(c);
+    return 0;
+}
+
 int slamklt_batch_download(slamklt_ctx* c, slamklt_batch* b, double* out_pts, uint8_t* status) {
     if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);

@@ -106,6 +106,22 @@ def stereo_pair(seed: int, H: int = KITTI_H, W: int = KITTI_W, disparity=(2.0, 4
     return out[0], out[1], d
 
 
+def right_views(frames_u8: np.ndarray, seed: int, disparity=(2.0, 40.0), noise: float = 0.005) -> np.ndarray:
+    """Right-camera views of a left sequence: every frame resampled along x by a smooth disparity field in [disparity]
+    (a scene point at left x appears at right x - d), plus sensor noise.  Same shape and dtype as the input."""
+    n, H, W = frames_u8.shape
+    rng = np.random.default_rng(seed + 15485863)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float32)
+    d = disparity[0] + (disparity[1] - disparity[0]) * (0.5 + 0.5 * np.sin(xs / W * 2.1 + rng.uniform(0, 6)) *
+                                                        np.cos(ys / H * 1.3 + rng.uniform(0, 6)))
+    out = np.empty_like(frames_u8)
+    for t in range(n):
+        r = cv2.remap(frames_u8[t].astype(np.float32) / 255.0, xs + d.astype(np.float32), ys, cv2.INTER_CUBIC, borderMode=cv2.BORDER_REFLECT)
+        r = r + noise * np.random.default_rng(seed * 257 + t).standard_normal((H, W)).astype(np.float32)
+        out[t] = np.clip(np.rint(r * 255.0), 0, 255).astype(np.uint8)
+    return out
+
+
 def random_keypoints(seed: int, n: int, H: int, W: int, border: float = 12.0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     y = rng.uniform(1 + border, H - border, size=n)
