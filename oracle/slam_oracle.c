@@ -500,7 +500,9 @@ ORC_API void orc_shi_tomasi(const double* img, int H, int W, double* R) {
 }
 
 /* get_mask (extractor.jl:116-122) + Kernel.gaussian(sigma) blur (extractor.jl:69) [3P].
- * Disc rasterisation rule of ImageDraw.CirclePointRadius assumed dy^2+dx^2 <= r^2 (least certain item). */
+ * Disc rasterisation [3P ImageDraw 0.2]: draw!(img, CirclePointRadius) goes through the filled Ellipse, which sets pixel (i, j) iff
+ * ((i - cy) / r)^2 + ((j - cx) / r)^2 < 1 in Float64 (strict: lattice points on the circle stay outside, up to the rounding of
+ * that expression, which is reproduced as written). */
 ORC_API void orc_mask(int H, int W, const double* pts, int n, int radius, double sigma, double* mask) {
     size_t N = (size_t)H * W;
     for (size_t i = 0; i < N; ++i) mask[i] = 1.0;
@@ -510,7 +512,8 @@ ORC_API void orc_mask(int H, int W, const double* pts, int n, int radius, double
             for (int y = cy - radius; y <= cy + radius; ++y) {
                 if (y < 1 || y > H || x < 1 || x > W) continue;
                 int dy = y - cy, dx = x - cx;
-                if (dy * dy + dx * dx <= radius * radius) mask[(y - 1) + (size_t)(x - 1) * H] = 0.0;
+                double vy = (double)dy / (double)radius, vx = (double)dx / (double)radius;
+                if (vy * vy + vx * vx < 1.0) mask[(y - 1) + (size_t)(x - 1) * H] = 0.0;
             }
     }
     if (!(sigma > 0)) return;

@@ -11,6 +11,15 @@
 namespace sk {
 
 constexpr int DET_THREADS = 256;
+// ImageDraw's filled CirclePointRadius is drawn as an ellipse: pixel (i, j) belongs to it iff
+// ((i - cy) / r)^2 + ((j - cx) / r)^2 < 1 evaluated in Float64 [3P ImageDraw 0.2 ellipse2d.jl] -- strict, so the four axis
+// extremes and the other lattice points exactly on the circle stay outside (for a few radii, e.g. 41, the rounded sum of an
+// on-circle point is 0.9999999999999999 and it is inside: the expression is evaluated exactly as written, no FMA).
+__device__ __forceinline__ bool in_disc(int dy, int dx, int radius) {
+    const double vy = (double)dy / (double)radius, vx = (double)dx / (double)radius;
+    return vy * vy + vx * vx < 1.0;
+}
+
 constexpr int MAX_NEAR = 512;  // current points kept in shared memory per cell (more => slow path over the global list)
 
 // Shared-memory plan of one cell (doubles unless noted), identical on host and device:
@@ -147,6 +156,8 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 int sx = (int)sqrtf((float)rem);
                 while (sx * sx > rem) --sx;
                 while ((sx + 1) * (sx + 1) <= rem) ++sx;
+                while (sx >= 0 && !in_disc(dy, sx, a.radius)) --sx;  // the lattice points on the circle itself
+                if (sx < 0) continue;
                 const int xc = s_near[2 * k + 1] - 1 - (x0 - hw);
                 const int xa = max(xc - sx, 0), xb = min(xc + sx, rw - 1);
                 for (int xx = xa; xx <= xb; ++xx) s_m0[yy + xx * rh] = 0;
@@ -160,12 +171,12 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 if (n_near <= MAX_NEAR) {
                     for (int k = 0; k < n_near; ++k) {
                         const int dy = Y - s_near[2 * k], dx = X - s_near[2 * k + 1];
-                        if (dy * dy + dx * dx <= r2) { m = 0; break; }
+                        if (dy * dy + dx * dx <= r2 && in_disc(dy, dx, a.radius)) { m = 0; break; }
                     }
                 } else {
                     for (int k = 0; k < a.n_cur; ++k) {
                         const int dy = Y - (int)rint(cur[2 * k]), dx = X - (int)rint(cur[2 * k + 1]);
-                        if (dy * dy + dx * dx <= r2) { m = 0; break; }
+                        if (dy * dy + dx * dx <= r2 && in_disc(dy, dx, a.radius)) { m = 0; break; }
                     }
                 }
                 s_m0[i] = m;
