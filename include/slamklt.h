@@ -195,6 +195,40 @@ int slamklt_optical_flow_matching(slamklt_ctx* ctx, const slamklt_pyr* from, con
                                   const slamklt_matching_params* p, double* out_pixel_yx, double* out_undist_yx,
                                   double* out_position_xyz, uint8_t* status);
 
+/* triangulate_stereo!(map_manager, frame, max_error, cache) -- mapper.jl:142-183 -- for the stereo keypoints the caller selected
+ * (not yet 3-D, map point present: mapper.jl:157-161 stays host-side bookkeeping).  Per keypoint: DLT triangulation from
+ * und_yx = kp.undistorted_pixel and rund_yx = kp.right_undistorted_pixel with P1 = K, P2 = K_right * right_cam->Ti0
+ * (RecoverPose.triangulate: eigenvector of A'A for the smallest eigenvalue, normalised by its 4th component), depth >= 0.1 in
+ * both cameras, reprojection errors <= max_error (params.max_reprojection_error = 3.0), world point = wc * point (wc =
+ * frame.wc, column-major 4 x 4).  status: 1 = update_mappoint! with out_world_xyz[i]; 2 / 3 = remove_stereo_keypoint! (depth in
+ * the left / right camera), 4 / 5 = remove_stereo_keypoint! (reprojection error left / right); out_world_xyz is NaN unless 1.
+ * Agreement with a LAPACK eigen-solve: 1e-9 relative on the world point (tests/test_gpu_configs.py). */
+int slamklt_triangulate_stereo(slamklt_ctx* ctx, const double* und_yx, const double* rund_yx, int n, const slamklt_camera* cam,
+                               const slamklt_camera* right_cam, const double* wc, double max_error, double* out_world_xyz,
+                               uint8_t* status);
+
+/* ---- BRIEF descriptors + Hamming matching (only with params.do_local_matching, params.jl:69) ------------------------- */
+/* describe(e, image, keypoints) -- extractor.jl:103-105 -> ImageFeatures.create_descriptor(image, keypoints, BRIEF(size = 256)).
+ * kps_yx: n pairs of Int64 (y, x), 1-based (Vector{CartesianIndex{2}}).  pairs: n_bits x (dy1, dx1, dy2, dx2) Int32 -- the
+ * sampling pattern ImageFeatures draws from Julia's RNG (Random.seed!(123); gaussian(n_bits, window)); it cannot be regenerated
+ * outside Julia, the shim exports it once.  The image is smoothed with the 4*ceil(sigma)+1 tap Gaussian (sigma = sqrt(2) in
+ * BRIEF's defaults, replicate border, Float64) around each keypoint; bit b = smoothed[k + s1[b]] < smoothed[k + s2[b]], packed
+ * LSB first into n_bits/32 UInt32 per keypoint (same order as the chunks of a BitVector).  out_valid[i] = 0 for keypoints closer
+ * than ceil(window / 2) to the border: the reference drops those from the returned lists, the caller compacts. */
+int slamklt_describe(slamklt_ctx* ctx, const void* img, int dtype, int H, int W, int ld, const int64_t* kps_yx, int n,
+                     const int32_t* pairs, int n_bits, int window, double sigma, uint32_t* out_desc, uint8_t* out_valid);
+/* Descriptor side of find_best_match (mapper.jl:392-462) for many target map points at once.  Map point s owns the descriptor
+ * rows [set_off[s], set_off[s+1]) of desc (its keyframes_descriptors, `words` UInt32 each).  For target t (map point
+ * target_set[t]) the candidates cand[cand_off[t] .. cand_off[t+1]) -- the surrounding keypoints' map points that passed the
+ * geometric gates of mapper.jl:405-441, in the caller's order -- are scanned like the reference's loop: distance =
+ * mappoint_min_distance (map_point.jl:165-174, minimum Hamming distance over all descriptor pairs, counted in bits =
+ * hamming_distance * n_bits), candidates without descriptors skipped, "distance <= best" replaces the best (a later tie
+ * wins).  max_distance is the starting value of best / second (256 * max_descriptor_distance, mapper.jl:402).
+ * best_pos[t] = position inside the target's candidate list or -1. */
+int slamklt_find_best_match(slamklt_ctx* ctx, const uint32_t* desc, int n_desc, int words, const int32_t* set_off, int n_sets,
+                            const int32_t* target_set, const int32_t* cand_off, const int32_t* cand, int n_targets,
+                            int max_distance, int32_t* best_pos, int32_t* best_dist, int32_t* second_dist);
+
 /* ---- Extractor ------------------------------------------------------------------------- */
 /* detect(e, image, current_points; sigma_mask) -- extractor.jl:63-95.  out_yx: cap pairs of Int64.
  * *n_out receives the number of detected keypoints (no global cap, like the reference). */

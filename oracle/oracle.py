@@ -339,6 +339,94 @@ def optical_flow_matching(from_pyr, to_pyr, pixels, is_3d, world, undist, cw, ca
     return out_pix, out_und, out_pos, status
 
 
+def triangulate_stereo(und_yx, rund_yx, cam: Camera, rcam: Camera, wc, max_error=3.0):
+    """triangulate_stereo! (mapper.jl:142-183) restated with numpy; the 4 x 4 eigen-problem goes to LAPACK (np.linalg.eigh) like
+    the reference's geev.  [3P RecoverPose.triangulate]: rows x * P[3,:] - P[1,:], y * P[3,:] - P[2,:] per view (pixel units,
+    points as (x, y), mapper.jl:162-164), homogeneous point = eigenvector of A'A for the smallest eigenvalue.
+    Returns (world (n, 3) -- NaN unless status 1 --, status (n,) uint8: 1 update_mappoint!, 2 / 3 depth < 0.1 left / right,
+    4 / 5 reprojection error left / right > max_error -> remove_stereo_keypoint!)."""
+    und = np.asarray(und_yx, dtype=np.float64).reshape(-1, 2)
+    rund = np.asarray(rund_yx, dtype=np.float64).reshape(-1, 2)
+    n = len(und)
+    K1 = np.array([[cam.fx, 0, cam.cx, 0], [0, cam.fy, cam.cy, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+    K2 = np.array([[rcam.fx, 0, rcam.cx, 0], [0, rcam.fy, rcam.cy, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+    Ti0 = np.asarray(rcam.Ti0, dtype=np.float64).reshape(4, 4)
+    P1, P2 = K1, K2 @ Ti0                                       # mapper.jl:151-152
+    wc = np.asarray(wc, dtype=np.float64).reshape(4, 4)
+    world = np.full((n, 3), np.nan)
+    status = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        y1, x1 = und[i]; y2, x2 = rund[i]
+        A = np.stack([x1 * P1[2] - P1[0], y1 * P1[2] - P1[1], x2 * P2[2] - P2[0], y2 * P2[2] - P2[1]])
+        w, V = np.linalg.eigh(A.T @ A)
+        X = V[:, int(np.argmin(w))]
+        X = X * (1.0 / X[3])                                    # mapper.jl:165
+        if not X[2] >= 0.1: status[i] = 2; continue
+        R = Ti0 @ X
+        if not R[2] >= 0.1: status[i] = 3; continue
+        lp = np.array([cam.fy * X[1] / X[2] + cam.cy, cam.fx * X[0] / X[2] + cam.cx])      # project, camera.jl:62-67
+        if np.linalg.norm(und[i] - lp) > max_error: status[i] = 4; continue
+        rp = np.array([rcam.fy * R[1] / R[2] + rcam.cy, rcam.fx * R[0] / R[2] + rcam.cx])
+        if np.linalg.norm(rund[i] - rp) > max_error: status[i] = 5; continue
+        world[i] = (wc @ X)[:3]                                  # project_camera_to_world, frame.jl:452-456
+        status[i] = 1
+    return world, status
+
+
+def describe(image, keypoints, pairs, window=9, sigma=2 ** 0.5):
+    """describe (extractor.jl:103-105) -> ImageFeatures.create_descriptor(img, keypoints, BRIEF) [3P brief.jl], restated with numpy /
+    scipy: imfilter(img, Kernel.gaussian(sigma)) = separable correlation with the normalised 4*ceil(sigma)+1 taps, replicated
+    border; keypoints closer than ceil(window / 2) to the border are dropped; bit b = smoothed[k + s1[b]] < smoothed[k + s2[b]].
+    Returns (descriptors (m, n_bits / 32) uint32 packed LSB first, kept keypoints (m, 2))."""
+    import math
+    from scipy import ndimage
+    img = np.asarray(image, dtype=np.float64)
+    H, W = img.shape
+    hw = 2 * int(math.ceil(sigma))
+    taps = np.exp(-np.arange(-hw, hw + 1) ** 2 / (2 * sigma * sigma)); taps /= taps.sum()
+    sm = ndimage.correlate1d(ndimage.correlate1d(img, taps, axis=0, mode="nearest"), taps, axis=1, mode="nearest")
+    kps = np.asarray(keypoints, dtype=np.int64).reshape(-1, 2)
+    pr = np.asarray(pairs, dtype=np.int64).reshape(-1, 4)
+    lim = -(-window // 2)
+    keep = (kps[:, 0] - lim >= 1) & (kps[:, 1] - lim >= 1) & (kps[:, 0] + lim <= H) & (kps[:, 1] + lim <= W)
+    k = kps[keep]
+    a = sm[k[:, 0, None] - 1 + pr[None, :, 0], k[:, 1, None] - 1 + pr[None, :, 1]]
+    b = sm[k[:, 0, None] - 1 + pr[None, :, 2], k[:, 1, None] - 1 + pr[None, :, 3]]
+    bits = (a < b).astype(np.uint32).reshape(len(k), -1, 32)
+    desc = (bits << np.arange(32, dtype=np.uint32)[None, None, :]).sum(axis=2).astype(np.uint32)
+    return desc, k
+
+
+def hamming_bits(d1, d2):
+    """ImageFeatures.hamming_distance * n_bits: number of differing bits of two packed descriptors."""
+    return int(sum(bin(int(x) ^ int(y)).count("1") for x, y in zip(d1, d2)))
+
+
+def find_best_match(descriptors, set_offsets, target_sets, cand_offsets, candidates, max_distance):
+    """The descriptor side of find_best_match (mapper.jl:392-462) with mappoint_min_distance (map_point.jl:165-174), loops as in the
+    reference: candidates in order, empty descriptor sets skipped, `<=` so that a later tie replaces the best."""
+    nt = len(target_sets)
+    best_pos, best_dist, second_dist = np.full(nt, -1, np.int32), np.zeros(nt, np.int32), np.zeros(nt, np.int32)
+    for t in range(nt):
+        best = second = int(max_distance)
+        pos = -1
+        s1 = target_sets[t]
+        for c in range(cand_offsets[t], cand_offsets[t + 1]):
+            s2 = candidates[c]
+            if set_offsets[s2 + 1] == set_offsets[s2]:
+                continue
+            d = 2 ** 31 - 1
+            for i in range(set_offsets[s1], set_offsets[s1 + 1]):
+                for j in range(set_offsets[s2], set_offsets[s2 + 1]):
+                    d = min(d, hamming_bits(descriptors[i], descriptors[j]))
+            if d <= best:
+                second, best, pos = best, d, c - cand_offsets[t]
+            elif d <= second:
+                second = d
+        best_pos[t], best_dist[t], second_dist[t] = pos, best, second
+    return best_pos, best_dist, second_dist
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -94,7 +94,7 @@ SYMBOLS = [
     "slamklt_ctx_sync", "slamklt_get_stats", "slamklt_profile", "slamklt_profile_report", "slamklt_timer_start", "slamklt_timer_stop", "slamklt_pyr_create",
     "slamklt_pyr_destroy", "slamklt_pyr_build", "slamklt_pyr_copy", "slamklt_pyr_clone", "slamklt_pyr_swap",
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
-    "slamklt_flow_matching", "slamklt_optical_flow_matching", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
+    "slamklt_flow_matching", "slamklt_optical_flow_matching", "slamklt_triangulate_stereo", "slamklt_describe", "slamklt_find_best_match", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
     "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_track_cross", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
     "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
 ]
@@ -131,6 +131,10 @@ def lib():
         L.slamklt_flow_matching.argtypes = [vp, vp, vp, dp, dp, u8p, C.c_int, C.POINTER(LKParams), C.c_int, dp, u8p]
         L.slamklt_optical_flow_matching.argtypes = [vp, vp, vp, dp, u8p, dp, dp, C.c_int, dp, C.POINTER(CameraC), C.POINTER(CameraC),
                                                     C.POINTER(MatchingParams), dp, dp, dp, u8p]
+        L.slamklt_triangulate_stereo.argtypes = [vp, dp, dp, C.c_int, C.POINTER(CameraC), C.POINTER(CameraC), dp, C.c_double, dp, u8p]
+        i32p, u32p = C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+        L.slamklt_describe.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, i64p, C.c_int, i32p, C.c_int, C.c_int, C.c_double, u32p, u8p]
+        L.slamklt_find_best_match.argtypes = [vp, u32p, C.c_int, C.c_int, i32p, C.c_int, i32p, i32p, i32p, C.c_int, C.c_int, i32p, i32p, i32p]
         L.slamklt_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.POINTER(DetectParams),
                                      i64p, C.c_int, ip]
         L.slamklt_batch_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
@@ -419,8 +423,75 @@ def optical_flow_matching_frame(from_pyramid: LKPyramid, to_pyramid: LKPyramid, 
     return out_pix, out_und, out_pos, st
 
 
+def triangulate_stereo(ctx: Context, undistorted, right_undistorted, camera: Camera, right_camera: Camera, wc, max_error=3.0):
+    """triangulate_stereo! (mapper.jl:142-183) for the stereo keypoints the caller selected: DLT triangulation from the left /
+    right undistorted pixels, depth and reprojection checks, world point = wc * point.  Returns (world (n, 3), status (n,)):
+    status 1 = update_mappoint!, 2..5 = remove_stereo_keypoint! (include/slamklt.h)."""
+    und = np.ascontiguousarray(undistorted, dtype=np.float64).reshape(-1, 2)
+    rund = np.ascontiguousarray(right_undistorted, dtype=np.float64).reshape(-1, 2)
+    n = len(und)
+    assert len(rund) == n
+    T = np.ascontiguousarray(np.asarray(wc, dtype=np.float64).reshape(4, 4).ravel(order="F"))
+    world = np.full((n, 3), np.nan)
+    st = np.zeros(n, dtype=np.uint8)
+    cam, rcam = camera._c(), right_camera._c()
+    _ck(lib().slamklt_triangulate_stereo(ctx._h, _dp(und), _dp(rund), n, C.byref(cam), C.byref(rcam), _dp(T), float(max_error), _dp(world),
+                                         st.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return world, st
+
+
+def brief_pairs_stand_in(n_bits=256, window=9, seed=123):
+    """A sampling pattern with the distribution of ImageFeatures' `gaussian(size, window)` (normal with std window^2 / 25, offsets
+    floored and kept inside +-ceil(window / 2)).  It is NOT the reference's pattern: that one is drawn from Julia's RNG
+    (Random.seed!(123)) and has to be exported from Julia once (julia/SlamKLT.jl does).  Tests and benchmarks use this stand-in."""
+    rng = np.random.default_rng(seed)
+    lim = -(-window // 2)
+    out = []
+    while len(out) < 4 * n_bits:
+        v = rng.normal(0.0, window * window / 25.0)
+        if -lim <= v <= lim:
+            out.append(int(np.floor(v)))
+    return np.asarray(out, dtype=np.int32).reshape(n_bits, 4)
+
+
+def describe(ctx: Context, image, keypoints, pairs, window=9, sigma=2 ** 0.5):
+    """describe(e, image, keypoints) (extractor.jl:103-105 -> create_descriptor with BRIEF(size = len(pairs))).  keypoints: (n, 2)
+    int64 1-based (y, x); pairs: (n_bits, 4) int32 (dy1, dx1, dy2, dx2).  Returns (descriptors (m, n_bits / 32) uint32, keypoints
+    (m, 2)) of the keypoints far enough from the border, like the reference."""
+    a, code = _image(image)
+    H, W = a.shape
+    kps = np.ascontiguousarray(keypoints, dtype=np.int64).reshape(-1, 2)
+    pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4)
+    n, n_bits = len(kps), len(pr)
+    desc = np.zeros((n, n_bits // 32), dtype=np.uint32)
+    valid = np.zeros(n, dtype=np.uint8)
+    _ck(lib().slamklt_describe(ctx._h, a.ctypes.data_as(C.c_void_p), code, H, W, H, kps.ctypes.data_as(C.POINTER(C.c_int64)), n,
+                               pr.ctypes.data_as(C.POINTER(C.c_int32)), n_bits, int(window), float(sigma),
+                               desc.ctypes.data_as(C.POINTER(C.c_uint32)), valid.ctypes.data_as(C.POINTER(C.c_uint8))))
+    keep = valid.astype(bool)
+    return desc[keep], kps[keep]
+
+
+def find_best_match(ctx: Context, descriptors, set_offsets, target_sets, cand_offsets, candidates, max_distance):
+    """Descriptor side of find_best_match (mapper.jl:392-462) for many targets: see include/slamklt.h.  Returns (best_pos,
+    best_dist, second_dist) int32 arrays, distances in bits."""
+    d = np.ascontiguousarray(descriptors, dtype=np.uint32)
+    d = d.reshape(len(d), -1) if d.ndim == 2 else d.reshape(0, 8)
+    so = np.ascontiguousarray(set_offsets, dtype=np.int32)
+    ts = np.ascontiguousarray(target_sets, dtype=np.int32)
+    co = np.ascontiguousarray(cand_offsets, dtype=np.int32)
+    ca = np.ascontiguousarray(candidates, dtype=np.int32)
+    nt = len(ts)
+    bp, bd, sd = np.zeros(nt, np.int32), np.zeros(nt, np.int32), np.zeros(nt, np.int32)
+    ip = C.POINTER(C.c_int32)
+    _ck(lib().slamklt_find_best_match(ctx._h, d.ctypes.data_as(C.POINTER(C.c_uint32)), len(d), d.shape[1], so.ctypes.data_as(ip), len(so) - 1,
+                                      ts.ctypes.data_as(ip), co.ctypes.data_as(ip), ca.ctypes.data_as(ip), nt, int(max_distance),
+                                      bp.ctypes.data_as(ip), bd.ctypes.data_as(ip), sd.ctypes.data_as(ip)))
+    return bp, bd, sd
+
+
 class Extractor:
-    """Extractor (extractor.jl:7-22); the BRIEF descriptor is out of scope."""
+    """Extractor (extractor.jl:7-22); `describe` (BRIEF) is the free function above (the sampling pattern is an argument)."""
 
     def __init__(self, max_points, radius, grid_resolution, cell_size):
         self.max_points, self.radius = int(max_points), int(radius)

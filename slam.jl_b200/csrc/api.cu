@@ -977,6 +977,142 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     return 0;
 }
 
+int slamklt_triangulate_stereo(slamklt_ctx* c, const double* und, const double* rund, int n, const slamklt_camera* cam,
+                               const slamklt_camera* rcam, const double* wc, double max_error, double* out_world, uint8_t* status) {
+    if (!c || !cam || !rcam || !wc) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
+    if (n == 0) return 0;  // "No stereo keypoints to triangulate", mapper.jl:146-149
+    if (!und || !rund || !out_world || !status) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const size_t N = (size_t)n;
+    int r;
+    if ((r = c->match.ensure(N * 7 * 8 + N))) return r;  // [und 2n | rund 2n | world 3n] doubles, then status bytes
+    double* d = (double*)c->match.p;
+    CK(cudaMemcpyAsync(d, und, N * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + 2 * N, rund, N * 16, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += N * 32;
+    TriArgs a{};
+    a.n = n; a.cam = cam_dev(cam); a.rcam = cam_dev(rcam);
+    for (int k = 0; k < 16; ++k) { a.Ti0[k] = rcam->Ti0[k]; a.wc[k] = wc[k]; }
+    a.max_error = max_error;
+    a.und = d; a.rund = d + 2 * N; a.world = d + 4 * N; a.status = (uint8_t*)(d + 7 * N);
+    mark(c->hk(), "k_triangulate_stereo");
+    launch_triangulate_stereo(c->stream, a);
+    c->launches += 1;
+    CKL();
+    prof_end(c);
+    CK(cudaMemcpyAsync(out_world, a.world, N * 24, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(status, a.status, N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += N * 25;
+    return 0;
+}
+
+// ---- BRIEF describe + Hamming matching -----------------------------------------------
+int slamklt_describe(slamklt_ctx* c, const void* img, int dtype, int H, int W, int ld, const int64_t* kps_yx, int n, const int32_t* pairs,
+                     int n_bits, int window, double sigma, uint32_t* out_desc, uint8_t* out_valid) {
+    if (!c || !img) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
+    if (H < 3 || W < 3 || ld < H || n < 0) return fail(SLAMKLT_E_INVALID, "bad shape");
+    if (n_bits <= 0 || n_bits % 32 != 0 || n_bits > 1024) return fail(SLAMKLT_E_INVALID, "descriptor size %d must be a multiple of 32 (<= 1024)", n_bits);
+    if (window < 1 || window > 9) return fail(SLAMKLT_E_INVALID, "window %d outside [1,9]", window);
+    if (!(sigma > 0) || sigma > 4.0) return fail(SLAMKLT_E_INVALID, "sigma outside (0,4]");
+    if (n == 0) return 0;
+    if (!kps_yx || !pairs || !out_desc || !out_valid) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    const int lim = (window + 1) / 2;  // ceil(Int, window / 2)
+    for (int b = 0; b < 4 * n_bits; ++b)
+        if (pairs[b] < -lim || pairs[b] > lim) return fail(SLAMKLT_E_INVALID, "sampling offset %d outside the window", pairs[b]);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    int r;
+    if ((r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
+    const double* d_img;
+    if (dtype == SLAMKLT_F64) d_img = (const double*)c->staging.p;
+    else {
+        if ((r = c->img64.ensure((size_t)H * W * 8))) return r;
+        PyrGeom g;
+        if ((r = make_geom(H, W, 0, &g))) return r;
+        if ((r = c->outp.ensure(g.frame_elems * sizeof(float)))) return r;
+        FrameSet fs{(float*)c->outp.p, g.frame_elems, 1, 0};
+        c->launches += launch_convert(c->stream, c->staging.p, dtype, H, (size_t)H * W, fs, 0, 1, g, (double*)c->img64.p, c->hk());
+        CKL();
+        d_img = (const double*)c->img64.p;
+    }
+    const size_t N = (size_t)n, words = (size_t)n_bits / 32;
+    // device block: [kps 2n i64 | pairs 4*n_bits i32 | desc n*words u32 | valid n u8]
+    const size_t o_pairs = N * 16, o_desc = o_pairs + (size_t)n_bits * 16, o_valid = o_desc + N * words * 4;
+    if ((r = c->match.ensure(o_valid + N))) return r;
+    char* d = (char*)c->match.p;
+    CK(cudaMemcpyAsync(d, kps_yx, N * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + o_pairs, pairs, (size_t)n_bits * 16, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += N * 16 + (size_t)n_bits * 16;
+    BriefArgs a{};
+    a.img = d_img; a.H = H; a.W = W; a.ld = H; a.n = n;
+    a.kps = (const long long*)d; a.pairs = (const int4*)(d + o_pairs);
+    a.n_bits = n_bits; a.lim = lim;
+    a.hw = 2 * (int)std::ceil(sigma);  // Kernel.gaussian(sigma): length 4*ceil(sigma)+1 [3P]
+    double sum = 0;
+    for (int i = -a.hw; i <= a.hw; ++i) { a.kw[i + a.hw] = std::exp(-(double)i * i / (2 * sigma * sigma)); sum += a.kw[i + a.hw]; }
+    for (int i = 0; i <= 2 * a.hw; ++i) a.kw[i] /= sum;
+    a.desc = (unsigned*)(d + o_desc); a.valid = (uint8_t*)(d + o_valid);
+    mark(c->hk(), "k_brief");
+    launch_brief(c->stream, a);
+    c->launches += 1;
+    CKL();
+    prof_end(c);
+    CK(cudaMemcpyAsync(out_desc, a.desc, N * words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out_valid, a.valid, N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += N * (words * 4 + 1);
+    return 0;
+}
+
+int slamklt_find_best_match(slamklt_ctx* c, const uint32_t* desc, int n_desc, int words, const int32_t* set_off, int n_sets,
+                            const int32_t* target_set, const int32_t* cand_off, const int32_t* cand, int n_targets, int max_distance,
+                            int32_t* best_pos, int32_t* best_dist, int32_t* second_dist) {
+    if (!c) return fail(SLAMKLT_E_INVALID, "ctx is NULL");
+    if (n_targets < 0 || n_desc < 0 || n_sets < 0 || words < 1) return fail(SLAMKLT_E_INVALID, "bad shape");
+    if (n_targets == 0) return 0;
+    if (!desc || !set_off || !target_set || !cand_off || !cand || !best_pos || !best_dist || !second_dist) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (set_off[0] != 0 || set_off[n_sets] != n_desc || cand_off[0] != 0) return fail(SLAMKLT_E_INVALID, "offset arrays must start at 0 and end at the row count");
+    const int n_cand = cand_off[n_targets];
+    for (int t = 0; t < n_targets; ++t)
+        if (target_set[t] < 0 || target_set[t] >= n_sets || cand_off[t + 1] < cand_off[t]) return fail(SLAMKLT_E_INVALID, "bad target %d", t);
+    for (int k = 0; k < n_cand; ++k)
+        if (cand[k] < 0 || cand[k] >= n_sets) return fail(SLAMKLT_E_INVALID, "candidate set id out of range");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const size_t b_desc = (size_t)n_desc * words * 4, b_set = ((size_t)n_sets + 1) * 4, b_t = (size_t)n_targets * 4, b_co = b_t + 4, b_c = (size_t)std::max(n_cand, 1) * 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    const size_t o_desc = take(b_desc), o_set = take(b_set), o_ts = take(b_t), o_co = take(b_co), o_c = take(b_c), o_bp = take(b_t), o_bd = take(b_t), o_sd = take(b_t);
+    int r;
+    if ((r = c->match.ensure(off))) return r;
+    char* d = (char*)c->match.p;
+    CK(cudaMemcpyAsync(d + o_desc, desc, b_desc, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + o_set, set_off, b_set, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + o_ts, target_set, b_t, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d + o_co, cand_off, b_co, cudaMemcpyHostToDevice, c->stream));
+    if (n_cand > 0) CK(cudaMemcpyAsync(d + o_c, cand, (size_t)n_cand * 4, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += b_desc + b_set + b_t + b_co + (size_t)n_cand * 4;
+    HammingArgs a{};
+    a.desc = (const unsigned*)(d + o_desc); a.set_off = (const int*)(d + o_set); a.words = words; a.n_targets = n_targets;
+    a.max_distance = max_distance; a.target_set = (const int*)(d + o_ts); a.cand_off = (const int*)(d + o_co); a.cand = (const int*)(d + o_c);
+    a.best_pos = (int*)(d + o_bp); a.best_dist = (int*)(d + o_bd); a.second_dist = (int*)(d + o_sd);
+    mark(c->hk(), "k_best_match");
+    launch_best_match(c->stream, a);
+    c->launches += 1;
+    CKL();
+    prof_end(c);
+    CK(cudaMemcpyAsync(best_pos, a.best_pos, b_t, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(best_dist, a.best_dist, b_t, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(second_dist, a.second_dist, b_t, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += 3 * b_t;
+    return 0;
+}
+
 // ---- extractor -------------------------------------------------------------------------------
 static int fill_det(const slamklt_detect_params* p, int H, int W, int n_cur, DetArgs* a) {
     if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");

@@ -123,6 +123,44 @@ struct MatchArgs {
     uint8_t* status;         // in/out
     double* out_pix; double* out_und; double* out_pos;
 };
+// BRIEF describe + Hamming matching (brief.cu)
+struct BriefArgs {
+    const double* img;      // column-major H x W (ld)
+    int H, W, ld, n;
+    const long long* kps;   // n x 2 (y, x), 1-based
+    const int4* pairs;      // n_bits x (dy1, dx1, dy2, dx2)
+    int n_bits, lim, hw, pad_;
+    double kw[2 * 8 + 1];   // 1-D smoothing taps, length 2*hw+1
+    unsigned* desc;         // n x n_bits/32
+    uint8_t* valid;         // n
+};
+struct HammingArgs {
+    const unsigned* desc;   // descriptor rows, `words` 32-bit words each
+    const int* set_off;     // n_sets + 1: rows [set_off[s], set_off[s+1]) are the descriptors of map point s
+    int words, n_targets, max_distance, pad_;
+    const int* target_set;  // n_targets
+    const int* cand_off;    // n_targets + 1
+    const int* cand;        // candidate set ids, in the caller's order
+    int* best_pos;          // position of the best candidate inside the target's list, -1 if none
+    int* best_dist;
+    int* second_dist;
+};
+void launch_brief(cudaStream_t s, const BriefArgs& a);
+void launch_best_match(cudaStream_t s, const HammingArgs& a);
+
+// triangulate_stereo! (mapper.jl:142-183)
+struct TriArgs {
+    int n, pad_;
+    MatchCam cam, rcam;
+    double Ti0[16];          // right camera: transformation from the left camera (column-major)
+    double wc[16];           // frame.wc (camera -> world, column-major)
+    double max_error;
+    const double* und;       // n x 2 kp.undistorted_pixel (y, x)
+    const double* rund;      // n x 2 kp.right_undistorted_pixel (y, x)
+    double* world;           // out: n x 3 world point (NaN unless status 1)
+    uint8_t* status;         // out: 1 triangulated, 2 / 3 depth < 0.1 in the left / right camera, 4 / 5 reprojection error left / right
+};
+void launch_triangulate_stereo(cudaStream_t s, const TriArgs& a);
 void launch_match_prior(cudaStream_t s, const MatchArgs& a);
 void launch_match_update(cudaStream_t s, const MatchArgs& a);
 

@@ -87,8 +87,111 @@ __global__ void k_match_update(const MatchArgs a) {
     a.out_pos[3 * (size_t)i] = p0; a.out_pos[3 * (size_t)i + 1] = p1; a.out_pos[3 * (size_t)i + 2] = p2;
 }
 
+// triangulate_stereo! (mapper.jl:142-183), one thread per stereo keypoint.  DLT system of RecoverPose.triangulate [3P]:
+// rows x * P[3,:] - P[1,:], y * P[3,:] - P[2,:] for both views with P1 = to_4x4(K) and P2 = to_4x4(K_right) * Ti0 (pixel units,
+// points in (x, y) order, mapper.jl:151-152,162-164); the homogeneous point is the eigenvector of A'A for the smallest
+// eigenvalue.  The reference gets it from LAPACK's geev; here a cyclic Jacobi iteration on the symmetric 4 x 4 matrix (the
+// eigenvector is defined up to scale, and the point is normalised by its 4th component right away, mapper.jl:165).
+__device__ void jacobi4_smallest(double M[4][4], double v[4]) {
+    double V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 4; ++p) {
+            diag += M[p][p] * M[p][p];
+            for (int q = p + 1; q < 4; ++q) off += M[p][q] * M[p][q];
+        }
+        if (off <= 1e-40 * diag || off == 0.0) break;
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = M[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (M[q][q] - M[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; ++k) {  // columns p, q
+                    const double mkp = M[k][p], mkq = M[k][q];
+                    M[k][p] = c * mkp - sn * mkq; M[k][q] = sn * mkp + c * mkq;
+                }
+                for (int k = 0; k < 4; ++k) {  // rows p, q
+                    const double mpk = M[p][k], mqk = M[q][k];
+                    M[p][k] = c * mpk - sn * mqk; M[q][k] = sn * mpk + c * mqk;
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int best = 0;
+    for (int k = 1; k < 4; ++k)
+        if (M[k][k] < M[best][best]) best = k;
+    for (int k = 0; k < 4; ++k) v[k] = V[k][best];
+}
+
+__global__ void k_triangulate_stereo(const TriArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    // P1 = to_4x4(K), P2 = to_4x4(K_right) * Ti0, row-major here
+    double P1[3][4] = {{a.cam.fx, 0, a.cam.cx, 0}, {0, a.cam.fy, a.cam.cy, 0}, {0, 0, 1, 0}};
+    double P2[3][4];
+    for (int c = 0; c < 4; ++c) {
+        const double t0 = a.Ti0[0 + 4 * c], t1 = a.Ti0[1 + 4 * c], t2 = a.Ti0[2 + 4 * c];
+        P2[0][c] = a.rcam.fx * t0 + a.rcam.cx * t2;
+        P2[1][c] = a.rcam.fy * t1 + a.rcam.cy * t2;
+        P2[2][c] = t2;
+    }
+    const double y1 = a.und[2 * (size_t)i], x1 = a.und[2 * (size_t)i + 1];
+    const double y2 = a.rund[2 * (size_t)i], x2 = a.rund[2 * (size_t)i + 1];
+    double A[4][4];
+    for (int c = 0; c < 4; ++c) {
+        A[0][c] = x1 * P1[2][c] - P1[0][c];
+        A[1][c] = y1 * P1[2][c] - P1[1][c];
+        A[2][c] = x2 * P2[2][c] - P2[0][c];
+        A[3][c] = y2 * P2[2][c] - P2[1][c];
+    }
+    double M[4][4];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) M[r][c] = A[0][r] * A[0][c] + A[1][r] * A[1][c] + A[2][r] * A[2][c] + A[3][r] * A[3][c];
+    double v[4];
+    jacobi4_smallest(M, v);
+    const double iw = 1.0 / v[3];
+    const double X = v[0] * iw, Y = v[1] * iw, Z = v[2] * iw;  // left camera coordinates (w = 1)
+    uint8_t st = 1;
+    double w0 = nan, w1 = nan, w2 = nan;
+    if (!(Z >= 0.1)) st = 2;  // left_point[3] < 0.1 (a NaN point is dropped as well)
+    else {
+        const double rx = a.Ti0[0] * X + a.Ti0[4] * Y + a.Ti0[8] * Z + a.Ti0[12];
+        const double ry = a.Ti0[1] * X + a.Ti0[5] * Y + a.Ti0[9] * Z + a.Ti0[13];
+        const double rz = a.Ti0[2] * X + a.Ti0[6] * Y + a.Ti0[10] * Z + a.Ti0[14];
+        if (!(rz >= 0.1)) st = 3;
+        else {
+            // project (camera.jl:62-67): (fy * y / z + cy, fx * x / z + cx)
+            const double iz = 1.0 / Z;
+            const double ly = a.cam.fy * Y * iz + a.cam.cy, lx = a.cam.fx * X * iz + a.cam.cx;
+            const double ey = y1 - ly, ex = x1 - lx;
+            if (sqrt(ey * ey + ex * ex) > a.max_error) st = 4;
+            else {
+                const double irz = 1.0 / rz;
+                const double qy = a.rcam.fy * ry * irz + a.rcam.cy, qx = a.rcam.fx * rx * irz + a.rcam.cx;
+                const double fy_ = y2 - qy, fx_ = x2 - qx;
+                if (sqrt(fy_ * fy_ + fx_ * fx_) > a.max_error) st = 5;
+                else {
+                    // project_camera_to_world (frame.jl:452-456): wc * (X, Y, Z, 1)
+                    w0 = a.wc[0] * X + a.wc[4] * Y + a.wc[8] * Z + a.wc[12];
+                    w1 = a.wc[1] * X + a.wc[5] * Y + a.wc[9] * Z + a.wc[13];
+                    w2 = a.wc[2] * X + a.wc[6] * Y + a.wc[10] * Z + a.wc[14];
+                }
+            }
+        }
+    }
+    a.status[i] = st;
+    a.world[3 * (size_t)i] = w0; a.world[3 * (size_t)i + 1] = w1; a.world[3 * (size_t)i + 2] = w2;
+}
+
 }  // namespace
 
+void launch_triangulate_stereo(cudaStream_t s, const TriArgs& a) { k_triangulate_stereo<<<(a.n + 127) / 128, 128, 0, s>>>(a); }
 void launch_match_prior(cudaStream_t s, const MatchArgs& a) { k_match_prior<<<(a.n + 127) / 128, 128, 0, s>>>(a); }
 void launch_match_update(cudaStream_t s, const MatchArgs& a) { k_match_update<<<(a.n + 127) / 128, 128, 0, s>>>(a); }
 

@@ -295,3 +295,89 @@ def test_degenerate_inputs_match_oracle(ctx):
     # detect on the flat image finds nothing; on a tiny image with more cells than pixels the grid is clipped
     e = slamklt.Extractor(500, 5, (4, 5), 35)
     assert len(slamklt.detect(ctx, e, flat, np.zeros((0, 2)))) == 0 == len(O.detect(O.Extractor(500, 5, (4, 5), 35), flat, np.zeros((0, 2))))
+
+
+def _stereo_scene(n, seed, noise=0.3):
+    """n points in front of a KITTI-like rig, observed by both cameras with `noise` px of measurement noise; a few are put behind
+    the cameras / far off the epipolar geometry so that every rejection branch of triangulate_stereo! is taken."""
+    rng = np.random.default_rng(seed)
+    cam = dict(synth.KITTI_CAMERA)
+    Ti0 = np.eye(4); Ti0[0, 3] = -0.54                       # right camera 0.54 m to the right: x_r = x_l - 0.54
+    X = np.stack([rng.uniform(-8, 8, n), rng.uniform(-2, 2, n), rng.uniform(3, 60, n), np.ones(n)], axis=1)
+    R = X @ Ti0.T
+    proj = lambda P: np.stack([cam["fy"] * P[:, 1] / P[:, 2] + cam["cy"], cam["fx"] * P[:, 0] / P[:, 2] + cam["cx"]], axis=1)
+    und, rund = proj(X) + rng.normal(0, noise, (n, 2)), proj(R) + rng.normal(0, noise, (n, 2))
+    rund[::17, 0] += 9.0                                      # breaks the epipolar geometry: reprojection error
+    rund[5::23, 1] = und[5::23, 1] + 30.0                     # negative disparity: point behind the cameras
+    th = 0.3
+    wc = np.array([[np.cos(th), 0, np.sin(th), 1.5], [0, 1, 0, -0.2], [-np.sin(th), 0, np.cos(th), 4.0], [0, 0, 0, 1.0]])
+    return und, rund, cam, Ti0, wc
+
+
+def test_triangulate_stereo_matches_lapack_restatement(ctx):
+    """triangulate_stereo! (mapper.jl:142-183): the device's Jacobi eigen-solve against the oracle's LAPACK one.
+    Tolerance: 1e-9 relative on the world point, identical status classes."""
+    und, rund, cam, Ti0, wc = _stereo_scene(3000, 42)
+    gc, grc = slamklt.Camera(**cam), slamklt.Camera(**cam, Ti0=Ti0)
+    oc, orc = O.Camera(**cam), O.Camera(**cam, Ti0=Ti0)
+    wg, sg = slamklt.triangulate_stereo(ctx, und, rund, gc, grc, wc, max_error=3.0)
+    wo, so = O.triangulate_stereo(und, rund, oc, orc, wc, max_error=3.0)
+    assert set(np.unique(so)) >= {1, 2, 5} or set(np.unique(so)) >= {1, 4}, np.unique(so, return_counts=True)
+    agree = so == sg
+    assert agree.mean() >= 0.999, (np.unique(so, return_counts=True), np.unique(sg, return_counts=True))
+    both = (so == 1) & (sg == 1)
+    assert both.sum() > 2000
+    rel = np.abs(wg[both] - wo[both]).max(axis=1) / np.abs(wo[both]).max(axis=1)
+    assert rel.max() < 1e-9, rel.max()
+    assert np.isnan(wg[sg != 1]).all()
+    # noiseless observations reproduce the scene exactly (sanity of the DLT itself, independent of the oracle)
+    und0, rund0, cam0, Ti00, wc0 = _stereo_scene(200, 7, noise=0.0)
+    w0, s0 = slamklt.triangulate_stereo(ctx, und0, rund0, gc, grc, wc0)
+    good = np.ones(200, bool); good[::17] = False; good[5::23] = False
+    rng = np.random.default_rng(7)
+    X = np.stack([rng.uniform(-8, 8, 200), rng.uniform(-2, 2, 200), rng.uniform(3, 60, 200), np.ones(200)], axis=1)
+    assert (s0[good] == 1).all()
+    assert np.allclose(w0[good], (X @ wc0.T)[good, :3], rtol=0, atol=1e-6)
+    assert slamklt.triangulate_stereo(ctx, np.zeros((0, 2)), np.zeros((0, 2)), gc, grc, wc)[0].shape == (0, 3)
+
+
+def test_brief_describe_and_hamming_matching(ctx):
+    """describe (extractor.jl:103-105) and the descriptor side of find_best_match (mapper.jl:392-462,
+    map_point.jl:165-174) against the oracle's restatement.  Integer / bit work: results must be identical."""
+    fr, _ = synth.make_sequence(2011, 2, H=188, W=320)
+    img, img2 = synth.to_f64(fr)[0], synth.to_f64(fr)[1]
+    pairs = slamklt.brief_pairs_stand_in(256, 9, seed=123)
+    assert pairs.shape == (256, 4) and np.abs(pairs).max() <= 5
+    rng = np.random.default_rng(3)
+    kps = np.stack([rng.integers(1, 189, 700), rng.integers(1, 321, 700)], axis=1).astype(np.int64)
+    kps[:8] = [[1, 1], [188, 320], [5, 5], [6, 6], [183, 315], [184, 316], [6, 320], [188, 6]]   # around the border rule
+    dg, kg = slamklt.describe(ctx, img, kps, pairs)
+    do, ko = O.describe(img, kps, pairs)
+    assert np.array_equal(kg, ko) and len(kg) < len(kps)
+    assert np.array_equal(dg, do)
+    d8, k8 = slamklt.describe(ctx, fr[0], kps, pairs)                      # UInt8 frame: same i/255 values
+    assert np.array_equal(d8, do) and np.array_equal(k8, ko)
+    assert dg.shape[1] == 8 and 0.3 < np.unpackbits(dg.view(np.uint8)).mean() < 0.7
+    # map points = sets of 1..4 descriptors (observations in several keyframes); targets with candidate lists, some empty sets
+    d2, _ = O.describe(img2, ko, pairs)                                    # second view of (roughly) the same places
+    n = min(len(do), len(d2))
+    rows, set_off = [], [0]
+    for s in range(300):
+        m = int(rng.integers(0, 5))                                        # 0 = map point without descriptors
+        for _ in range(m):
+            src = do if rng.random() < 0.5 else d2
+            rows.append(src[int(rng.integers(0, n))])
+        set_off.append(len(rows))
+    desc = np.array(rows, dtype=np.uint32)
+    targets = rng.integers(0, 300, 200).astype(np.int32)
+    cand_off, cand = [0], []
+    for t in range(200):
+        cand += list(rng.integers(0, 300, int(rng.integers(0, 12))))
+        cand_off.append(len(cand))
+    cand = np.array(cand, dtype=np.int32)
+    for max_d in (256, 60):
+        bg = slamklt.find_best_match(ctx, desc, set_off, targets, cand_off, cand, max_d)
+        bo = O.find_best_match(desc, set_off, targets, cand_off, cand, max_d)
+        for g, o in zip(bg, bo):
+            assert np.array_equal(g, o)
+    assert (bg[0] >= 0).any() and (bg[0] < 0).any()
