@@ -6,8 +6,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
+
+#include <sched.h>
 #include <string>
 #include <utility>
 #include <vector>
@@ -175,6 +181,76 @@ struct HostBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// host worker pool (only used to repack Float64 host frames, see pack_u8_exact)
+// ---------------------------------------------------------------------------------------------
+class HostPool {
+public:
+    explicit HostPool(int n_threads) {
+        for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++epoch_; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    // fn(i) for i in [0, n) on the workers; returns at once.  wait() joins in on what is left and returns when all items are done.
+    void start(int n, std::function<void(int)> fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = std::move(fn); n_ = n; next_.store(0); left_.store(n);
+            active_ = n > 0;
+            ++epoch_;
+        }
+        cv_.notify_all();
+    }
+    void wait() {
+        if (!active_) return;
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return left_.load() == 0; });
+        active_ = false;
+    }
+
+private:
+    void work() {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n_) break;
+            fn_(i);
+            if (left_.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+        }
+    }
+    void run() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::function<void(int)> fn_;
+    int n_ = 0;
+    bool active_ = false;
+    std::atomic<int> next_{0}, left_{0};
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
+// Lossless repacking of a Float64 frame that holds 8-bit data (every pixel exactly k/255, what Gray{Float64}.(load(png)) of the
+// reference's example produces, example/kitty/main.jl:36-40): dst[i] = k.  Returns false at the first pixel that is not such a
+// value; the caller then ships the frame as Float64.  The device reconstructs (double)k / 255.0, i.e. the identical Float64.
+namespace sk { bool pack_u8_exact_impl(const double* src, uint8_t* dst, size_t n); }  // host_pack.cpp (AVX-512 / AVX2 / scalar)
+static bool pack_u8_exact(const double* src, uint8_t* dst, size_t n) { return sk::pack_u8_exact_impl(src, dst, n); }
+
 struct slamklt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -190,6 +266,7 @@ struct slamklt_ctx {
     uint64_t launches = 0, h2d = 0, d2h = 0;
     DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match, gtab;
     HostBuf h_out, h_status, h_misc;
+    HostPool* pool = nullptr;  // created on first use
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
     // per-kernel profiling (off by default)
     bool prof_on = false;
@@ -231,6 +308,7 @@ struct slamklt_batch {
     int n_frames = 0, n_slots = 0, slot0 = 0, max_pts = 0, n_pts = 0;
     int up_dtype = -1, up_ld = 0;
     void* d_maps = nullptr;  // device array of per-level tensor maps over the slot ring
+    HostBuf h_pack;          // pinned staging of the 8-bit repacked host frames (slamklt_batch_step)
     TScratch ts{};           // scratch ring of the y-filtered product planes (kept in L2 by an access-policy window)
     int build_group = 0;     // frames per build group (0: whole batch at once, planes inside the frame blocks)
     DevBuf staging, img64, pts, outp, status, gtab;
@@ -428,6 +506,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match, &c->gtab};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
+    delete c->pool;
     for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaFree(c->d_counters);
@@ -1257,6 +1336,7 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     for (auto* v : b->views) delete v;
     if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
     b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
+    b->h_pack.release();
     if (b->d_maps) cudaFree(b->d_maps);
     if (b->ts.base) cudaFree(b->ts.base);
     cudaFree(b->base);
@@ -1421,26 +1501,43 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     CK(cudaEventRecord(evStart, c->stream));
     CK(cudaStreamWaitEvent(c->copy_stream, evStart, 0));
     if (side_lk) CK(cudaStreamWaitEvent(c->lk_stream, evStart, 0));
+    // Float64 host frames that hold 8-bit data are shipped as 8 bits per pixel (pack_u8_exact: lossless, the device rebuilds the
+    // identical Float64): host worker threads repack chunk k+1 while the copy engine and the GPU work on chunk k.  The first
+    // pixel that is not an exact k/255 switches the rest of the step back to plain Float64 uploads.
+    bool try_pack = imgs && dtype == SLAMKLT_F64 && ld == H && (size_t)nf * H * W >= (1u << 20) && getenv("SLAMKLT_NO_PACK") == nullptr;
+    if (try_pack) {
+        if ((r = b->h_pack.ensure((size_t)nf * H * W))) return r;
+        if (!c->pool) {
+            int avail = (int)std::thread::hardware_concurrency();
+            cpu_set_t set;
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+            const char* e = getenv("SLAMKLT_HOST_THREADS");
+            int want = e ? atoi(e) : std::min(avail, 16);
+            c->pool = new HostPool(std::max(want, 1) - 1);
+        }
+    }
+    int n_packed = 0, n_plain = 0;
+    const size_t npx = (size_t)H * W;
+    std::atomic<int> pack_bad{0};
+    // repack chunk k on the workers (asynchronously: the calling thread meanwhile queues the GPU work of the chunk before)
+    auto start_pack = [&](int k) {
+        const int f0 = k * chunk, n = std::min(nf, f0 + chunk) - f0;
+        uint8_t* hp = (uint8_t*)b->h_pack.p + (size_t)f0 * npx;
+        const int cols = 64, blocks = (W + cols - 1) / cols;
+        c->pool->start(n * blocks, [=, &pack_bad](int item) {
+            const int f = item / blocks, x0 = (item - f * blocks) * cols, x1 = std::min(W, x0 + cols);
+            const double* sp = (const double*)((const char*)imgs + (size_t)(f0 + f) * frame_stride_bytes) + (size_t)x0 * H;
+            if (!pack_u8_exact(sp, hp + (size_t)f * npx + (size_t)x0 * H, (size_t)(x1 - x0) * H)) pack_bad.store(1);
+        });
+    };
+    struct PoolJoin { HostPool* p; ~PoolJoin() { if (p) p->wait(); } } pool_join{try_pack ? c->pool : nullptr};  // no job outlives this call
+    if (try_pack) start_pack(0);
     if (imgs) {
         if (n_pts > 0) {
             CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)nf * n_pts * 16, cudaMemcpyHostToDevice, c->copy_stream));
             c->h2d += (uint64_t)nf * n_pts * 16;
         }
-        b->n_pts = n_pts; b->up_dtype = dtype; b->up_ld = ld;
-        const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
-        for (int k = 0; k < nchunks; ++k) {
-            const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
-            char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
-            if (contiguous) {
-                CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
-            } else {
-                for (int f = f0; f < f1; ++f)
-                    CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
-                                         (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
-            }
-            c->h2d += (uint64_t)n * fbytes;
-            CK(cudaEventRecord(evH2D[k], c->copy_stream));
-        }
+        b->n_pts = n_pts; b->up_ld = ld;
     }
     LKArgs a{};
     a.A = fs_of(b); a.B = fs_of(b);
@@ -1454,11 +1551,43 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     a.n_frames = nf;
     if ((r = set_gtab(b->gtab, &a))) return r;
     char* const gtab0 = (char*)a.gtab;
+    const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
     for (int k = 0; k < nchunks; ++k) {
         const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+        int cd = dtype;                                                         // dtype this chunk reaches the device in
         const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
-        if (imgs) CK(cudaStreamWaitEvent(c->stream, evH2D[k], 0));
-        if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, dtype, sigma, mode, nullptr, &b->ts, b->build_group))) return r;
+        if (imgs) {
+            bool packed = false;
+            if (try_pack) {
+                c->pool->wait();
+                packed = pack_bad.load() == 0;
+                if (!packed) try_pack = false;
+                else {
+                    const uint8_t* hp = (const uint8_t*)b->h_pack.p + (size_t)f0 * npx;
+                    char* dst = (char*)b->staging.p + (size_t)f0 * npx;
+                    CK(cudaMemcpyAsync(dst, hp, (size_t)n * npx, cudaMemcpyHostToDevice, c->copy_stream));
+                    c->h2d += (uint64_t)n * npx;
+                    cd = SLAMKLT_U8; src = dst;
+                    ++n_packed;
+                    if (k + 1 < nchunks) start_pack(k + 1);
+                }
+            }
+            if (!packed) {
+                char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
+                if (contiguous) {
+                    CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
+                } else {
+                    for (int f = f0; f < f1; ++f)
+                        CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
+                                             (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
+                }
+                c->h2d += (uint64_t)n * fbytes;
+                ++n_plain;
+            }
+            CK(cudaEventRecord(evH2D[k], c->copy_stream));
+            CK(cudaStreamWaitEvent(c->stream, evH2D[k], 0));
+        }
+        if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, cd, sigma, mode, nullptr, &b->ts, b->build_group))) return r;
         if (n_pts > 0) {
             if (side_lk) { CK(cudaEventRecord(evBuilt[k], c->stream)); CK(cudaStreamWaitEvent(lks, evBuilt[k], 0)); }
             a.offA = f0; a.offB = f0 + 1; a.n_frames = n;
@@ -1479,6 +1608,8 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
             }
         }
     }
+    // what the staging buffer now holds (slamklt_batch_detect reads it): one dtype, or nothing usable after a mixed step
+    if (imgs) b->up_dtype = n_plain == 0 ? SLAMKLT_U8 : (n_packed == 0 ? dtype : -1);
     // Only work that touches THIS batch again has to wait for its tracking kernels (see lk_pending above and
     // batch_wait_lk): another batch may build on the compute stream while this one is still being tracked.
     if (n_pts > 0 && side_lk) { CK(cudaEventRecord(b->ev_lk_done, lks)); b->lk_pending = true; }

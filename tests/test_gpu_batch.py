@@ -166,3 +166,44 @@ def test_full_size_batch64_against_oracle(ctx):
         d = np.abs(po[both] - out[i][both]).max(axis=1)
         assert np.mean(d < 0.01) >= 0.999 and d.max() < 0.02
     batch.close()
+
+
+def test_step_repacks_8bit_frames_losslessly_and_falls_back(ctx, monkeypatch):
+    """slamklt_batch_step ships Float64 host frames whose pixels are all exact k/255 as 8 bits per pixel (lossless: the device
+    rebuilds the identical Float64).  The result must be bit-identical to the plain Float64 upload (SLAMKLT_NO_PACK=1), frames
+    that are not 8-bit data must take the Float64 path, and a batch that turns non-8-bit half way must switch over cleanly."""
+    H, W, L, NF, NP = 376, 1241, 3, 16, 300       # 16 x 466 616 px: above the 1 Mpx threshold, 8 chunks of 2 frames
+    fr, _ = synth.make_sequence(2020, NF + 1, H=H, W=W)
+    f64 = synth.to_f64(fr)
+    alg = slamklt.LucasKanade(pyramid_levels=L)
+    pts = np.stack([synth.random_keypoints(300 + i, NP, H, W, border=4.0) for i in range(NF)])
+
+    def run(frames, no_pack):
+        if no_pack:
+            monkeypatch.setenv("SLAMKLT_NO_PACK", "1")
+        else:
+            monkeypatch.delenv("SLAMKLT_NO_PACK", raising=False)
+        b = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+        b.prime(frames[0])
+        h0 = ctx.stats()["h2d_bytes"]
+        out, st = b.step(slamklt.StreamBatch.pack_frames(frames[1:]), pts, alg)
+        sent = ctx.stats()["h2d_bytes"] - h0
+        layer = b.slot(0).plane(2, "layer")       # after the rotation slot 0 is the last frame of the batch
+        b.close()
+        return out, st, sent, layer
+
+    o_plain, s_plain, sent_plain, l_plain = run(f64, True)
+    o_pack, s_pack, sent_pack, l_pack = run(f64, False)
+    assert np.array_equal(s_plain, s_pack) and np.array_equal(np.nan_to_num(o_plain), np.nan_to_num(o_pack)) and np.array_equal(l_plain, l_pack)
+    assert sent_plain > NF * H * W * 8 and sent_pack < NF * H * W * 1.2 + NF * NP * 16 + 1024
+    assert (s_pack & 1).mean() > 0.8
+    # not 8-bit data at all: plain upload, and the same answer as the explicit plain path
+    g = f64 + 1e-9
+    o1, s1, sent1, _ = run(g, False)
+    o2, s2, sent2, _ = run(g, True)
+    assert sent1 == sent2 and np.array_equal(s1, s2) and np.array_equal(np.nan_to_num(o1), np.nan_to_num(o2))
+    # 8-bit until frame 9, then not: the first chunks go packed, the rest plain
+    m = f64.copy(); m[10:] += 1e-9
+    o3, s3, sent3, _ = run(m, False)
+    o4, s4, sent4, _ = run(m, True)
+    assert sent_pack < sent3 < sent4 and np.array_equal(s3, s4) and np.array_equal(np.nan_to_num(o3), np.nan_to_num(o4))

@@ -11,5 +11,5 @@ for f in lk_tma lk_patch pyramid api lk; do
   $NV $flags -Xptxas -v -c $f.cu -o variants/obj_$name/$f.o 2> variants/obj_$name/$f.log &
 done
 wait
-$NV -shared -o variants/libslamklt_$name.so variants/obj_$name/*.o detect.o match.o brief.o -Xlinker --exclude-libs,ALL
+$NV -shared -o variants/libslamklt_$name.so variants/obj_$name/*.o detect.o match.o brief.o host_pack.o -Xlinker --exclude-libs,ALL
 grep -E "Used|spill" variants/obj_$name/lk_tma.log | head -4
