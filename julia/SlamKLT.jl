@@ -9,6 +9,9 @@
 # order; Matrix{Gray{Float64}} reinterprets to column-major Float64 with ld = H; Vector{CartesianIndex{2}} is dense
 # Int64 pairs.
 
+import Random   # BRIEF's sampling pattern is drawn from Julia's RNG (see _brief_pairs); BRIEF itself comes from ImageFeatures,
+                # which src/SLAM.jl already loads
+
 const libslamklt = get(ENV, "SLAMKLT_LIB", "libslamklt.so")
 
 const SLAMKLT_F64 = Cint(0)
@@ -161,12 +164,55 @@ function fb_tracking!(previous_pyramid::LKPyramid, current_pyramid::LKPyramid, k
     fb_tracking!(new_keypoints, previous_pyramid, current_pyramid, keypoints, algorithm; displacement, max_distance)
 end
 
-# ---- extractor.jl:7-22 (describe / BRIEF stays with ImageFeatures: SURVEY 8f)
+# ---- extractor.jl:7-22.  The descriptor field stays (params.do_local_matching = true needs `describe`).
 struct Extractor
     max_points::Int
+    descriptor::BRIEF
     radius::Int
     grid_resolution::Tuple{Int, Int}
     cell_size::Int
+end
+Extractor(max_points, radius, grid_resolution, cell_size) =
+    Extractor(max_points, BRIEF(; size = 256), radius, grid_resolution, cell_size)       # extractor.jl:20-22
+
+# BRIEF's sampling pattern comes from Julia's RNG (ImageFeatures brief.jl: Random.seed!(params.seed); params.sampling_type(size,
+# window)); it is drawn here exactly as create_descriptor draws it and handed to the library as (dy1, dx1, dy2, dx2) rows.
+function _brief_pairs(b::BRIEF)
+    Random.seed!(b.seed)                                   # ImageFeatures brief.jl does the same before sampling
+    s1, s2 = b.sampling_type(b.size, b.window)
+    pairs = Matrix{Int32}(undef, 4, b.size)
+    for k in 1:b.size
+        pairs[1, k] = s1[k][1]; pairs[2, k] = s1[k][2]; pairs[3, k] = s2[k][1]; pairs[4, k] = s2[k][2]
+    end
+    pairs
+end
+
+# extractor.jl:103-105: create_descriptor(image, keypoints, e.descriptor) -> (Vector{BitVector}, Vector{CartesianIndex{2}})
+function describe(e::Extractor, image, keypoints)
+    b = e.descriptor
+    img = reinterpret(Float64, image)
+    H, W = size(img)
+    n = length(keypoints)
+    n == 0 && return BitVector[], CartesianIndex{2}[]
+    kps = keypoints isa Vector{CartesianIndex{2}} ? keypoints : collect(CartesianIndex{2}, keypoints)
+    pairs = _brief_pairs(b)
+    words = b.size ÷ 32
+    desc = Matrix{UInt32}(undef, words, n)
+    valid = Vector{UInt8}(undef, n)
+    GC.@preserve img kps pairs desc valid _ck(ccall((:slamklt_describe, libslamklt), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{Int64}, Cint, Ptr{Int32}, Cint, Cint, Cdouble, Ptr{UInt32}, Ptr{UInt8}),
+        klt_ctx().handle, pointer(img), SLAMKLT_F64, H, W, H, pointer(kps), n, pointer(pairs), b.size, b.window, b.sigma,
+        pointer(desc), pointer(valid)))
+    descriptors = BitVector[]; kept = CartesianIndex{2}[]
+    for j in 1:n
+        valid[j] == 0 && continue
+        d = BitVector(undef, b.size)
+        for w in 1:words, bit in 0:31                      # bit b of word w = descriptor bit 32 (w - 1) + b + 1
+            d[32 * (w - 1) + bit + 1] = (desc[w, j] >> bit) & 0x1 == 0x1
+        end
+        push!(descriptors, d); push!(kept, kps[j])
+    end
+    descriptors, kept
 end
 
 # extractor.jl:63-95
@@ -186,6 +232,32 @@ function detect(e::Extractor, image, current_points; σ_mask = 3)
         klt_ctx().handle, pointer(img), SLAMKLT_F64, H, W, H, isempty(cur) ? Ptr{Float64}(C_NULL) : pointer(cur), length(cur),
         prm, pointer(out), cap, n_out))
     resize!(out, n_out[])
+end
+
+# ---- optional (SURVEY 8f row 2): triangulate_stereo! (mapper.jl:142-183) with the per-keypoint DLT + checks on the device ------
+# The GEEV4x4Cache argument is kept for the call site (mapper.jl:72-74) and ignored.
+function triangulate_stereo!(map_manager::MapManager, frame::Frame, max_error, cache)
+    stereo_keypoints = get_stereo_keypoints(frame)
+    isempty(stereo_keypoints) && (@warn "[MP] No stereo keypoints to triangulate."; return)
+    ids = Int64[]; und = Point2f[]; rund = Point2f[]
+    for kp in stereo_keypoints                                     # host-side bookkeeping of mapper.jl:156-161
+        kp.is_3d && continue
+        mp = get_mappoint(map_manager, kp.id)
+        mp ≡ nothing && (remove_mappoint_obs!(map_manager, kp.id, frame.kfid); continue)
+        mp.is_3d && continue
+        push!(ids, kp.id); push!(und, kp.undistorted_pixel); push!(rund, kp.right_undistorted_pixel)
+    end
+    n = length(ids)
+    n == 0 && return
+    world = Vector{Point3f}(undef, n); status = Vector{UInt8}(undef, n)
+    cam = Ref(_cam(frame.camera)); rcam = Ref(_cam(frame.right_camera))
+    wc = collect(Float64, lock(() -> frame.wc, frame.pose_lock))
+    GC.@preserve und rund world status wc _ck(ccall((:slamklt_triangulate_stereo, libslamklt), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ref{SlamKltCamera}, Ref{SlamKltCamera}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{UInt8}),
+        klt_ctx().handle, pointer(und), pointer(rund), n, cam, rcam, pointer(wc), Float64(max_error), pointer(world), pointer(status)))
+    for j in 1:n
+        status[j] == 0x01 ? update_mappoint!(map_manager, ids[j], world[j]) : remove_stereo_keypoint!(frame, ids[j])
+    end
 end
 
 # ---- optional (SURVEY 8f rows 1-2): optical_flow_matching! with its per-keypoint geometry on the device ------------------
