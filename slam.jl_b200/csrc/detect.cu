@@ -29,7 +29,7 @@ constexpr int MAX_NEAR = 512;  // current points kept in shared memory per cell 
 //   C: candidates (response double + index int, at most ceil(cs/2)^2 strict maxima); during the mask phase the list of
 //      nearby current points (2*MAX_NEAR ints)
 //   D: 64 ints of scan scratch
-struct DetSmem { size_t oA, oB, oTmp, oM0, oCandR, oCandI, oNear, oMisc, total; };
+struct DetSmem { size_t oA, oB, oTmp, oM0, oCandR, oCandI, oNear, oMisc, oBits, total; };
 __host__ __device__ inline DetSmem det_smem_plan(int cs, int hw) {
     const size_t P = cs + 2, pad = P * P, rw = cs + 2 * hw;
     const size_t nc = (size_t)((cs + 1) / 2) * ((cs + 1) / 2);
@@ -49,7 +49,8 @@ __host__ __device__ inline DetSmem det_smem_plan(int cs, int hw) {
     const size_t endNear = m.oNear + 2 * (size_t)MAX_NEAR * 4;
     if (endNear > endC) endC = endNear;
     m.oMisc = (endC + 15) & ~(size_t)15;
-    m.total = m.oMisc + 64 * 4;
+    m.oBits = m.oMisc + 64 * 4;          // bit planes of the fast mask path: 64 column words + 64 "zero" + 64 "full" row words
+    m.total = m.oBits + 3 * 64 * 8;
     return m;
 }
 
@@ -140,6 +141,97 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         const int rh = h + 2 * hw, rw = w + 2 * hw;
         const int r2 = a.radius * a.radius;
         const DivH drh(rh);
+        // ---- fast path: the binary mask of the halo region as one 64-bit word per region column (bit = region row).  Discs are
+        // rasterised column by column with one atomicAnd each; the replicated image border is a bit fill; the 13-tap y pass reads a
+        // 13-bit pattern per output and only patterns that are neither all ones nor all zeros run the tap loop (same taps, same
+        // order => same Float64 sums); the x pass does the same on per-row "all zero" / "all full" words.
+        const bool fastmask = hw > 0 && rh <= 64 && rw <= 64 && n_near <= MAX_NEAR;
+        if (fastmask) {
+            unsigned long long* s_col = (unsigned long long*)(smem_raw + sm.oBits);
+            unsigned long long* s_zero = s_col + 64;
+            unsigned long long* s_full = s_zero + 64;
+            const unsigned long long allrows = rh == 64 ? ~0ull : ((1ull << rh) - 1ull);
+            for (int i = tid; i < 64; i += DET_THREADS) { s_col[i] = allrows; s_zero[i] = 0ull; s_full[i] = 0ull; }
+            __syncthreads();
+            const int ry0 = y0 - hw, rx0 = x0 - hw;  // image row / column (0-based) of region row / column 0
+            const int ncolsd = 2 * a.radius + 1;
+            for (int it = tid; it < n_near * ncolsd; it += DET_THREADS) {
+                const int k = it / ncolsd, dx = it - k * ncolsd - a.radius;
+                const int X = s_near[2 * k + 1] - 1 + dx;  // 0-based image column
+                const int xx = X - rx0;
+                if (X < 0 || X >= W || xx < 0 || xx >= rw) continue;
+                const int rem = r2 - dx * dx;
+                int sy = (int)sqrtf((float)rem);
+                while (sy * sy > rem) --sy;
+                while ((sy + 1) * (sy + 1) <= rem) ++sy;
+                // strictly inside the circle the Float64 ellipse test always holds; only a lattice point ON the circle needs it
+                if (sy * sy == rem && !in_disc(sy, dx, a.radius)) --sy;
+                if (sy < 0) continue;
+                const int Yc = s_near[2 * k] - 1;
+                const int ra = max(max(Yc - sy, 0) - ry0, 0), rb = min(min(Yc + sy, H - 1) - ry0, rh - 1);
+                if (ra > rb) continue;
+                const int len = rb - ra + 1;
+                const unsigned long long bits = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << ra;
+                atomicAnd(&s_col[xx], ~bits);
+            }
+            __syncthreads();
+            // replicate border of the full-image mask: rows above / below the image repeat the first / last image row ...
+            const int top = max(0, -ry0), bot = min(rh, H - ry0);  // region rows [top, bot) lie in the image
+            const int left = max(0, -rx0), right = min(rw, W - rx0);
+            for (int xx = tid + left; xx < right; xx += DET_THREADS) {
+                unsigned long long wv = s_col[xx];
+                if (top > 0) {
+                    const unsigned long long lowm = (1ull << top) - 1ull;
+                    wv = ((wv >> top) & 1ull) ? (wv | lowm) : (wv & ~lowm);
+                }
+                if (bot < rh) {
+                    const unsigned long long him = allrows & ~((1ull << bot) - 1ull);
+                    wv = ((wv >> (bot - 1)) & 1ull) ? (wv | him) : (wv & ~him);
+                }
+                s_col[xx] = wv;
+            }
+            __syncthreads();
+            // ... and columns left / right of the image repeat the first / last image column
+            for (int xx = tid; xx < rw; xx += DET_THREADS) {
+                if (xx < left) s_col[xx] = s_col[left];
+                else if (xx >= right) s_col[xx] = s_col[right - 1];
+            }
+            __syncthreads();
+            const int nt = 2 * hw + 1;
+            const unsigned pmask = (1u << nt) - 1u;
+            double sall = 0.0, call = 0.0;
+            for (int t = 0; t < nt; ++t) sall += a.kw[t];
+            for (int t = 0; t < nt; ++t) call += a.kw[t] * sall;
+            // y pass -> s_tmp[h][rw]
+            for (int i = tid; i < h * rw; i += DET_THREADS) {
+                int y, xx;
+                dh.split(i, y, xx);
+                const unsigned pat = (unsigned)(s_col[xx] >> y) & pmask;
+                double acc;
+                if (pat == pmask) { acc = sall; atomicOr(&s_full[y], 1ull << xx); }
+                else if (pat == 0u) { acc = 0.0; atomicOr(&s_zero[y], 1ull << xx); }
+                else {
+                    acc = 0.0;
+                    for (int t = 0; t < nt; ++t) acc += ((pat >> t) & 1u) ? a.kw[t] : 0.0;
+                }
+                s_tmp[i] = acc;
+            }
+            __syncthreads();
+            for (int i = tid; i < npx; i += DET_THREADS) {
+                int y, x;
+                dh.split(i, y, x);
+                const unsigned zb = (unsigned)(s_zero[y] >> x) & pmask, fb = (unsigned)(s_full[y] >> x) & pmask;
+                double acc;
+                if (zb == pmask) acc = 0.0;
+                else if (fb == pmask) acc = call;
+                else {
+                    const double* tp = s_tmp + y + x * h;
+                    acc = 0.0;
+                    for (int t = 0; t < nt; ++t) acc += a.kw[t] * tp[t * h];
+                }
+                s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * acc;
+            }
+        } else {
         // binary mask on the halo region; coordinates clamped to the image (replicate border of the blur)
         const bool inner = y0 - hw >= 0 && y1 + hw <= H && x0 - hw >= 0 && x1 + hw <= W && n_near <= MAX_NEAR;
         if (inner) {
@@ -156,7 +248,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 int sx = (int)sqrtf((float)rem);
                 while (sx * sx > rem) --sx;
                 while ((sx + 1) * (sx + 1) <= rem) ++sx;
-                while (sx >= 0 && !in_disc(dy, sx, a.radius)) --sx;  // the lattice points on the circle itself
+                if (sx * sx == rem && !in_disc(dy, sx, a.radius)) --sx;  // only a lattice point ON the circle needs the Float64 test
                 if (sx < 0) continue;
                 const int xc = s_near[2 * k + 1] - 1 - (x0 - hw);
                 const int xa = max(xc - sx, 0), xb = min(xc + sx, rw - 1);
@@ -171,12 +263,14 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 if (n_near <= MAX_NEAR) {
                     for (int k = 0; k < n_near; ++k) {
                         const int dy = Y - s_near[2 * k], dx = X - s_near[2 * k + 1];
-                        if (dy * dy + dx * dx <= r2 && in_disc(dy, dx, a.radius)) { m = 0; break; }
+                        const int d2 = dy * dy + dx * dx;
+                        if (d2 < r2 || (d2 == r2 && in_disc(dy, dx, a.radius))) { m = 0; break; }
                     }
                 } else {
                     for (int k = 0; k < a.n_cur; ++k) {
                         const int dy = Y - (int)rint(cur[2 * k]), dx = X - (int)rint(cur[2 * k + 1]);
-                        if (dy * dy + dx * dx <= r2 && in_disc(dy, dx, a.radius)) { m = 0; break; }
+                        const int d2 = dy * dy + dx * dx;
+                        if (d2 < r2 || (d2 == r2 && in_disc(dy, dx, a.radius))) { m = 0; break; }
                     }
                 }
                 s_m0[i] = m;
@@ -209,6 +303,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 s_img[(y + 1) + (x + 1) * P] = s_m0[i] ? img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] : img[(size_t)(y0 + y) + (size_t)(x0 + x) * H] * 0.0;
             }
         }
+        }  // generic mask path
     } else {
         for (int i = tid; i < npx; i += DET_THREADS) {
             int y, x;
@@ -235,6 +330,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
     // ---- Shi-Tomasi response on the cell sub-image (replicate border at the cell edge) --------
     // NPT independent pixels per thread and round are unrolled together: the Float64 chains of one pixel are short on ILP
     constexpr int NPT = 5;
+    const double k9 = 1.0 / 9.0;  // the 3x3 mean is imfilter with a (1/9)-valued kernel: products accumulated tap by tap
     for (int base = 0; base < npx; base += DET_THREADS * NPT) {
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
@@ -249,7 +345,9 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
                 const double g_y = ((mp - mm) + 2.0 * (zp - zm) + (pp - pm)) / 8.0;
                 const double g_x = ((pm - mm) + 2.0 * (p0 - m0) + (pp - mp)) / 8.0;
                 const int o = (y + 1) + (x + 1) * P;
-                s_gyy[o] = g_y * g_y; s_gyx[o] = g_y * g_x; s_gxx[o] = g_x * g_x;
+                // the box filter multiplies every tap by 1/9 (imfilter with a (1/9)-valued kernel): the rounded product is the
+                // same for each of the nine windows a pixel belongs to, so it is formed once here
+                s_gyy[o] = k9 * (g_y * g_y); s_gyx[o] = k9 * (g_y * g_x); s_gxx[o] = k9 * (g_x * g_x);
             }
         }
     }
@@ -277,7 +375,6 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
         s_R[yy + xx * P] = -__longlong_as_double(0x7ff0000000000000LL);
     }
     __syncthreads();
-    const double k9 = 1.0 / 9.0;  // the 3x3 mean is imfilter with a (1/9)-valued kernel: products accumulated tap by tap
     for (int base = 0; base < npx; base += DET_THREADS * NPT) {
 #pragma unroll
         for (int k = 0; k < NPT; ++k) {
@@ -292,7 +389,7 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
 #pragma unroll
                     for (int dy = -1; dy <= 1; ++dy) {
                         const int j = o + dy + dx * P;
-                        sa += k9 * s_gyy[j]; sb += k9 * s_gyx[j]; sc += k9 * s_gxx[j];
+                        sa += s_gyy[j]; sb += s_gyx[j]; sc += s_gxx[j];
                     }
                 s_R[o] = ((sa + sc) - sqrt((sa - sc) * (sa - sc) + 4.0 * sb * sb)) / 2.0;
             }
