@@ -773,6 +773,9 @@ int slamklt_pyr_download(slamklt_ctx* c, const slamklt_pyr* p, int level, int pl
         default: return fail(SLAMKLT_E_INVALID, "unknown plane %d", plane);
     }
     if ((which >= 0 || comp >= 0 || prefix) && !p->built) return fail(SLAMKLT_E_INVALID, "pyramid has no gradients (not built)");
+    if (plane == SLAMKLT_PLANE_BLUR && p->parent && p->parent->n_frames > 1 && getenv("SLAMKLT_NO_FUSED_RESIZE") == nullptr)
+        return fail(SLAMKLT_E_INVALID, "the blurred planes of a batch slot are not retained (blur and decimation are one kernel there); "
+                                       "build a standalone pyramid to inspect them");
     if (which >= 0 && p->parent && p->parent->ts.base)
         return fail(SLAMKLT_E_INVALID, "the smoothed product planes of a batch slot are not retained (the batch builds them through a scratch ring); "
                                        "build a standalone pyramid to inspect them");

@@ -21,9 +21,11 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <vector>
 
 // experiment knob: software prefetch of the raw Float64 column COLS_PREFETCH_DIST columns ahead (1 = into L2, 2 = into L1)
 #ifndef COLS_PREFETCH
@@ -603,6 +605,12 @@ struct RowArgs {
     const float* t_base;
     size_t t_stride, o_t;
     int t_ring;
+    // MODE 2 (blur x pass fused with the bilinear decimation): next level's layer plane and the source-index / weight tables
+    int keep_blur;          // also store the blurred plane (LKCache.gaussian_filtered) at o_out0
+    int Ho, Wo, pout;
+    size_t o_next;
+    const int* iy_tab; const float* wy_tab;   // per output row: 1-based source row iy (rows iy-1, iy 0-based) and weight
+    const int* ix_tab; const float* wx_tab;   // per output column
 };
 
 // base + k columns as one IMAD.WIDE.U32 (u32 x u32 + u64)
@@ -624,7 +632,9 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     const int rl = threadIdx.x % LR;
     const int ch = threadIdx.x / LR;
     const int NC = (a.W + KRt - 1) / KRt;
-    const int r = blockIdx.x * LR + rl;
+    // MODE 2: the CTA owns 8 output rows of the next level; its LR = 16 source rows start at the first row they sample
+    const int srow0 = MODE == 2 ? __ldg(a.iy_tab + min(8 * (int)blockIdx.x, a.Ho - 1)) - 1 : 0;
+    const int r = MODE == 2 ? min(srow0 + rl, a.H - 1) : blockIdx.x * LR + rl;
     const int plane = blockIdx.y;
     const int f = blockIdx.z;
     const bool chok = ch < NC;  // the block is rounded up to whole warps
@@ -734,7 +744,7 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
     }
 
     const bool fullc = x0 + KRt <= n;
-    if (MODE == 0) {
+    if (MODE == 0 || (MODE == 2 && a.keep_blur)) {
         float* q = row_ptr(out, pitch4, x0);
         if (a.inv_n) {
 #pragma unroll
@@ -746,7 +756,43 @@ __global__ void __launch_bounds__(32 * LR, (LR == 16 && KRt <= 40) ? 2 : 1) k_ro
             for (int j = 0; j < KRt; ++j)
                 if (fullc || x0 + j < n) *row_ptr(q, pitch4, j) = x[j];
         }
-    } else {
+    }
+    if constexpr (MODE == 2) {
+        // ---- bilinear decimation (pyramid.jl:120-121, [3P] imresize!) of the rows this CTA just blurred, same arithmetic and
+        // order as k_resize: vertical lerp of the two source rows, then horizontal lerp of the two source columns.
+        extern __shared__ float sV[];                   // 8 output rows x (NC * KRt + 1) vertically interpolated values
+        const int wpad = NC * KRt + 1;
+        if (!(MODE == 0 || a.keep_blur) && a.inv_n) {   // (the NA normalisation was applied above only when the plane is stored)
+#pragma unroll
+            for (int j = 0; j < KRt; ++j)
+                if (fullc || x0 + j < n) x[j] *= __ldg(a.inv_n + x0 + j);
+        }
+        int mi = -1;
+        float wy = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int i = 8 * (int)blockIdx.x + m;
+            if (i < a.Ho && __ldg(a.iy_tab + i) - 1 - srow0 == rl) { mi = m; wy = __ldg(a.wy_tab + i); }
+        }
+#pragma unroll
+        for (int j = 0; j < KRt; ++j) {
+            const float below = __shfl_down_sync(FULL, x[j], 1);  // row rl + 1 of the same chunk (rl <= 14 for every producing row)
+            if (mi >= 0 && chok && (fullc || x0 + j < n)) sV[mi * wpad + x0 + j] = (1.f - wy) * x[j] + wy * below;
+        }
+        __syncthreads();
+        float* nxt = fb + a.o_next;
+        for (int idx = threadIdx.x; idx < 8 * a.Wo; idx += blockDim.x) {
+            const int m = idx & 7, jo = idx >> 3;
+            const int i = 8 * (int)blockIdx.x + m;
+            if (i < a.Ho) {
+                const int ix = __ldg(a.ix_tab + jo);
+                const float wx = __ldg(a.wx_tab + jo);
+                const float c0 = sV[m * wpad + ix - 1], c1 = sV[m * wpad + ix];
+                nxt[i + (size_t)jo * a.pout] = (1.f - wx) * c0 + wx * c1;
+            }
+        }
+    }
+    if constexpr (MODE == 1) {
         // exclusive prefix along x in Float64: out[., j+1] = sum_{x' <= j} v[x']
         if (!fullc) {
 #pragma unroll
@@ -875,6 +921,57 @@ static void dispatch_rows(cudaStream_t s, const RowArgs& a, const IirDev& c, int
 }
 
 static int krow_of(int W) { return W <= 32 * 40 ? 40 : 64; }
+
+// blur x pass fused with the decimation (MODE 2): 8 output rows per CTA, 16 source rows, dynamic shared memory for the
+// vertically interpolated rows
+static void dispatch_rows_resize(cudaStream_t s, const RowArgs& a, const IirDev& c) {
+    dim3 grid((a.Ho + 7) / 8, 1, a.n_frames);
+    if (a.W <= 32 * 40) {
+        const int NC = (a.W + 39) / 40;
+        const int threads = ((16 * NC + 31) / 32) * 32;
+        const size_t smem = (size_t)8 * (NC * 40 + 1) * sizeof(float);
+        static const bool once = [] { cudaFuncSetAttribute(k_rows<40, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (32 * 40 + 1) * 4); return true; }();
+        (void)once;
+        k_rows<40, 16, 2><<<grid, threads, smem, s>>>(a, c);
+    } else {
+        const int NC = (a.W + 63) / 64;
+        const int threads = ((16 * NC + 31) / 32) * 32;
+        const size_t smem = (size_t)8 * (NC * 64 + 1) * sizeof(float);
+        static const bool once = [] { cudaFuncSetAttribute(k_rows<64, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (32 * 64 + 1) * 4); return true; }();
+        (void)once;
+        k_rows<64, 16, 2><<<grid, threads, smem, s>>>(a, c);
+    }
+}
+
+// source index / weight tables of the bilinear decimation n_in -> n_out ([3P] imresize!: 1-based source coordinate
+// sf * (i - 1/2) + 1/2, computed in double like the reference), cached on the device per (n_in, n_out)
+struct ResizeTab { int* idx; float* w; };
+static ResizeTab resize_table(int n_in, int n_out) {
+    static std::map<std::pair<int, std::pair<int, int>>, ResizeTab> cache;  // (device, (n_in, n_out))
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto key = std::make_pair(dev, std::make_pair(n_in, n_out));
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    std::vector<int> idx(n_out);
+    std::vector<float> w(n_out);
+    const double sf = (double)n_in / (double)n_out;
+    for (int i = 0; i < n_out; ++i) {
+        const double r = sf * ((double)i + 0.5) + 0.5;
+        int ii = (int)std::floor(r);
+        ii = std::min(std::max(ii, 1), n_in - 1);
+        idx[i] = ii; w[i] = (float)(r - ii);
+    }
+    ResizeTab t{nullptr, nullptr};
+    cudaMalloc(&t.idx, sizeof(int) * n_out);
+    cudaMalloc(&t.w, sizeof(float) * n_out);
+    cudaMemcpy(t.idx, idx.data(), sizeof(int) * n_out, cudaMemcpyHostToDevice);
+    cudaMemcpy(t.w, w.data(), sizeof(float) * n_out, cudaMemcpyHostToDevice);
+    cache[key] = t;
+    return t;
+}
 
 // Strip width of the fused column kernel.  A strip of cs columns costs about cs + 0.6 column-times (two halo columns that only
 // load); the grid runs in ceil(units / resident warps) rounds and the last round is rarely full, so the width is chosen to
@@ -1038,6 +1135,19 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             rb.fs = fs; rb.f0 = f0; rb.n_frames = n_frames; rb.H = L.H; rb.W = L.W; rb.pitch = L.pitch; rb.nplanes = 1;
             rb.zero_border = ctor; rb.o_in0 = plane_off(L, DP_TMP); rb.o_out0 = plane_off(L, DP_BLUR); rb.plane_elems = L.plane_elems;
             rb.inv_n = ctor ? inv_nx[l] : nullptr;
+            // blur x pass and decimation in one kernel: the blurred plane is only stored when somebody may read it back
+            // (single pyramids: LKCache.gaussian_filtered, parity downloads); SLAMKLT_NO_FUSED_RESIZE=1 keeps the two kernels
+            static const bool fused = getenv("SLAMKLT_NO_FUSED_RESIZE") == nullptr;
+            if (fused && L.H >= 16) {
+                const ResizeTab ty = resize_table(L.H, N.H), tx = resize_table(L.W, N.W);
+                rb.keep_blur = n_frames == 1 ? 1 : 0;
+                rb.Ho = N.H; rb.Wo = N.W; rb.pout = N.pitch; rb.o_next = plane_off(N, DP_I);
+                rb.iy_tab = ty.idx; rb.wy_tab = ty.w; rb.ix_tab = tx.idx; rb.wx_tab = tx.w;
+                snprintf(nm, sizeof(nm), "k_rows_blur_resize_L%d", l); mark(hk, nm);
+                dispatch_rows_resize(sA, rb, c1);
+                launches += 1;
+                continue;
+            }
             snprintf(nm, sizeof(nm), "k_rows_blur_L%d", l); mark(hk, nm);
             dispatch_rows(sA, rb, c1, 0);
             snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
