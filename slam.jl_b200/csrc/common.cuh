@@ -88,6 +88,7 @@ struct LKArgs {
     // optional table of first-set-up structure tensors, [keypoint][gtab_levels] entries of 16 bytes, filled by k_lk_gprep
     void* gtab;
     int gtab_levels, pad4_;
+    unsigned long long npf_magic;  // ceil(2^40 / n_per_frame), set by the launcher (frame index of a keypoint without a division)
 };
 
 struct DetArgs {

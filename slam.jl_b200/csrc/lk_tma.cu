@@ -259,13 +259,18 @@ __device__ __forceinline__ double join_d(int di, float df) { return (double)di +
 // so that the forward-backward kernel carries none of optflow!'s or optical_flow_matching!'s bookkeeping
 template <int W2, int PR, int PC, int MODE>
 __device__ __forceinline__ void lk_point_tma(const LKArgs& a, const int gw, const int lane, LKTmaSmem<W2, PR, PC>& sm, unsigned& parT, unsigned& parA,
-                                             const double2 pt0, const int next_raw, int& next, double2& pt_next) {
+                                             const double2 pt0, const int next_raw, int& next, double2& pt_next, unsigned long long& acc_wpx,
+                                             unsigned long long& acc_nit) {
     using T = TmaTile<W2, PR, PC>;
     constexpr int TR = T::TR, TC = T::TC, AR = T::AR;
-    const int f = gw / a.n_per_frame;
+    // frame of this keypoint: gw / n_per_frame as a 64-bit multiply by ceil(2^40 / n_per_frame) (exact for gw < 2^40 / n_per_frame)
+    const int f = (int)(((unsigned long long)(unsigned)gw * a.npf_magic) >> 40);
     // template side (A) and target side (B) swap roles on the backward pass: keep the two physical slots and derive pointers
-    // and tensor maps where they are used (once per set-up) instead of carrying them in registers
-    const int slot_first = a.A.slot(a.offA + f), slot_second = a.B.slot(a.offB + f);
+    // and tensor maps where they are used (once per set-up) instead of carrying them in registers.  slot = (slot0 + off + f) mod
+    // n_slots with one conditional subtraction (slot0 < n_slots and off + f <= n_slots)
+    int slot_first = a.A.slot0 + a.offA + f, slot_second = a.B.slot0 + a.offB + f;
+    if (slot_first >= a.A.n_slots) slot_first -= a.A.n_slots;
+    if (slot_second >= a.B.n_slots) slot_second -= a.B.n_slots;
     bool swapped = false;
 #define LKT_SLOT_A (swapped ? slot_second : slot_first)
 #define LKT_SLOT_B (swapped ? slot_first : slot_second)
@@ -623,10 +628,7 @@ retry:
         }
         a.status[gw] = result | ((prior_first && !second_try && result == 3) ? 4 : 0);  // bit2: tracked by the prior pass
     }
-    if (lane == 0 && a.counters) {
-        atomicAdd(a.counters, (unsigned long long)wpx);
-        atomicAdd(a.counters + 1, (unsigned long long)nit);
-    }
+    acc_wpx += wpx; acc_nit += nit;  // flushed once per CTA by the kernel
 }
 
 // resident one-warp CTAs per SM the register allocation is bounded for.  Measured on B200 (64 x 2000 keypoints, forward-backward
@@ -659,13 +661,14 @@ __global__ void __launch_bounds__(32, MODE == 1 ? LKT_MINB : 16) k_lk_tma(const 
     if (lane == 0) base = (int)atomicAdd(a.work, 1u);
     base = __shfl_sync(FULL, base, 0);
     double2 pt = make_double2(0.0, 0.0);
+    unsigned long long acc_wpx = 0, acc_nit = 0;  // executed window-pixel iterations / iterations of this CTA's keypoints
     if (base < total) pt = __ldg(reinterpret_cast<const double2*>(a.pts + 2 * (size_t)base));
     while (base < total) {
         int next_raw = 0;
         if (lane == 0) next_raw = (int)atomicAdd(a.work, 1u);
         int next = -1;
         double2 pt_next = make_double2(0.0, 0.0);
-        lk_point_tma<W2, PR, PC, MODE>(a, base, lane, sm, parT, parA, pt, next_raw, next, pt_next);
+        lk_point_tma<W2, PR, PC, MODE>(a, base, lane, sm, parT, parA, pt, next_raw, next, pt_next, acc_wpx, acc_nit);
         __syncwarp();
         if (next < 0) {  // the keypoint ended early (failed before its last stage): fetch the next one here
             next = __shfl_sync(FULL, next_raw, 0);
@@ -673,6 +676,10 @@ __global__ void __launch_bounds__(32, MODE == 1 ? LKT_MINB : 16) k_lk_tma(const 
         }
         base = next;
         pt = pt_next;
+    }
+    if (lane == 0 && a.counters && acc_nit) {
+        atomicAdd(a.counters, acc_wpx);
+        atomicAdd(a.counters + 1, acc_nit);
     }
 }
 
@@ -702,12 +709,15 @@ bool launch_lk_tma(cudaStream_t s, const LKArgs& a) {
         const int want = e ? atoi(e) : per_sm;
         return sms * (want >= 1 && want <= per_sm ? want : per_sm);
     }();
+    if ((unsigned long long)total * (unsigned long long)a.n_per_frame >= (1ull << 40)) return false;  // (the frame-index multiply)
     const int grid = total < slots ? total : slots;
     cudaMemsetAsync(a.work, 0, sizeof(unsigned), s);
-    if (a.gtab) launch_lk_gprep(s, a);
-    if (a.mode == 0) k_lk_tma<19, 3, 5, 0><<<grid, 32, 0, s>>>(a);
-    else if (a.mode == 1) k_lk_tma<19, 3, 5, 1><<<grid, 32, 0, s>>>(a);
-    else k_lk_tma<19, 3, 5, 2><<<grid, 32, 0, s>>>(a);
+    LKArgs b = a;
+    b.npf_magic = ((1ull << 40) + (unsigned long long)a.n_per_frame - 1) / (unsigned long long)a.n_per_frame;
+    if (b.gtab) launch_lk_gprep(s, b);
+    if (b.mode == 0) k_lk_tma<19, 3, 5, 0><<<grid, 32, 0, s>>>(b);
+    else if (b.mode == 1) k_lk_tma<19, 3, 5, 1><<<grid, 32, 0, s>>>(b);
+    else k_lk_tma<19, 3, 5, 2><<<grid, 32, 0, s>>>(b);
     return true;
 }
 
