@@ -264,6 +264,18 @@ int slamklt_batch_rotate(slamklt_ctx* ctx, slamklt_batch* b);
 int slamklt_batch_step(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, int dtype, int ld,
                        size_t frame_stride_bytes, const double* pts_yx, int n_pts, double sigma, int mode,
                        const slamklt_lk_params* p, double* out_pts_yx, uint8_t* status);
+/* the same step in two halves (stream consumers: front_end.jl:454-481 over many independent sequences).  _begin queues the
+ * uploads, builds, tracking and result copies and returns without waiting for the device; _end waits until out_pts_yx / status
+ * are filled, then rotates.  imgs, pts_yx, out_pts_yx and status must stay valid and untouched in between.  Several batches of
+ * one context may have a step in flight at once: the uploads of one overlap the kernels of the other.  A batch accepts no other
+ * call between its _begin and its _end. */
+int slamklt_batch_step_begin(slamklt_ctx* ctx, slamklt_batch* b, const void* imgs, int dtype, int ld,
+                             size_t frame_stride_bytes, const double* pts_yx, int n_pts, double sigma, int mode,
+                             const slamklt_lk_params* p, double* out_pts_yx, uint8_t* status);
+int slamklt_batch_step_end(slamklt_ctx* ctx, slamklt_batch* b);
+/* diagnostics: measured rates (bytes of Float64 source per second) of the two upload engines slamklt_batch_step uses for
+ * page-locked Float64 frames -- the host worker pool that repacks 8-bit data and the plain copies; 0 = not measured yet */
+int slamklt_upload_rates(slamklt_ctx* ctx, double* pack_bytes_per_s, double* raw_bytes_per_s);
 /* parity access: view of slot `slot` (0..n_frames) as a pyramid handle owned by the batch */
 int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out);
 /* batched detect on the frames last uploaded to the batch (config 5: re-extraction every frame).

@@ -96,7 +96,7 @@ SYMBOLS = [
     "slamklt_pyr_info", "slamklt_pyr_level_dims", "slamklt_pyr_download", "slamklt_optflow", "slamklt_fb_track",
     "slamklt_flow_matching", "slamklt_optical_flow_matching", "slamklt_triangulate_stereo", "slamklt_describe", "slamklt_find_best_match", "slamklt_detect", "slamklt_batch_create", "slamklt_batch_destroy", "slamklt_batch_prime", "slamklt_batch_upload",
     "slamklt_batch_build", "slamklt_batch_track", "slamklt_batch_track_cross", "slamklt_batch_process", "slamklt_batch_download", "slamklt_batch_rotate",
-    "slamklt_batch_step", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
+    "slamklt_batch_step", "slamklt_batch_step_begin", "slamklt_batch_step_end", "slamklt_upload_rates", "slamklt_batch_slot", "slamklt_batch_detect", "slamklt_host_alloc", "slamklt_host_free",
 ]
 
 
@@ -149,6 +149,9 @@ def lib():
         L.slamklt_batch_rotate.argtypes = [vp, vp]
         L.slamklt_batch_step.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, C.c_double, C.c_int,
                                          C.POINTER(LKParams), dp, u8p]
+        L.slamklt_batch_step_begin.argtypes = L.slamklt_batch_step.argtypes
+        L.slamklt_batch_step_end.argtypes = [vp, vp]
+        L.slamklt_upload_rates.argtypes = [vp, dp, dp]
         L.slamklt_batch_slot.argtypes = [vp, C.c_int, C.POINTER(vp)]
         L.slamklt_batch_detect.argtypes = [vp, vp, dp, C.c_int, C.POINTER(DetectParams), i64p, C.c_int, ip]
         L.slamklt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -198,6 +201,12 @@ class Context:
         s = Stats()
         _ck(lib().slamklt_get_stats(self._h, C.byref(s), 1 if reset else 0))
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def upload_rates(self) -> dict:
+        """Measured rates of the two upload engines of StreamBatch.step (GB of Float64 source per second; 0 = not measured)."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        _ck(lib().slamklt_upload_rates(self._h, C.byref(a), C.byref(b)))
+        return {"repack_GBps": a.value / 1e9, "plain_copy_GBps": b.value / 1e9}
 
     def profile(self, enable: bool):
         _ck(lib().slamklt_profile(self._h, 1 if enable else 0))
@@ -609,6 +618,31 @@ class StreamBatch:
                                      self.H, packed_frames.strides[0], _dp(pts), n, float(sigma), mode, C.byref(p), _dp(out_pts),
                                      status.ctypes.data_as(C.POINTER(C.c_uint8))))
         self._npts = n
+        return out_pts, status
+
+    def step_begin(self, packed_frames, points, alg: LucasKanade, max_distance=1.0, sigma=1.0, mode=MODE_UPDATE, out_pts=None,
+                   status=None):
+        """First half of step(): queue everything and return without waiting.  Returns (out_pts, status), valid after step_end().
+        The frames, points and result arrays are kept alive by the batch until then; frames and points must not be modified."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(self.n_frames, -1, 2)
+        n = pts.shape[1]
+        if out_pts is None:
+            out_pts = np.empty((self.n_frames, n, 2))
+        if status is None:
+            status = np.empty((self.n_frames, n), dtype=np.uint8)
+        p = alg._c(max_distance)
+        _ck(lib().slamklt_batch_step_begin(self.ctx._h, self._h, packed_frames.ctypes.data_as(C.c_void_p), self._code(packed_frames),
+                                           self.H, packed_frames.strides[0], _dp(pts), n, float(sigma), mode, C.byref(p), _dp(out_pts),
+                                           status.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._npts = n
+        self._inflight = (packed_frames, pts, out_pts, status)
+        return out_pts, status
+
+    def step_end(self):
+        """Second half of step(): wait for the results of step_begin(), rotate, return (out_pts, status)."""
+        _ck(lib().slamklt_batch_step_end(self.ctx._h, self._h))
+        _, _, out_pts, status = self._inflight
+        self._inflight = None
         return out_pts, status
 
     def slot(self, i) -> LKPyramid:

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -255,6 +256,8 @@ struct slamklt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of the pipelined batch step
+    cudaStream_t raw_stream = nullptr;   // H2D of the chunks that travel as plain Float64 while host threads repack the others
+    double pack_Bps = 0.0, raw_Bps = 0.0;  // measured source bytes per second of the two upload engines (0 = not measured yet)
     cudaStream_t d2h_stream = nullptr;   // D2H of the pipelined batch step
     PyrStreams pyr_streams{};            // build DAG: main + two side streams
     cudaStream_t lk_stream = nullptr;    // tracking of chunk k overlaps the build of chunk k+1
@@ -311,11 +314,16 @@ struct slamklt_batch {
     HostBuf h_pack;          // pinned staging of the 8-bit repacked host frames (slamklt_batch_step)
     TScratch ts{};           // scratch ring of the y-filtered product planes (kept in L2 by an access-policy window)
     int build_group = 0;     // frames per build group (0: whole batch at once, planes inside the frame blocks)
-    DevBuf staging, img64, pts, outp, status, gtab;
+    DevBuf staging, staging8, img64, pts, outp, status, gtab;
     std::vector<slamklt_pyr*> views;
     bool primed = false;
     cudaEvent_t ev_lk_done = nullptr;  // last tracking kernel that read this batch's slots (recorded on the lk stream)
     bool lk_pending = false;
+    cudaEvent_t ev_step_done = nullptr;  // everything slamklt_batch_step_begin queued, result copies included
+    bool step_pending = false;
+    bool quiesced = false;               // nothing of this batch is in flight on any stream (set by the calls that wait for it)
+    std::vector<cudaEvent_t> raw_ev;     // timing events around the plain Float64 chunk copies of the last step (2 per chunk)
+    std::vector<std::pair<int, size_t>> raw_meas;  // (chunk, bytes) of those copies: read back at the next step
 };
 
 // a batch whose last tracking kernel is still in flight on the lk stream must be waited for before the compute stream
@@ -481,6 +489,7 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
     CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, p_build));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->raw_stream, cudaStreamNonBlocking));
     c->pyr_streams.main = c->stream;
     CK(cudaStreamCreateWithPriority(&c->lk_stream, cudaStreamNonBlocking, p_lk));
     CK(cudaStreamCreateWithPriority(&c->pyr_streams.b, cudaStreamNonBlocking, p_build));
@@ -500,7 +509,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     // every stream of the context may still use the buffers freed below
-    cudaStream_t all[] = {c->stream, c->lk_stream, c->copy_stream, c->d2h_stream, c->pyr_streams.b, c->pyr_streams.c};
+    cudaStream_t all[] = {c->stream, c->lk_stream, c->copy_stream, c->raw_stream, c->d2h_stream, c->pyr_streams.b, c->pyr_streams.c};
     for (cudaStream_t st : all) if (st) cudaStreamSynchronize(st);
     for (auto& kv : c->norm_cache) cudaFree(kv.second);
     DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match, &c->gtab};
@@ -513,6 +522,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_join);
     for (auto e : c->pipe_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->raw_stream);
     cudaStreamDestroy(c->d2h_stream);
     for (auto& e : c->pyr_streams.ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->lk_stream);
@@ -528,6 +538,7 @@ int slamklt_ctx_sync(slamklt_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->lk_stream));
+    CK(cudaStreamSynchronize(c->d2h_stream));
     return 0;
 }
 
@@ -542,6 +553,14 @@ int slamklt_get_stats(slamklt_ctx* c, slamklt_stats* out, int reset) {
     out->lk_window_iters = h[0]; out->lk_iters = h[1];
     out->h2d_bytes = c->h2d; out->d2h_bytes = c->d2h;
     if (reset) CK(cudaMemsetAsync(c->d_counters, 0, sizeof(h), c->stream));
+    return 0;
+}
+
+// measured rates of the two upload engines of slamklt_batch_step (source bytes per second; 0 = not measured yet)
+int slamklt_upload_rates(slamklt_ctx* c, double* pack_Bps, double* raw_Bps) {
+    if (!c || !pack_Bps || !raw_Bps) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    *pack_Bps = c->pack_Bps; *raw_Bps = c->raw_Bps;
     return 0;
 }
 
@@ -1304,6 +1323,7 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;
     b->views.resize(b->n_slots, nullptr);
     CK(cudaEventCreateWithFlags(&b->ev_lk_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_step_done, cudaEventDisableTiming));
     if ((r = make_maps(c, g, b->base, b->n_slots, &b->d_maps))) return r;
     // Scratch ring for the y-filtered product planes: SLAMKLT_BUILD_GROUP frames per build group (default 0 = off).  Measured on
     // B200 (64 KITTI frames, ncu --cache-control none): with groups of 8 and the L2 window the T planes never reach HBM (DRAM
@@ -1336,9 +1356,14 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaStreamSynchronize(c->lk_stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->raw_stream));
+    CK(cudaStreamSynchronize(c->d2h_stream));
     for (auto* v : b->views) delete v;
     if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
-    b->staging.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
+    if (b->ev_step_done) cudaEventDestroy(b->ev_step_done);
+    for (auto e : b->raw_ev) cudaEventDestroy(e);
+    b->staging.release(); b->staging8.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
     b->h_pack.release();
     if (b->d_maps) cudaFree(b->d_maps);
     if (b->ts.base) cudaFree(b->ts.base);
@@ -1360,6 +1385,7 @@ int slamklt_batch_prime(slamklt_ctx* c, slamklt_batch* b, const void* img, int d
     if (r) return r;
     CK(cudaStreamSynchronize(c->stream));
     b->primed = true;
+    b->quiesced = !b->step_pending;
     return 0;
 }
 
@@ -1373,6 +1399,7 @@ int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
+    b->quiesced = false;
     int r = upload_frames(c, b->staging, imgs, dtype, ld, frame_stride_bytes, b->n_frames, b->g.H0, b->g.W0);
     if (r) return r;
     if (n_pts > 0) {
@@ -1390,6 +1417,7 @@ int slamklt_batch_build(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
+    b->quiesced = false;
     return build_frames(c, fs_of(b), 1, b->n_frames, b->g, b->staging.p, b->up_dtype, sigma, mode, nullptr, &b->ts, b->build_group);
 }
 
@@ -1402,6 +1430,7 @@ int slamklt_batch_track(slamklt_ctx* c, slamklt_batch* b, const slamklt_lk_param
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
+    b->quiesced = false;
     LKArgs a{};
     a.A = fs_of(b); a.B = fs_of(b); a.offA = 0; a.offB = 1;
     fill_lk_levels(b->g, &a);
@@ -1433,6 +1462,7 @@ int slamklt_batch_track_cross(slamklt_ctx* c, slamklt_batch* from, slamklt_batch
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, from);
     BATCH_WAIT_LK(c, to);
+    from->quiesced = false; to->quiesced = false;
     LKArgs a{};
     a.A = fs_of(from); a.B = fs_of(to); a.offA = 1; a.offB = 1;
     fill_lk_levels(to->g, &a);
@@ -1463,6 +1493,7 @@ int slamklt_batch_download(slamklt_ctx* c, slamklt_batch* b, double* out_pts, ui
         c->d2h += (out_pts ? n * 16 : 0) + (status ? n : 0);
     }
     CK(cudaStreamSynchronize(c->stream));
+    b->quiesced = !b->step_pending;
     return 0;
 }
 
@@ -1474,39 +1505,35 @@ int slamklt_batch_rotate(slamklt_ctx* c, slamklt_batch* b) {
 }
 
 // Chunked pipeline shared by slamklt_batch_step (host buffers) and slamklt_batch_process (device-resident frames):
-// H2D of chunk k+1 (copy stream) || pyramid build of chunk k (main + side streams) || tracking of chunk k-1 (lk stream)
+// H2D of chunk k+1 (copy streams) || pyramid build of chunk k (main + side streams) || tracking of chunk k-1 (lk stream)
 // || D2H of chunk k-2 (d2h stream).  imgs == nullptr: frames already sit in the batch staging buffer.
+// Nothing here waits for the device: the caller synchronises (slamklt_batch_step_end / slamklt_batch_download).
+//
+// Float64 host frames reach the device through TWO engines at once (round 2): host worker threads repack chunks that hold 8-bit
+// data to one byte per pixel (pack_u8_exact: lossless, the device rebuilds the identical Float64) while the copy engine ships
+// other chunks as plain Float64 -- both pull from host memory concurrently, so the step is bound by the sum of their rates
+// instead of by the slower of "all repacked" / "all plain".  Which chunk goes which way is a greedy schedule over the two
+// measured rates (source bytes per second of the worker pool, bytes per second of the plain copies), refreshed every step.
+enum { UP_PLAIN = 0, UP_PACK = 1, UP_RAW = 2 };
+
+static long long now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
                           const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts,
-                          uint8_t* status, int want_chunks) {
+                          uint8_t* status, int want_chunks, bool throughput = false) {
     int r;
     const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
     const size_t es = dtype_size(dtype), fbytes = (size_t)H * W * es;
     if ((r = b->staging.ensure((size_t)nf * fbytes))) return r;
-    const int chunk = nf >= 2 * want_chunks ? (nf + want_chunks - 1) / want_chunks : nf;
-    const int nchunks = (nf + chunk - 1) / chunk;
-    while ((int)c->pipe_ev.size() < 3 * nchunks + 1) {
-        cudaEvent_t e;
-        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->pipe_ev.push_back(e);
-    }
-    cudaEvent_t* evH2D = c->pipe_ev.data();
-    cudaEvent_t* evBuilt = c->pipe_ev.data() + nchunks;
-    cudaEvent_t* evLK = c->pipe_ev.data() + 2 * nchunks;
-    cudaEvent_t evStart = c->pipe_ev[3 * nchunks];
-    const bool side_lk = !c->prof_on;  // the per-kernel profiler times one serial stream
-    cudaStream_t lks = side_lk ? c->lk_stream : c->stream;
-    // order the side streams after everything already queued on the compute stream (staging / slot reuse)
-    if (b->lk_pending) {  // the previous tracking kernel of THIS batch still reads its slots / points / result buffers
-        CK(cudaStreamWaitEvent(c->stream, b->ev_lk_done, 0));
-        b->lk_pending = false;
-    }
-    CK(cudaEventRecord(evStart, c->stream));
-    CK(cudaStreamWaitEvent(c->copy_stream, evStart, 0));
-    if (side_lk) CK(cudaStreamWaitEvent(c->lk_stream, evStart, 0));
-    // Float64 host frames that hold 8-bit data are shipped as 8 bits per pixel (pack_u8_exact: lossless, the device rebuilds the
-    // identical Float64): host worker threads repack chunk k+1 while the copy engine and the GPU work on chunk k.  The first
-    // pixel that is not an exact k/255 switches the rest of the step back to plain Float64 uploads.
+    const size_t npx = (size_t)H * W;
+    const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
+    // ---- chunks (frame ranges, each built + tracked by its own launches) and how each one's frames reach the device
+    struct Chunk { int f0, n; char how; };
+    std::vector<Chunk> chunks;
+    auto uniform = [&](int want, char how) {
+        const int len = nf >= 2 * want ? (nf + want - 1) / want : nf;
+        for (int f = 0; f < nf; f += len) chunks.push_back(Chunk{f, std::min(len, nf - f), how});
+    };
     bool try_pack = imgs && dtype == SLAMKLT_F64 && ld == H && (size_t)nf * H * W >= (1u << 20) && getenv("SLAMKLT_NO_PACK") == nullptr;
     if (try_pack) {
         if ((r = b->h_pack.ensure((size_t)nf * H * W))) return r;
@@ -1518,26 +1545,140 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
             int want = e ? atoi(e) : std::min(avail, 16);
             c->pool = new HostPool(std::max(want, 1) - 1);
         }
+        // rate of the plain copies of this batch's previous step (its events have completed: the step was waited for)
+        if (!b->raw_meas.empty()) {
+            double ms_sum = 0.0, bytes = 0.0;
+            for (auto& m : b->raw_meas) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, b->raw_ev[2 * m.first], b->raw_ev[2 * m.first + 1]) == cudaSuccess && ms > 0.f) { ms_sum += ms; bytes += (double)m.second; }
+                else cudaGetLastError();
+            }
+            if (ms_sum > 0.0) { const double rate = bytes / (ms_sum * 1e-3); c->raw_Bps = c->raw_Bps > 0 ? 0.5 * (c->raw_Bps + rate) : rate; }
+            b->raw_meas.clear();
+        }
+        // the plain-copy engine only helps when it can read the caller's buffer directly (page-locked memory)
+        cudaPointerAttributes at;
+        bool pinned = cudaPointerGetAttributes(&at, imgs) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        const bool two_engines = pinned && contiguous && nf >= 8 && getenv("SLAMKLT_NO_HYBRID") == nullptr;
+        const char* forced = getenv("SLAMKLT_UPLOAD_PLAN");  // test / experiment knob, e.g. "PRPPRPPR" (P = repacked, R = plain), cycled over the chunks
+        if (two_engines && forced && *forced) {
+            uniform(want_chunks, UP_PACK);
+            const size_t fl = strlen(forced);
+            for (size_t k = 0; k < chunks.size(); ++k) if (forced[k % fl] == 'R' || forced[k % fl] == 'r') chunks[k].how = UP_RAW;
+        } else if (two_engines && throughput) {
+            // Throughput mode (another batch's kernels hide this step's uploads): the first `a` frames travel as plain Float64 on
+            // the copy engine while the workers repack the rest, a chosen so that both finish together:
+            //   a*fb/rw + (nf-a)*fb/8/rw  =  (nf-a)*fb/pk      (the repacked bytes cross the same link)
+            // Few, large chunks: the kernels run on full grids (measured on B200: 8 chunks of 8 frames cost 2.3 ms of GPU time per
+            // step against 1.5 ms for 2 chunks).
+            const double pk = c->pack_Bps > 0 ? c->pack_Bps : 60e9, rw = c->raw_Bps > 0 ? c->raw_Bps : 45e9;
+            const double share = std::max(0.0, (1.0 / pk - 0.125 / rw) / (0.875 / rw + 1.0 / pk));
+            int n_raw = std::min(nf - 1, (int)std::lround(share * nf));
+            if (c->raw_Bps == 0.0 && n_raw == 0) n_raw = 1;  // (first step: get the plain-copy rate measured)
+            // chunks stay in frame order (pair i tracks slot i -> slot i + 1, so frame i - 1 must be built before frame i is
+            // tracked): the plain part first -- its copy starts at once -- then the repacked part
+            if (n_raw > 0) chunks.push_back(Chunk{0, n_raw, UP_RAW});
+            chunks.push_back(Chunk{n_raw, nf - n_raw, UP_PACK});
+        } else {
+            uniform(throughput ? std::min(want_chunks, 2) : want_chunks, UP_PACK);
+        }
+    } else {
+        uniform(want_chunks, UP_PLAIN);
+    }
+    const int nchunks = (int)chunks.size();
+    // Repacked frames sit compactly (1 B/px) at frame_index * npx, plain ones at frame_index * 8 * npx: in one buffer a plain chunk
+    // would overlap the repacked chunks behind it, so a two-engine plan keeps its repacked frames in a buffer of their own.
+    bool any_raw = false;
+    for (const Chunk& ch : chunks) any_raw |= ch.how == UP_RAW;
+    if (any_raw && (r = b->staging8.ensure((size_t)nf * npx))) return r;
+    char* const pk_base = any_raw ? (char*)b->staging8.p : (char*)b->staging.p;
+    while ((int)c->pipe_ev.size() < 3 * nchunks + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_ev.push_back(e);
+    }
+    cudaEvent_t* evH2D = c->pipe_ev.data();
+    cudaEvent_t* evBuilt = c->pipe_ev.data() + nchunks;
+    cudaEvent_t* evLK = c->pipe_ev.data() + 2 * nchunks;
+    cudaEvent_t evStart = c->pipe_ev[3 * nchunks], evPts = c->pipe_ev[3 * nchunks + 1];
+    const bool side_lk = !c->prof_on;  // the per-kernel profiler times one serial stream
+    cudaStream_t lks = side_lk ? c->lk_stream : c->stream;
+    // A batch with nothing in flight (slamklt_batch_step_end / _download / _prime returned) can be written at once: its copies need
+    // not queue behind ANOTHER batch's pyramid builds on the compute stream.  Otherwise order the copy streams after everything
+    // already queued on the compute stream (staging / slot reuse).
+    const bool fresh = b->quiesced;
+    b->quiesced = false;
+    if (b->lk_pending) {  // the previous tracking kernel of THIS batch still reads its slots / points / result buffers
+        CK(cudaStreamWaitEvent(c->stream, b->ev_lk_done, 0));
+        b->lk_pending = false;
+    }
+    if (!fresh) {
+        CK(cudaEventRecord(evStart, c->stream));
+        CK(cudaStreamWaitEvent(c->copy_stream, evStart, 0));
+        CK(cudaStreamWaitEvent(c->raw_stream, evStart, 0));
+        if (side_lk) CK(cudaStreamWaitEvent(c->lk_stream, evStart, 0));
     }
     int n_packed = 0, n_plain = 0;
-    const size_t npx = (size_t)H * W;
     std::atomic<int> pack_bad{0};
+    std::atomic<long long> pack_t1{0};
+    long long pack_t0 = 0;
+    double pack_ns = 0.0, pack_bytes = 0.0;
     // repack chunk k on the workers (asynchronously: the calling thread meanwhile queues the GPU work of the chunk before)
     auto start_pack = [&](int k) {
-        const int f0 = k * chunk, n = std::min(nf, f0 + chunk) - f0;
+        const int f0 = chunks[k].f0, n = chunks[k].n;
         uint8_t* hp = (uint8_t*)b->h_pack.p + (size_t)f0 * npx;
         const int cols = 64, blocks = (W + cols - 1) / cols;
-        c->pool->start(n * blocks, [=, &pack_bad](int item) {
+        pack_t0 = now_ns();
+        pack_t1.store(pack_t0);
+        c->pool->start(n * blocks, [=, &pack_bad, &pack_t1](int item) {
             const int f = item / blocks, x0 = (item - f * blocks) * cols, x1 = std::min(W, x0 + cols);
             const double* sp = (const double*)((const char*)imgs + (size_t)(f0 + f) * frame_stride_bytes) + (size_t)x0 * H;
             if (!pack_u8_exact(sp, hp + (size_t)f * npx + (size_t)x0 * H, (size_t)(x1 - x0) * H)) pack_bad.store(1);
+            const long long t = now_ns();
+            long long seen = pack_t1.load(std::memory_order_relaxed);
+            while (t > seen && !pack_t1.compare_exchange_weak(seen, t, std::memory_order_relaxed)) {}
         });
     };
+    auto next_packed = [&](int after) { for (int k = after + 1; k < nchunks; ++k) if (chunks[k].how == UP_PACK) return k; return -1; };
     struct PoolJoin { HostPool* p; ~PoolJoin() { if (p) p->wait(); } } pool_join{try_pack ? c->pool : nullptr};  // no job outlives this call
-    if (try_pack) start_pack(0);
+    if (try_pack) { const int k0 = next_packed(-1); if (k0 >= 0) start_pack(k0); }
+    // plain copy of chunk k (whole frames as they are) on stream st; timed when it is one of the hybrid plan's copies
+    auto copy_plain = [&](int k, cudaStream_t st, bool timed) -> int {
+        const int f0 = chunks[k].f0, n = chunks[k].n, f1 = f0 + n;
+        char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
+        if (timed) {
+            const int slot = (int)b->raw_meas.size();
+            while ((int)b->raw_ev.size() < 2 * (slot + 1)) { cudaEvent_t e; CK(cudaEventCreate(&e)); b->raw_ev.push_back(e); }
+            CK(cudaEventRecord(b->raw_ev[2 * slot], st));
+            b->raw_meas.emplace_back(slot, (size_t)n * fbytes);
+        }
+        if (contiguous) {
+            CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = f0; f < f1; ++f)
+                CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
+                                     (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, st));
+        }
+        if (timed) CK(cudaEventRecord(b->raw_ev[2 * b->raw_meas.back().first + 1], st));
+        CK(cudaEventRecord(evH2D[k], st));
+        c->h2d += (uint64_t)n * fbytes;
+        return 0;
+    };
+    // the plain copies of the plan are queued a few chunks ahead of the chunk the host is working on: far enough to keep the copy
+    // engine busy while the calling thread helps repacking, near enough that a repacked chunk's small copy is not stuck behind them
+    static const int raw_look = [] { const char* e = getenv("SLAMKLT_RAW_LOOKAHEAD"); return e ? atoi(e) : 3; }();
+    int raw_next = 0;
+    auto queue_raw_upto = [&](int last) -> int {
+        for (; raw_next <= last && raw_next < nchunks; ++raw_next)
+            if (chunks[raw_next].how == UP_RAW) { int rr = copy_plain(raw_next, c->raw_stream, true); if (rr) return rr; }
+        return 0;
+    };
     if (imgs) {
         if (n_pts > 0) {
             CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)nf * n_pts * 16, cudaMemcpyHostToDevice, c->copy_stream));
+            CK(cudaEventRecord(evPts, c->copy_stream));
+            CK(cudaStreamWaitEvent(lks, evPts, 0));  // (chunk 0's frames may travel on the other copy stream)
             c->h2d += (uint64_t)nf * n_pts * 16;
         }
         b->n_pts = n_pts; b->up_ld = ld;
@@ -1554,40 +1695,34 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     a.n_frames = nf;
     if ((r = set_gtab(b->gtab, &a))) return r;
     char* const gtab0 = (char*)a.gtab;
-    const bool contiguous = (ld == H) && (frame_stride_bytes == fbytes || nf == 1);
+    bool any_d2h = false;
     for (int k = 0; k < nchunks; ++k) {
-        const int f0 = k * chunk, f1 = std::min(nf, f0 + chunk), n = f1 - f0;
+        const int f0 = chunks[k].f0, n = chunks[k].n;
         int cd = dtype;                                                         // dtype this chunk reaches the device in
         const char* src = (const char*)b->staging.p + (size_t)f0 * fbytes;
         if (imgs) {
-            bool packed = false;
-            if (try_pack) {
+            if ((r = queue_raw_upto(throughput ? nchunks : k + raw_look))) return r;
+            if (chunks[k].how == UP_PACK) {
                 c->pool->wait();
-                packed = pack_bad.load() == 0;
-                if (!packed) try_pack = false;
-                else {
+                pack_ns += (double)(pack_t1.load() - pack_t0); pack_bytes += (double)n * fbytes;
+                if (pack_bad.load() != 0) {
+                    // not 8-bit data: this chunk and every chunk still planned for repacking travel as plain Float64
+                    for (int j = k; j < nchunks; ++j) if (chunks[j].how == UP_PACK) chunks[j].how = UP_PLAIN;
+                    try_pack = false;
+                } else {
                     const uint8_t* hp = (const uint8_t*)b->h_pack.p + (size_t)f0 * npx;
-                    char* dst = (char*)b->staging.p + (size_t)f0 * npx;
+                    char* dst = pk_base + (size_t)f0 * npx;
                     CK(cudaMemcpyAsync(dst, hp, (size_t)n * npx, cudaMemcpyHostToDevice, c->copy_stream));
+                    CK(cudaEventRecord(evH2D[k], c->copy_stream));
                     c->h2d += (uint64_t)n * npx;
                     cd = SLAMKLT_U8; src = dst;
                     ++n_packed;
-                    if (k + 1 < nchunks) start_pack(k + 1);
+                    const int kn = next_packed(k);
+                    if (kn >= 0) start_pack(kn);
                 }
             }
-            if (!packed) {
-                char* dst = (char*)b->staging.p + (size_t)f0 * fbytes;
-                if (contiguous) {
-                    CK(cudaMemcpyAsync(dst, (const char*)imgs + (size_t)f0 * fbytes, (size_t)n * fbytes, cudaMemcpyHostToDevice, c->copy_stream));
-                } else {
-                    for (int f = f0; f < f1; ++f)
-                        CK(cudaMemcpy2DAsync((char*)b->staging.p + (size_t)f * fbytes, (size_t)H * es, (const char*)imgs + (size_t)f * frame_stride_bytes,
-                                             (size_t)ld * es, (size_t)H * es, W, cudaMemcpyHostToDevice, c->copy_stream));
-                }
-                c->h2d += (uint64_t)n * fbytes;
-                ++n_plain;
-            }
-            CK(cudaEventRecord(evH2D[k], c->copy_stream));
+            if (chunks[k].how == UP_PLAIN) { if ((r = copy_plain(k, c->copy_stream, false))) return r; }
+            if (chunks[k].how != UP_PACK) ++n_plain;
             CK(cudaStreamWaitEvent(c->stream, evH2D[k], 0));
         }
         if ((r = build_frames(c, fs_of(b), 1 + f0, n, b->g, src, cd, sigma, mode, nullptr, &b->ts, b->build_group))) return r;
@@ -1608,20 +1743,25 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
                 CK(cudaMemcpyAsync(out_pts + (size_t)f0 * n_pts * 2, a.out_pts, (size_t)n * n_pts * 16, cudaMemcpyDeviceToHost, c->d2h_stream));
                 CK(cudaMemcpyAsync(status + (size_t)f0 * n_pts, a.status, (size_t)n * n_pts, cudaMemcpyDeviceToHost, c->d2h_stream));
                 c->d2h += (uint64_t)n * n_pts * 17;
+                any_d2h = true;
             }
         }
     }
+    if (pack_ns > 0.0) { const double rate = pack_bytes / (pack_ns * 1e-9); c->pack_Bps = c->pack_Bps > 0 ? 0.5 * (c->pack_Bps + rate) : rate; }
     // what the staging buffer now holds (slamklt_batch_detect reads it): one dtype, or nothing usable after a mixed step
     if (imgs) b->up_dtype = n_plain == 0 ? SLAMKLT_U8 : (n_packed == 0 ? dtype : -1);
     // Only work that touches THIS batch again has to wait for its tracking kernels (see lk_pending above and
     // batch_wait_lk): another batch may build on the compute stream while this one is still being tracked.
     if (n_pts > 0 && side_lk) { CK(cudaEventRecord(b->ev_lk_done, lks)); b->lk_pending = true; }
+    // one event that covers everything queued above: result copies after tracking after builds after uploads
+    if (any_d2h) CK(cudaEventRecord(b->ev_step_done, c->d2h_stream));
+    else if (n_pts > 0) CK(cudaEventRecord(b->ev_step_done, lks));
+    else CK(cudaEventRecord(b->ev_step_done, c->stream));
     return 0;
 }
 
-// Whole step through host buffers: upload + build + track + download + rotate, pipelined in chunks of frames.
-int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
-                       const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
+static int check_step_args(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, const double* pts, int n_pts, int mode,
+                           const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
     if (!c || !b || !imgs) return fail(SLAMKLT_E_INVALID, "NULL argument");
     if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
     if (ld < b->g.H0) return fail(SLAMKLT_E_INVALID, "ld < H");
@@ -1631,18 +1771,59 @@ int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int d
     int r = check_lk(p, b->g.nl, b->g.nl);
     if (r) return r;
     if (!b->primed) return fail(SLAMKLT_E_INVALID, "batch slot 0 was never built (call slamklt_batch_prime)");
+    if (b->step_pending) return fail(SLAMKLT_E_INVALID, "the batch has a step in flight (call slamklt_batch_step_end first)");
+    return 0;
+}
+
+// First half of slamklt_batch_step: queue upload + build + track + download of one step and return without waiting for the
+// device.  imgs, pts_yx, out_pts_yx and status must stay valid (and untouched) until slamklt_batch_step_end.  Several batches
+// of one context may have a step in flight: their copies, builds and tracking kernels overlap (a stream consumer keeps two
+// batches going so that the uploads of one hide behind the kernels of the other).
+static int step_begin(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes, const double* pts,
+                      int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status, bool throughput) {
+    int r = check_step_args(c, b, imgs, dtype, ld, pts, n_pts, mode, p, out_pts, status);
+    if (r) return r;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    // more chunks hide more of the copy but run the kernels on smaller grids: 8 for 8-byte pixels, fewer for light copies
+    static const int forced = [] { const char* e = getenv("SLAMKLT_STEP_CHUNKS"); return e ? atoi(e) : 0; }();
+    int want = dtype == SLAMKLT_F64 ? 8 : (dtype == SLAMKLT_F32 ? 4 : 2);
+    // throughput mode: the caller keeps several batches in flight, so another batch's kernels hide this step's uploads and large
+    // chunks (full grids) win; measured on B200, UInt8 frames: 1.55 ms per step with one chunk against 1.63 with two
+    if (throughput && dtype != SLAMKLT_F64) want = 1;
+    if (forced > 0) want = forced;
+    if ((r = batch_pipeline(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, want, throughput))) return r;
+    b->step_pending = true;
+    return 0;
+}
+
+int slamklt_batch_step_begin(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
+                             const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
+    return step_begin(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, true);
+}
+
+// Second half: wait until the step's results sit in the caller's buffers, then rotate (the last frame becomes slot 0).
+int slamklt_batch_step_end(slamklt_ctx* c, slamklt_batch* b) {
+    if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
+    if (!b->step_pending) return fail(SLAMKLT_E_INVALID, "no step in flight on this batch");
     {
         std::lock_guard<std::mutex> lk(c->mu);
         CK(cudaSetDevice(c->device));
-        // more chunks hide more of the copy but run the kernels on smaller grids: 8 for 8-byte pixels, fewer for light copies
-        const int want = dtype == SLAMKLT_F64 ? 8 : (dtype == SLAMKLT_F32 ? 4 : 2);
-        if ((r = batch_pipeline(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, want))) return r;
-        CK(cudaStreamSynchronize(c->d2h_stream));
-        CK(cudaStreamSynchronize(c->lk_stream));
-        CK(cudaStreamSynchronize(c->copy_stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventSynchronize(b->ev_step_done));
+        b->step_pending = false;
+        b->lk_pending = false;   // ev_step_done was recorded after the last tracking kernel
+        b->quiesced = true;
     }
     return slamklt_batch_rotate(c, b);
+}
+
+// Whole step through host buffers: upload + build + track + download + rotate, pipelined in chunks of frames.
+int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dtype, int ld, size_t frame_stride_bytes,
+                       const double* pts, int n_pts, double sigma, int mode, const slamklt_lk_params* p, double* out_pts, uint8_t* status) {
+    // latency mode: nothing else hides this step's uploads, so it is cut into more chunks that pipeline against each other
+    int r = step_begin(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, false);
+    if (r) return r;
+    return slamklt_batch_step_end(c, b);
 }
 
 // Device-resident step: frames and points were uploaded before (slamklt_batch_upload); build every pyramid and track every
@@ -1666,6 +1847,7 @@ int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out) {
     slamklt_pyr*& v = b->views[slot];
     if (!v) { v = new slamklt_pyr(); v->g = b->g; v->parent = b; v->logical_slot = slot; v->owns = false; }
     v->built = true;
+    b->quiesced = false;  // the view may be handed to calls that queue work on the compute stream
     *out = v;
     return 0;
 }
@@ -1685,6 +1867,7 @@ int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, in
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
+    b->quiesced = false;
     const double* d_img;
     if (b->up_dtype == SLAMKLT_F64) d_img = (const double*)b->staging.p;
     else {

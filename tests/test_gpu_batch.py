@@ -207,3 +207,79 @@ def test_step_repacks_8bit_frames_losslessly_and_falls_back(ctx, monkeypatch):
     o3, s3, sent3, _ = run(m, False)
     o4, s4, sent4, _ = run(m, True)
     assert sent_pack < sent3 < sent4 and np.array_equal(s3, s4) and np.array_equal(np.nan_to_num(o3), np.nan_to_num(o4))
+
+
+def test_step_hybrid_upload_and_two_batches_in_flight(ctx, monkeypatch):
+    """Round 2: (1) page-locked Float64 host frames travel through two engines at once -- host threads repack some chunks to 8
+    bits, the copy engine ships the others as plain Float64 (SLAMKLT_UPLOAD_PLAN forces the split here; by default it follows
+    the two measured rates) -- and the result is bit-identical to the all-plain upload; (2) slamklt_batch_step_begin / _end keep
+    two batches in flight and give what two synchronous steps give; (3) misuse is refused."""
+    H, W, L, NF, NP = 376, 1241, 3, 16, 300
+    fr, _ = synth.make_sequence(2021, NF + 1, H=H, W=W)
+    f64 = synth.to_f64(fr)
+    alg = slamklt.LucasKanade(pyramid_levels=L)
+    pts = np.stack([synth.random_keypoints(500 + i, NP, H, W, border=4.0) for i in range(NF)])
+    pin = slamklt.PinnedArray((NF, W, H), np.float64)
+    pin.array[...] = np.transpose(f64[1:], (0, 2, 1))
+    pin_rev = slamklt.PinnedArray((NF, W, H), np.float64)
+    pin_rev.array[...] = np.transpose(f64[:-1][::-1], (0, 2, 1))
+
+    def run(plan):
+        for k in ("SLAMKLT_NO_PACK", "SLAMKLT_UPLOAD_PLAN", "SLAMKLT_NO_HYBRID"):
+            monkeypatch.delenv(k, raising=False)
+        if plan == "plain":
+            monkeypatch.setenv("SLAMKLT_NO_PACK", "1")
+        elif plan == "packed":
+            monkeypatch.setenv("SLAMKLT_NO_HYBRID", "1")
+        elif plan != "auto":
+            monkeypatch.setenv("SLAMKLT_UPLOAD_PLAN", plan)
+        b = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+        b.prime(f64[0])
+        h0 = ctx.stats()["h2d_bytes"]
+        out, st = b.step(pin.array, pts, alg)
+        sent = ctx.stats()["h2d_bytes"] - h0
+        out2, st2 = b.step(pin_rev.array, pts[::-1], alg)     # a second step on the rotated batch (auto: measured rates now exist)
+        layer = b.slot(0).plane(1, "layer")
+        b.close()
+        return np.nan_to_num(out), st, sent, np.nan_to_num(out2), st2, layer
+
+    ref = run("plain")
+    full = NF * H * W * 8
+    for plan in ("packed", "PRPRPRRP", "RP", "RRRRRRRR", "auto"):
+        got = run(plan)
+        for a, b_ in zip(ref[:2] + ref[3:], got[:2] + got[3:]):
+            assert np.array_equal(a, b_), plan
+        if plan == "packed":
+            assert got[2] < full * 0.2
+        if plan == "PRPRPRRP":
+            assert full * 0.5 < got[2] < full * 0.75       # 4 of 8 chunks plain + 4 packed
+        if plan == "RRRRRRRR":
+            assert got[2] > full
+    for k in ("SLAMKLT_NO_PACK", "SLAMKLT_UPLOAD_PLAN", "SLAMKLT_NO_HYBRID"):
+        monkeypatch.delenv(k, raising=False)
+
+    # two batches in flight
+    bx, by = slamklt.StreamBatch(ctx, H, W, L, NF, NP), slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+    bx.prime(f64[0]); by.prime(f64[NF])
+    bx.step_begin(pin.array, pts, alg)
+    by.step_begin(pin_rev.array, pts[::-1], alg)
+    with pytest.raises(slamklt.SlamKltError):
+        bx.step_begin(pin.array, pts, alg)                 # a step is already in flight on bx
+    ox, sx = bx.step_end()
+    oy, sy = by.step_end()
+    with pytest.raises(slamklt.SlamKltError):
+        bx.step_end()                                      # nothing in flight any more
+    assert np.array_equal(sx, ref[1]) and np.array_equal(np.nan_to_num(ox), ref[0])
+    bs = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+    bs.prime(f64[NF])
+    oy_ref, sy_ref = bs.step(pin_rev.array, pts[::-1], alg)
+    assert np.array_equal(sy, sy_ref) and np.array_equal(np.nan_to_num(oy), np.nan_to_num(oy_ref))
+    # and again on the rotated batches, the other way round
+    by.step_begin(pin.array, pts, alg)
+    bx.step_begin(pin_rev.array, pts[::-1], alg)
+    ox2, sx2 = bx.step_end()
+    oy2, sy2 = by.step_end()
+    assert np.array_equal(sx2, ref[4]) and np.array_equal(np.nan_to_num(ox2), ref[3])
+    for b in (bx, by, bs):
+        b.close()
+    pin.free(); pin_rev.free()
