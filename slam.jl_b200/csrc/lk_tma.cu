@@ -231,18 +231,20 @@ __global__ void __launch_bounds__(128) k_lk_gprep(const LKArgs a, GEntry* __rest
 }
 
 // ---- tracking kernel --------------------------------------------------------------------------------------------------------
+// 10 496 bytes: with the 1 KB the hardware reserves per CTA, twenty one-warp CTAs fit the 227 KB of an SM.  The small members sit in
+// the padding between the target tile and the 128-byte aligned template tiles.
 template <int W2, int PR, int PC>
 struct __align__(128) LKTmaSmem {
     using T = TmaTile<W2, PR, PC>;
     float sT[T::TC][T::TR];
-    __align__(128) float sI[T::AC][T::AR];
-    __align__(128) float2 sG[T::AC][T::AR];
-    __align__(16) float2 sZ[4 * T::AR + 1];  // zeros at every offset j*AR the gradient loads use: patch rows outside the window read here
     __align__(16) double q[2];               // forward result (the backward pass starts from it; the distance gate needs it again)
     int dsave[4];                            // displacement at the start of the current level (optflow! keeps it when the level fails)
     __align__(8) uint64_t barT;
     uint64_t barA;
+    __align__(128) float sI[T::AC][T::AR];
+    __align__(128) float2 sG[T::AC][T::AR];
 };
+static_assert(sizeof(LKTmaSmem<19, 3, 5>) == 10496, "shared memory budget of the tracking kernel (20 CTAs per SM)");
 
 // Position bookkeeping.  The reference keeps d and c as Float64 vectors; the kernel keeps the current estimate of a level as an
 // integer pixel plus an fp32 fraction in [0, 1): floor / ceil / bilinear weights / tile offsets then need no Float64 arithmetic
@@ -439,12 +441,12 @@ retry:
                     const float2* const tGp = &sm.sG[pj0][pi0s] + skip;
 #pragma unroll
                     for (int i = 0; i < PR; ++i) {
-                        const float2* const gr = (pi0 + i < nrows) ? tGp + i : &sm.sZ[0];
+                        const bool in_win = pi0 + i < nrows;  // patch rows beyond the window carry real data: their gradients are zeroed
 #pragma unroll
                         for (int q = 0; q < NQT; ++q) tIp[i][q] = make_float2(tI[(2 * q) * AR + i], tI[(2 * q + 1) * AR + i]);
                         tIl[i] = tI[(PC - 1) * AR + i];
 #pragma unroll
-                        for (int j = 0; j < PC; ++j) tG[i][j] = gr[j * AR];
+                        for (int j = 0; j < PC; ++j) { const float2 gv = tGp[j * AR + i]; tG[i][j] = in_win ? gv : make_float2(0.f, 0.f); }
                     }
                     if (ncols < T::GC) {  // clipped (or smaller) window: gradient columns beyond it carry real data, zero them
 #pragma unroll
@@ -636,7 +638,7 @@ retry:
 // (LKT_TR=24, 9.5 KB of shared memory) reaches 21-24 CTAs but re-stages so often that it loses: 0.976 ms at 16, 0.885 ms at 24.
 // The optflow! / optical_flow_matching! instantiations carry more state and keep the 128-register bound.
 #ifndef LKT_MINB
-#define LKT_MINB 18
+#define LKT_MINB 20
 #endif
 
 // Kernel: one warp (= one CTA) per keypoint; the grid is persistent (one-warp CTAs filling every SM, or one per keypoint when there
@@ -648,7 +650,6 @@ __global__ void __launch_bounds__(32, MODE == 1 ? LKT_MINB : 16) k_lk_tma(const 
     const int lane = threadIdx.x;
     // the gradient tile's columns beyond the box are never written by the TMA, nor is the zero row: clear them once
     for (int i = lane; i < TmaTile<W2, PR, PC>::AC * TmaTile<W2, PR, PC>::AR; i += 32) (&sm.sG[0][0])[i] = make_float2(0.f, 0.f);
-    for (int i = lane; i < 4 * TmaTile<W2, PR, PC>::AR + 1; i += 32) sm.sZ[i] = make_float2(0.f, 0.f);
     if (lane == 0) {
         mbar_init1(&sm.barT);
         mbar_init1(&sm.barA);
