@@ -271,6 +271,7 @@ struct slamklt_ctx {
     HostBuf h_out, h_status, h_misc;
     HostPool* pool = nullptr;  // created on first use
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
+    std::map<long long, double*> ytab_cache;                 // (first mask-blur tap bits) -> device table of tap-subset sums (detect)
     // per-kernel profiling (off by default)
     bool prof_on = false;
     Hook hook{nullptr, nullptr};
@@ -512,6 +513,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     cudaStream_t all[] = {c->stream, c->lk_stream, c->copy_stream, c->raw_stream, c->d2h_stream, c->pyr_streams.b, c->pyr_streams.c};
     for (cudaStream_t st : all) if (st) cudaStreamSynchronize(st);
     for (auto& kv : c->norm_cache) cudaFree(kv.second);
+    for (auto& kv : c->ytab_cache) cudaFree(kv.second);
     DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match, &c->gtab};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
@@ -1255,6 +1257,27 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_fra
         CK(cudaMemcpyAsync(c->cur.p, cur_host, (size_t)n_frames * a.n_cur * 16, cudaMemcpyHostToDevice, c->stream));
         c->h2d += (uint64_t)n_frames * a.n_cur * 16;
         a.cur = (const double*)c->cur.p;
+    }
+    if (a.n_cur > 0 && a.hw == 6) {
+        // table of the 2^13 tap-subset sums of the mask blur's y pass (detect.cu, k_detect_cells2): entry `pat` adds the taps whose
+        // bit is set in tap order with the same Float64 additions the tap loop performs (adding 0.0 for a clear bit changes nothing)
+        long long key;
+        std::memcpy(&key, &a.kw[0], sizeof(key));
+        auto it = c->ytab_cache.find(key);
+        if (it == c->ytab_cache.end()) {
+            std::vector<double> tab(1u << 13);
+            for (unsigned pat = 0; pat < (1u << 13); ++pat) {
+                double acc = 0.0;
+                for (int t = 0; t < 13; ++t) acc += ((pat >> t) & 1u) ? a.kw[t] : 0.0;
+                tab[pat] = acc;
+            }
+            double* d = nullptr;
+            CK(cudaMalloc(&d, tab.size() * sizeof(double)));
+            CK(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            it = c->ytab_cache.emplace(key, d).first;
+        }
+        a.ytab = it->second;
     }
     a.cell_out = (int64_t*)c->cell_out.p; a.cell_cnt = (int*)c->cell_cnt.p;
     a.out = (int64_t*)c->det_out.p; a.n_out = (int*)c->det_n.p;

@@ -99,6 +99,7 @@ struct DetArgs {
     int radius, grid_h, grid_w, cs, k_cell, hw, slots, pad_;
     double min_resp;
     double kw[33];      // 1-D mask blur weights, length 2*hw+1
+    const double* ytab; // hw == 6 only: the 2^13 sums of tap subsets (bit t set = tap t included), added in tap order (device)
     int64_t* cell_out;  // [frame][cell][slots][2]
     int* cell_cnt;      // [frame][cell]
     int64_t* out;       // [frame][cap][2]
@@ -201,6 +202,7 @@ size_t lk_tma_level_bytes();
 int lk_tma_encode(const PyrGeom& g, float* base, int n_slots, void* host_out, char* err, size_t errcap);
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);
+size_t detect2_smem_bytes(int cs, int hw);
 
 void iir_design(double sigma, double a[3], double* scale, double M[9]);
 void iir_dev(double sigma, int K, int KR, IirDev* out);

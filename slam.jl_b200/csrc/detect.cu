@@ -6,6 +6,8 @@
 // One CTA per 35x35 cell keeps the whole cell in shared memory.  The path is Float64 end to end and this file
 // is compiled with -fmad=false so that responses are bit-identical to the reference arithmetic order: keypoint
 // sets must be identical except for exact score ties, and near-ties must not flip either.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sk {
@@ -453,6 +455,369 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
     if (tid == 0) *cnt_out = n_sel;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Register-tiled variant (round 2).  Same arithmetic, same operation order, same outputs as k_detect_cells; what changes is how
+// the work is cut.  Every stencil phase walks STRIPS of DET_RS pixels with a sliding window in registers (a new row costs three
+// shared-memory loads per plane instead of nine), the replicate border of the cell is a clamp on the neighbour column / row
+// instead of halo-fill passes with their barriers, the 13-tap y pass of the binary mask is one load from a table of the 2^13
+// possible tap-subset sums (built on the host with the same sequential Float64 additions), the "all zero / all ones" row words
+// come from 13 shifts-and-ANDs per column plus a ballot transpose instead of one shared-memory atomic per pixel, and the
+// current points are rasterised in chunks of MAX_NEAR so that no cell ever needs a slow path.
+// Covers: no mask, or a 13-tap mask blur (sigma_mask = 3, the reference's default) with cell_size + 12 <= 64.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int DET_RS = 5;
+constexpr int DET2_HW = 6, DET2_NT = 2 * DET2_HW + 1;
+
+struct Det2Smem { size_t oImg, oG, oTmp, oNear, oCandR, oCandI, oMaskW, oMisc, oBits, total; };
+__host__ __device__ inline Det2Smem det2_smem_plan(int cs, int hw) {
+    const size_t P = cs + 2, pad = P * P, rw = cs + 2 * hw;
+    const size_t nc = (size_t)((cs + 1) / 2) * ((cs + 1) / 2);
+    const size_t nstrips = (size_t)cs * ((cs + DET_RS - 1) / DET_RS);
+    Det2Smem m;
+    m.oImg = 0;                                   // padded plane: image * mask, later the response (its halo is -inf)
+    m.oG = pad * 8;                               // three padded product planes (halo unused: neighbours are clamped)
+    const size_t endG = m.oG + 3 * pad * 8;
+    m.oTmp = m.oG;                                // mask phase: y-filtered mask, cs x rw doubles ...
+    m.oNear = m.oTmp + (size_t)cs * rw * 8;       // ... and the chunk of nearby current points
+    const size_t endMask = m.oNear + 2 * (size_t)MAX_NEAR * 4;
+    m.oCandR = m.oG;                              // after the response pass the product planes are dead: candidates ...
+    m.oCandI = m.oCandR + nc * 8;
+    m.oMaskW = m.oCandI + nc * 4;                 // ... and the per-strip maxima masks
+    const size_t endC = m.oMaskW + nstrips * 4;
+    size_t end = endG > endMask ? endG : endMask;
+    if (endC > end) end = endC;
+    m.oMisc = (end + 15) & ~(size_t)15;
+    m.oBits = m.oMisc + 64 * 4;                   // five bit planes of 64 words: column mask, F, Z (per column), full, zero (per row)
+    m.total = m.oBits + 5 * 64 * 8;
+    return m;
+}
+size_t detect2_smem_bytes(int cs, int hw) { return det2_smem_plan(cs, hw).total; }
+
+// CS: the cell size as a compile-time constant (plane pitch and offsets become immediates), or 0 = taken from the arguments
+#ifndef DET2_MINB
+#define DET2_MINB 4
+#endif
+template <bool MASKED, int CS>
+__global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RS = DET_RS, hw = MASKED ? DET2_HW : 0, nt = DET2_NT;
+    const int cs = CS ? CS : a.cs;
+    const int cell_id = blockIdx.x, f = blockIdx.y;
+    const int gy = cell_id / a.grid_w, gx = cell_id % a.grid_w;
+    const int H = a.H, W = a.W;
+    const int y0 = gy * cs, x0 = gx * cs;
+    const int y1 = min((gy + 1) * cs, H), x1 = min((gx + 1) * cs, W);
+    const int h = y1 - y0, w = x1 - x0;
+    int* cnt_out = a.cell_cnt + (size_t)f * gridDim.x + cell_id;
+    if (h <= 0 || w <= 0) { if (threadIdx.x == 0) *cnt_out = 0; return; }
+
+    const int P = cs + 2;
+    const size_t pad = (size_t)P * P;
+    const Det2Smem sm = det2_smem_plan(cs, hw);
+    double* s_img = (double*)(smem_raw + sm.oImg);
+    double* s_R = s_img;
+    double* s_gyy = (double*)(smem_raw + sm.oG);
+    double* s_gyx = s_gyy + pad;
+    double* s_gxx = s_gyx + pad;
+    double* s_tmp = (double*)(smem_raw + sm.oTmp);
+    int* s_near = (int*)(smem_raw + sm.oNear);
+    double* s_candr = (double*)(smem_raw + sm.oCandR);
+    int* s_candi = (int*)(smem_raw + sm.oCandI);
+    unsigned* s_maskw = (unsigned*)(smem_raw + sm.oMaskW);
+    int* s_misc = (int*)(smem_raw + sm.oMisc);
+
+    const double* img = a.img + (size_t)f * H * W;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const DivH dh(h), dw(w);
+    const int npx = h * w;
+
+    // halo of the response plane = -inf, so that out-of-cell neighbours never block a maximum.  The plane shares its bytes with
+    // the image tile, whose halo nobody reads (neighbours are clamped), so the ring can be written right away.
+    for (int t = tid; t < 2 * (w + 2) + 2 * h; t += DET_THREADS) {
+        int yy, xx;
+        if (t < w + 2) { yy = 0; xx = t; }
+        else if (t < 2 * (w + 2)) { yy = h + 1; xx = t - (w + 2); }
+        else if (t < 2 * (w + 2) + h) { yy = t - 2 * (w + 2) + 1; xx = 0; }
+        else { yy = t - 2 * (w + 2) - h + 1; xx = w + 1; }
+        s_R[yy + xx * P] = -__longlong_as_double(0x7ff0000000000000LL);
+    }
+
+    // ---- image * mask (extractor.jl:66-71, 116-122) into the padded tile ---------------------------------------------------
+    if (MASKED) {
+        unsigned long long* s_col = (unsigned long long*)(smem_raw + sm.oBits);
+        unsigned long long* s_F = s_col + 64;
+        unsigned long long* s_Z = s_F + 64;
+        unsigned long long* s_full = s_Z + 64;
+        unsigned long long* s_zero = s_full + 64;
+        const double* cur = a.cur + (size_t)f * a.n_cur * 2;
+        const int rh = h + 2 * hw, rw = w + 2 * hw;
+        const int r2 = a.radius * a.radius;
+        const int reach = a.radius + hw;
+        const unsigned long long allrows = rh == 64 ? ~0ull : ((1ull << rh) - 1ull);
+        for (int i = tid; i < 64; i += DET_THREADS) { s_col[i] = allrows; s_F[i] = 0ull; s_Z[i] = 0ull; }
+        const int ry0 = y0 - hw, rx0 = x0 - hw;  // image row / column (0-based) of region row / column 0
+        const int ncolsd = 2 * a.radius + 1;
+        for (int k0 = 0; k0 < a.n_cur; k0 += MAX_NEAR) {
+            if (tid == 0) s_misc[0] = 0;
+            __syncthreads();
+            const int k1 = min(a.n_cur, k0 + MAX_NEAR);
+            for (int k = k0 + tid; k < k1; k += DET_THREADS) {
+                const int cy = (int)rint(cur[2 * k]), cx = (int)rint(cur[2 * k + 1]);  // Julia round(): ties to even; 1-based
+                if (cy >= y0 + 1 - reach && cy <= y1 + reach && cx >= x0 + 1 - reach && cx <= x1 + reach) {
+                    const int slot = atomicAdd(&s_misc[0], 1);
+                    s_near[2 * slot] = cy; s_near[2 * slot + 1] = cx;
+                }
+            }
+            __syncthreads();
+            const int n_near = s_misc[0];
+            // discs column by column: one atomicAnd clears a column's rows (get_mask + ImageDraw circle)
+            for (int it = tid; it < n_near * ncolsd; it += DET_THREADS) {
+                const int k = it / ncolsd, dx = it - k * ncolsd - a.radius;
+                const int X = s_near[2 * k + 1] - 1 + dx;  // 0-based image column
+                const int xx = X - rx0;
+                if (X < 0 || X >= W || xx < 0 || xx >= rw) continue;
+                const int rem = r2 - dx * dx;
+                int sy = (int)sqrtf((float)rem);
+                while (sy * sy > rem) --sy;
+                while ((sy + 1) * (sy + 1) <= rem) ++sy;
+                if (sy * sy == rem && !in_disc(sy, dx, a.radius)) --sy;  // only a lattice point ON the circle needs the Float64 test
+                if (sy < 0) continue;
+                const int Yc = s_near[2 * k] - 1;
+                const int ra = max(max(Yc - sy, 0) - ry0, 0), rb = min(min(Yc + sy, H - 1) - ry0, rh - 1);
+                if (ra > rb) continue;
+                const int len = rb - ra + 1;
+                const unsigned long long bits = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << ra;
+                atomicAnd(&s_col[xx], ~bits);
+            }
+            __syncthreads();
+        }
+        if (a.n_cur <= 0) __syncthreads();
+        // replicate border of the full-image mask: rows above / below the image repeat the first / last image row ...
+        const int top = max(0, -ry0), bot = min(rh, H - ry0);  // region rows [top, bot) lie in the image
+        const int left = max(0, -rx0), right = min(rw, W - rx0);
+        for (int xx = tid + left; xx < right; xx += DET_THREADS) {
+            unsigned long long wv = s_col[xx];
+            if (top > 0) {
+                const unsigned long long lowm = (1ull << top) - 1ull;
+                wv = ((wv >> top) & 1ull) ? (wv | lowm) : (wv & ~lowm);
+            }
+            if (bot < rh) {
+                const unsigned long long him = allrows & ~((1ull << bot) - 1ull);
+                wv = ((wv >> (bot - 1)) & 1ull) ? (wv | him) : (wv & ~him);
+            }
+            s_col[xx] = wv;
+        }
+        __syncthreads();
+        // ... and columns left / right of the image repeat the first / last image column
+        if (left > 0 || right < rw) {
+            for (int xx = tid; xx < rw; xx += DET_THREADS) {
+                if (xx < left) s_col[xx] = s_col[left];
+                else if (xx >= right) s_col[xx] = s_col[right - 1];
+            }
+            __syncthreads();
+        }
+        // per column: F bit y = rows y .. y+12 all ones, Z bit y = all zeros; then transposed into row words by ballots
+        for (int xx = tid; xx < rw; xx += DET_THREADS) {
+            const unsigned long long c = s_col[xx], nc = ~c;
+            unsigned long long fw = c, zw = nc;
+#pragma unroll
+            for (int t = 1; t < nt; ++t) { fw &= c >> t; zw &= nc >> t; }
+            s_F[xx] = fw; s_Z[xx] = zw;
+        }
+        __syncthreads();
+        for (int y = wid; y < h; y += DET_THREADS / 32) {
+            const unsigned f0 = __ballot_sync(FULL, (s_F[lane] >> y) & 1ull), f1 = __ballot_sync(FULL, (s_F[lane + 32] >> y) & 1ull);
+            const unsigned z0 = __ballot_sync(FULL, (s_Z[lane] >> y) & 1ull), z1 = __ballot_sync(FULL, (s_Z[lane + 32] >> y) & 1ull);
+            if (lane == 0) { s_full[y] = (unsigned long long)f0 | ((unsigned long long)f1 << 32); s_zero[y] = (unsigned long long)z0 | ((unsigned long long)z1 << 32); }
+        }
+        // y pass -> s_tmp[rw][h]: the sum of the taps whose mask bit is set, taken from the table of all 2^13 subsets
+        const unsigned pmask = (1u << nt) - 1u;
+        for (int i = tid; i < h * rw; i += DET_THREADS) {
+            int y, xx;
+            dh.split(i, y, xx);
+            s_tmp[i] = __ldg(a.ytab + ((unsigned)(s_col[xx] >> y) & pmask));
+        }
+        const double sall = __ldg(a.ytab + pmask);
+        double call = 0.0;
+#pragma unroll
+        for (int t = 0; t < nt; ++t) call += a.kw[t] * sall;
+        __syncthreads();
+        // x pass on strips of RS pixels along x (lanes = consecutive rows); the 13-tap windows of a strip share their loads
+        const int nxs = (w + RS - 1) / RS;
+        for (int s = tid; s < h * nxs; s += DET_THREADS) {
+            int y, xs;
+            dh.split(s, y, xs);
+            const int xa = xs * RS, nx = min(RS, w - xa);
+            const unsigned wmask = (1u << (nx + nt - 1)) - 1u;
+            const bool allz = ((unsigned)(s_zero[y] >> xa) & wmask) == wmask;   // (bits of Z / F beyond rw are zero)
+            const bool allf = ((unsigned)(s_full[y] >> xa) & wmask) == wmask;
+            const double* ip = img + (size_t)(y0 + y) + (size_t)(x0 + xa) * H;
+            double* op = s_img + (y + 1) + (xa + 1) * P;
+            if (allz || allf) {  // every 13 x 13 window of the strip is all zeros / all ones
+                const double acc = allz ? 0.0 : call;
+#pragma unroll
+                for (int j = 0; j < RS; ++j)
+                    if (j < nx) op[j * P] = ip[(size_t)j * H] * acc;
+            } else {
+                const double* tp = s_tmp + y + xa * h;
+                double v[RS + nt - 1];
+#pragma unroll
+                for (int t = 0; t < RS + nt - 1; ++t) v[t] = (t < nx + nt - 1) ? tp[t * h] : 0.0;
+#pragma unroll
+                for (int j = 0; j < RS; ++j) {
+                    if (j < nx) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int t = 0; t < nt; ++t) acc += a.kw[t] * v[j + t];
+                        op[j * P] = ip[(size_t)j * H] * acc;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < npx; i += DET_THREADS) {
+            int y, x;
+            dh.split(i, y, x);
+            s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H];
+        }
+    }
+    __syncthreads();
+
+    // ---- strips along y: strip s = seg * w + x covers rows [seg * RS, seg * RS + RS) of column x (lanes = consecutive columns) ----
+    const int nseg = (h + RS - 1) / RS;
+    const int nstrips = w * nseg;
+    const double k9 = 1.0 / 9.0;  // the 3x3 mean is imfilter with a (1/9)-valued kernel: products accumulated tap by tap
+    // Sobel / 8 and the three products (Images.shi_tomasi on the cell sub-image: replicate border at the cell edge = clamped neighbours)
+    for (int s = tid; s < nstrips; s += DET_THREADS) {
+        int x, seg;
+        dw.split(s, x, seg);
+        const int ys = seg * RS, ye = min(ys + RS, h);
+        const double* cz = s_img + 1 + (x + 1) * P;
+        const double* cm = s_img + 1 + (max(x - 1, 0) + 1) * P;
+        const double* cp = s_img + 1 + (min(x + 1, w - 1) + 1) * P;
+        const int yp = max(ys - 1, 0);
+        double a_m = cm[yp], a_z = cz[yp], a_p = cp[yp];   // row y-1 of columns x-1, x, x+1
+        double b_m = cm[ys], b_z = cz[ys], b_p = cp[ys];   // row y
+        // rows past the end of a short last strip are computed on clamped (valid) inputs and simply not stored: the body has no
+        // branch, so the sliding window is renamed by the unroller instead of moved
+        double* const og = s_gyy + (x + 1) * P + 1 + ys;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int y = ys + r;
+            const int yn = min(y + 1, h - 1);
+            const double c_m = cm[yn], c_z = cz[yn], c_p = cp[yn];  // row y+1
+            const double g_y = ((c_m - a_m) + 2.0 * (c_z - a_z) + (c_p - a_p)) / 8.0;
+            const double g_x = ((a_p - a_m) + 2.0 * (b_p - b_m) + (c_p - c_m)) / 8.0;
+            if (y < ye) { og[r] = k9 * (g_y * g_y); og[r + pad] = k9 * (g_y * g_x); og[r + 2 * pad] = k9 * (g_x * g_x); }
+            a_m = b_m; a_z = b_z; a_p = b_p;
+            b_m = c_m; b_z = c_z; b_p = c_p;
+        }
+    }
+    __syncthreads();
+    // 3x3 sums (column outer, row inner, like the reference's tap order) and the smaller eigenvalue
+    for (int s = tid; s < nstrips; s += DET_THREADS) {
+        int x, seg;
+        dw.split(s, x, seg);
+        const int ys = seg * RS, ye = min(ys + RS, h);
+        const double* const pc[3] = {s_gyy + 1 + (max(x - 1, 0) + 1) * P, s_gyy + 1 + (x + 1) * P, s_gyy + 1 + (min(x + 1, w - 1) + 1) * P};
+        double A[3][3], B[3][3], C[3][3];  // [column][row slot]: rows y-1, y, y+1 of gyy, gyx, gxx
+        const int yp = max(ys - 1, 0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            A[c][0] = pc[c][yp]; B[c][0] = pc[c][yp + pad]; C[c][0] = pc[c][yp + 2 * pad];
+            A[c][1] = pc[c][ys]; B[c][1] = pc[c][ys + pad]; C[c][1] = pc[c][ys + 2 * pad];
+        }
+        double* const orow = s_R + (x + 1) * P + 1 + ys;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int y = ys + r;
+            const int yn = min(y + 1, h - 1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { A[c][2] = pc[c][yn]; B[c][2] = pc[c][yn + pad]; C[c][2] = pc[c][yn + 2 * pad]; }
+            double sa = 0.0, sb = 0.0, sc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { sa += A[c][q]; sb += B[c][q]; sc += C[c][q]; }
+            const double resp = ((sa + sc) - sqrt((sa - sc) * (sa - sc) + 4.0 * sb * sb)) / 2.0;
+            if (y < ye) orow[r] = resp;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { A[c][0] = A[c][1]; B[c][0] = B[c][1]; C[c][0] = C[c][1]; A[c][1] = A[c][2]; B[c][1] = B[c][2]; C[c][1] = C[c][2]; }
+        }
+    }
+    __syncthreads();
+    // ---- strict 3x3 local maxima (findlocalmaxima): one 5-bit word per strip, stored in column-major strip order ----------------
+    for (int s = tid; s < nstrips; s += DET_THREADS) {
+        int x, seg;
+        dw.split(s, x, seg);
+        const int ys = seg * RS, ye = min(ys + RS, h);
+        const double* cz = s_R + 1 + (x + 1) * P;
+        const double* cm = cz - P;
+        const double* cp = cz + P;
+        double a_m = cm[ys - 1], a_z = cz[ys - 1], a_p = cp[ys - 1];
+        double b_m = cm[ys], b_z = cz[ys], b_p = cp[ys];
+        unsigned bits = 0;
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int yn = min(ys + r + 1, h);  // (row h is the halo)
+            const double c_m = cm[yn], c_z = cz[yn], c_p = cp[yn];
+            const double v = b_z;
+            const int ismax = (a_m < v) & (b_m < v) & (c_m < v) & (a_z < v) & (c_z < v) & (a_p < v) & (b_p < v) & (c_p < v);
+            bits |= (unsigned)ismax << r;
+            a_m = b_m; a_z = b_z; a_p = b_p; b_m = c_m; b_z = c_z; b_p = c_p;
+        }
+        s_maskw[x * nseg + seg] = bits & ((1u << (ye - ys)) - 1u);
+    }
+    __syncthreads();
+    int n_cand = 0;
+    for (int base = 0; base < nstrips; base += DET_THREADS) {
+        const int t = base + tid;
+        const unsigned m = t < nstrips ? s_maskw[t] : 0u;
+        int tot;
+        int pos = n_cand + block_excl_scan(__popc(m), s_misc + 1, tot);
+        if (m) {
+            const int x = t / nseg, seg = t - x * nseg;
+#pragma unroll
+            for (int r = 0; r < RS; ++r)
+                if (m >> r & 1u) {
+                    const int y = seg * RS + r;
+                    s_candr[pos] = s_R[(y + 1) + (x + 1) * P];
+                    s_candi[pos] = y + x * h;
+                    ++pos;
+                }
+        }
+        n_cand += tot;
+    }
+    __syncthreads();
+
+    // ---- top-k by response, stable (sortperm with lt = >), threshold, emit in column-major order ----
+    int64_t* out = a.cell_out + ((size_t)f * gridDim.x + cell_id) * a.slots * 2;
+    int n_sel = 0;
+    for (int base = 0; base < n_cand; base += DET_THREADS) {
+        const int i = base + tid;
+        int sel = 0;
+        if (i < n_cand) {
+            const double r = s_candr[i];
+            int rank = 0;
+            for (int j = 0; j < n_cand; ++j) {
+                const double rj = s_candr[j];
+                rank += (rj > r) || (rj == r && j < i);
+            }
+            sel = (rank < a.k_cell) && !(r < a.min_resp);
+        }
+        int tot;
+        const int pos = block_excl_scan(sel, s_misc + 1, tot);
+        if (sel && n_sel + pos < a.slots) {
+            int y, x;
+            dh.split(s_candi[i], y, x);
+            out[2 * (n_sel + pos)] = (int64_t)y + 1 + y0;
+            out[2 * (n_sel + pos) + 1] = (int64_t)x + 1 + x0;
+        }
+        n_sel += tot;
+    }
+    if (tid == 0) *cnt_out = n_sel;
+}
+
 // cells are visited y-outer, x-inner (extractor.jl:81); one CTA per frame concatenates the cell lists
 __global__ void __launch_bounds__(DET_THREADS) k_detect_compact(DetArgs a, int n_cells) {
     __shared__ int s_warp[DET_THREADS / 32 + 1];
@@ -479,12 +844,34 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_compact(DetArgs a, int n
     if (threadIdx.x == 0) a.n_out[f] = s_base;
 }
 
+// shapes the register-tiled kernel covers (SLAMKLT_DETECT_V1=1 forces the first kernel: A/B timing)
+bool detect2_supported(const DetArgs& a) {
+    static const bool v1 = getenv("SLAMKLT_DETECT_V1") != nullptr;
+    if (v1) return false;
+    if (a.n_cur <= 0) return true;
+    return a.hw == DET2_HW && a.cs + 2 * DET2_HW <= 64 && a.ytab != nullptr;
+}
+
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk) {
     const int n_cells = a.grid_h * a.grid_w;
-    const size_t smem = detect_smem_bytes(a.cs, a.hw);
-    cudaFuncSetAttribute(k_detect_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(n_cells, a.n_frames);
     mark(hk, "k_detect_cells");
+    if (detect2_supported(a)) {
+        const bool masked = a.n_cur > 0;
+        const size_t smem = detect2_smem_bytes(a.cs, masked ? DET2_HW : 0);
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, DET_THREADS, smem, s>>>(a);
+        };
+        // the reference's cell size (35) gets the instantiation with compile-time plane offsets
+        if (masked) { if (a.cs == 35) go(k_detect_cells2<true, 35>); else go(k_detect_cells2<true, 0>); }
+        else { if (a.cs == 35) go(k_detect_cells2<false, 35>); else go(k_detect_cells2<false, 0>); }
+        mark(hk, "k_detect_compact");
+        k_detect_compact<<<a.n_frames, DET_THREADS, 0, s>>>(a, n_cells);
+        return 2;
+    }
+    const size_t smem = detect_smem_bytes(a.cs, a.hw);
+    cudaFuncSetAttribute(k_detect_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_detect_cells<<<grid, DET_THREADS, smem, s>>>(a);
     mark(hk, "k_detect_compact");
     k_detect_compact<<<a.n_frames, DET_THREADS, 0, s>>>(a, n_cells);

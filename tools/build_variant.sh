@@ -10,6 +10,7 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 for f in lk_tma lk_patch pyramid api lk; do
   $NV $flags -Xptxas -v -c $f.cu -o variants/obj_$name/$f.o 2> variants/obj_$name/$f.log &
 done
+$NV $flags -fmad=false -Xptxas -v -c detect.cu -o variants/obj_$name/detect.o 2> variants/obj_$name/detect.log &
 wait
-$NV -shared -o variants/libslamklt_$name.so variants/obj_$name/*.o detect.o match.o brief.o host_pack.o -Xlinker --exclude-libs,ALL
+$NV -shared -o variants/libslamklt_$name.so variants/obj_$name/*.o match.o brief.o host_pack.o -Xlinker --exclude-libs,ALL
 grep -E "Used|spill" variants/obj_$name/lk_tma.log | head -4
