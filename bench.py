@@ -445,7 +445,7 @@ def main():
     outs2 = slamklt.PinnedArray((NF, N_PTS), np.uint8)
     pinned += [outp2, outs2]
     results = [(outp, outs), (outp2, outs2)]
-    simple = rbatch is None and not cfg["detect"]
+    simple = rbatch is None   # mono configs go through slamklt_batch_step (stereo configs pair two batches call by call)
 
     def e2e_loop(seq, rseq, in_flight=2):
         """seq: [(frames, pts), (frames, pts)] alternating host buffers (palindrome); returns seconds for args.steps steps.
@@ -460,6 +460,8 @@ def main():
             fr, pt = seq[i % 2]
             if simple:
                 batch.step(fr.array, pt.array, alg, MAX_DIST, out_pts=outp.array, status=outs.array)   # one pipelined C call
+                if cfg["detect"]:
+                    batch.detect(ext, det_cur)
                 return
             batch.upload(fr.array, pt.array)
             batch.process(alg, MAX_DIST)
@@ -483,11 +485,16 @@ def main():
                 for i in range(n):
                     one(i)
                 return
+            def end(i):
+                pair[i % 2].step_end()
+                if cfg["detect"]:
+                    pair[i % 2].detect(ext, det_cur)    # re-extraction on the frames of the step just finished (synchronous)
+
             begin(0)
             for i in range(1, n):
                 begin(i)
-                pair[(i - 1) % 2].step_end()
-            pair[(n - 1) % 2].step_end()
+                end(i - 1)
+            end(n - 1)
 
         run(4)
         barrier()

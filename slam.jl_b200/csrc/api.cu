@@ -267,7 +267,7 @@ struct slamklt_ctx {
     unsigned long long* d_counters = nullptr;  // [0..1] executed window-iterations / iterations, then the work-counter ring
     unsigned work_idx = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
-    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, cur, match, gtab;
+    DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, det_bin, cur, match, gtab;
     HostBuf h_out, h_status, h_misc;
     HostPool* pool = nullptr;  // created on first use
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
@@ -322,6 +322,8 @@ struct slamklt_batch {
     bool lk_pending = false;
     cudaEvent_t ev_step_done = nullptr;  // everything slamklt_batch_step_begin queued, result copies included
     bool step_pending = false;
+    struct UpChunk { int f0, n, dtype; const void* ptr; };
+    std::vector<UpChunk> up_chunks;      // up_dtype == -2 (a step that mixed repacked and plain chunks): where each chunk's frames sit
     bool quiesced = false;               // nothing of this batch is in flight on any stream (set by the calls that wait for it)
     std::vector<cudaEvent_t> raw_ev;     // timing events around the plain Float64 chunk copies of the last step (2 per chunk)
     std::vector<std::pair<int, size_t>> raw_meas;  // (chunk, bytes) of those copies: read back at the next step
@@ -514,7 +516,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     for (cudaStream_t st : all) if (st) cudaStreamSynchronize(st);
     for (auto& kv : c->norm_cache) cudaFree(kv.second);
     for (auto& kv : c->ytab_cache) cudaFree(kv.second);
-    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->cur, &c->match, &c->gtab};
+    DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->det_bin, &c->cur, &c->match, &c->gtab};
     for (DevBuf* b : bufs) b->release();
     c->h_out.release(); c->h_status.release(); c->h_misc.release();
     delete c->pool;
@@ -1244,10 +1246,15 @@ static int fill_det(const slamklt_detect_params* p, int H, int W, int n_cur, Det
     return 0;
 }
 
-static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_frames, const double* cur_host, int cap, int64_t* out_yx, int* n_out) {
+static int prep_detect(slamklt_ctx* c, DetArgs& a);
+
+// src / src_dtype: the staged frames; Float64 always, other types only when the register-tiled kernel covers the request
+static int run_detect(slamklt_ctx* c, DetArgs& a, const void* src, int src_dtype, int n_frames, const double* cur_host, int cap, int64_t* out_yx, int* n_out) {
     const int n_cells = a.grid_h * a.grid_w;
     int r;
-    a.img = d_img; a.n_frames = n_frames; a.cap = cap;
+    a.img = src_dtype == SLAMKLT_F64 ? (const double*)src : nullptr;
+    a.src = src; a.src_dtype = src_dtype;
+    a.n_frames = n_frames; a.cap = cap;
     if ((r = c->cell_out.ensure((size_t)n_frames * n_cells * a.slots * 16))) return r;
     if ((r = c->cell_cnt.ensure((size_t)n_frames * n_cells * 4))) return r;
     if ((r = c->det_out.ensure((size_t)n_frames * cap * 16 + 16))) return r;
@@ -1258,6 +1265,26 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_fra
         c->h2d += (uint64_t)n_frames * a.n_cur * 16;
         a.cur = (const double*)c->cur.p;
     }
+    a.cell_out = (int64_t*)c->cell_out.p; a.cell_cnt = (int*)c->cell_cnt.p;
+    a.out = (int64_t*)c->det_out.p; a.n_out = (int*)c->det_n.p;
+    if (a.n_cur > 0 && detect2_supported(a)) {  // per (frame, cell row) lists of the current points within reach
+        if ((r = c->det_bin.ensure((size_t)n_frames * a.grid_h * ((size_t)a.n_cur * 8 + 4)))) return r;
+        a.bin_pts = (int2*)c->det_bin.p;
+        a.bin_cnt = (int*)((char*)c->det_bin.p + (size_t)n_frames * a.grid_h * a.n_cur * 8);
+    }
+    c->launches += launch_detect(c->stream, a, c->hk());
+    CKL();
+    prof_end(c);
+    // one copy for the counts and one for the whole [frame][cap][2] block (entries past n_out[f] are unspecified)
+    CK(cudaMemcpyAsync(n_out, c->det_n.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cap > 0) CK(cudaMemcpyAsync(out_yx, c->det_out.p, (size_t)n_frames * cap * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->d2h += (uint64_t)n_frames * (4 + (uint64_t)cap * 16);
+    return 0;
+}
+
+// Tables the register-tiled detect kernel needs (before detect2_supported is asked).
+static int prep_detect(slamklt_ctx* c, DetArgs& a) {
     if (a.n_cur > 0 && a.hw == 6) {
         // table of the 2^13 tap-subset sums of the mask blur's y pass (detect.cu, k_detect_cells2): entry `pat` adds the taps whose
         // bit is set in tap order with the same Float64 additions the tap loop performs (adding 0.0 for a clear bit changes nothing)
@@ -1279,16 +1306,6 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const double* d_img, int n_fra
         }
         a.ytab = it->second;
     }
-    a.cell_out = (int64_t*)c->cell_out.p; a.cell_cnt = (int*)c->cell_cnt.p;
-    a.out = (int64_t*)c->det_out.p; a.n_out = (int*)c->det_n.p;
-    c->launches += launch_detect(c->stream, a, c->hk());
-    CKL();
-    prof_end(c);
-    // one copy for the counts and one for the whole [frame][cap][2] block (entries past n_out[f] are unspecified)
-    CK(cudaMemcpyAsync(n_out, c->det_n.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (cap > 0) CK(cudaMemcpyAsync(out_yx, c->det_out.p, (size_t)n_frames * cap * 16, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    c->d2h += (uint64_t)n_frames * (4 + (uint64_t)cap * 16);
     return 0;
 }
 
@@ -1307,9 +1324,12 @@ int slamklt_detect(slamklt_ctx* c, const void* img, int dtype, int H, int W, int
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     if ((r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
-    const double* d_img;
-    if (dtype == SLAMKLT_F64) d_img = (const double*)c->staging.p;
+    if ((r = prep_detect(c, a))) return r;
+    const void* d_img;
+    int d_type = dtype;
+    if (dtype == SLAMKLT_F64 || detect2_supported(a)) d_img = c->staging.p;  // (the register-tiled kernel converts on load)
     else {
+        d_type = SLAMKLT_F64;
         if ((r = c->img64.ensure((size_t)H * W * 8))) return r;
         // reuse the convert kernel through a throw-away geometry: only the f64 copy is consumed
         PyrGeom g;
@@ -1319,9 +1339,9 @@ int slamklt_detect(slamklt_ctx* c, const void* img, int dtype, int H, int W, int
         FrameSet fs{(float*)scratch.p, g.frame_elems, 1, 0};
         c->launches += launch_convert(c->stream, c->staging.p, dtype, H, (size_t)H * W, fs, 0, 1, g, (double*)c->img64.p, c->hk());
         CKL();
-        d_img = (const double*)c->img64.p;
+        d_img = c->img64.p;
     }
-    r = run_detect(c, a, d_img, 1, cur, cap, out_yx, n_out);
+    r = run_detect(c, a, d_img, d_type, 1, cur, cap, out_yx, n_out);
     if (r) return r;
     if (*n_out > cap) return fail(SLAMKLT_E_CAPACITY, "detected %d keypoints but cap is %d", *n_out, cap);
     return 0;
@@ -1435,7 +1455,7 @@ int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int
 
 int slamklt_batch_build(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode) {
     if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
-    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, b->up_dtype == -2 ? "the frames of the last step sit on the device in two formats: upload them again (slamklt_batch_upload)" : "no frames uploaded");
     if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
@@ -1771,8 +1791,16 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
         }
     }
     if (pack_ns > 0.0) { const double rate = pack_bytes / (pack_ns * 1e-9); c->pack_Bps = c->pack_Bps > 0 ? 0.5 * (c->pack_Bps + rate) : rate; }
-    // what the staging buffer now holds (slamklt_batch_detect reads it): one dtype, or nothing usable after a mixed step
-    if (imgs) b->up_dtype = n_plain == 0 ? SLAMKLT_U8 : (n_packed == 0 ? dtype : -1);
+    // what the staging buffers now hold (slamklt_batch_detect reads them): one dtype, or -2 = per-chunk list after a mixed step
+    if (imgs) {
+        b->up_dtype = n_plain == 0 ? SLAMKLT_U8 : (n_packed == 0 ? dtype : -2);
+        b->up_chunks.clear();
+        if (b->up_dtype == -2)
+            for (const Chunk& ch : chunks)
+                b->up_chunks.push_back(slamklt_batch::UpChunk{ch.f0, ch.n, ch.how == UP_PACK ? SLAMKLT_U8 : dtype,
+                                                              ch.how == UP_PACK ? (const void*)(pk_base + (size_t)ch.f0 * npx)
+                                                                                : (const void*)((const char*)b->staging.p + (size_t)ch.f0 * fbytes)});
+    }
     // Only work that touches THIS batch again has to wait for its tracking kernels (see lk_pending above and
     // batch_wait_lk): another batch may build on the compute stream while this one is still being tracked.
     if (n_pts > 0 && side_lk) { CK(cudaEventRecord(b->ev_lk_done, lks)); b->lk_pending = true; }
@@ -1853,7 +1881,7 @@ int slamklt_batch_step(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int d
 // pair in one asynchronous call.  Results are fetched with slamklt_batch_download (which synchronises).
 int slamklt_batch_process(slamklt_ctx* c, slamklt_batch* b, double sigma, int mode, const slamklt_lk_params* p) {
     if (!c || !b) return fail(SLAMKLT_E_INVALID, "NULL argument");
-    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, b->up_dtype == -2 ? "the frames of the last step sit on the device in two formats: upload them again (slamklt_batch_upload)" : "no frames uploaded");
     if (mode != SLAMKLT_MODE_UPDATE && mode != SLAMKLT_MODE_CTOR) return fail(SLAMKLT_E_INVALID, "unknown mode %d", mode);
     int r = check_lk(p, b->g.nl, b->g.nl);
     if (r) return r;
@@ -1878,7 +1906,7 @@ int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out) {
 int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, int n_cur, const slamklt_detect_params* p,
                          int64_t* out_yx, int cap, int* n_out) {
     if (!c || !b || !n_out || (!out_yx && cap > 0)) return fail(SLAMKLT_E_INVALID, "NULL argument");
-    if (b->up_dtype < 0) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
+    if (b->up_dtype == -1) return fail(SLAMKLT_E_INVALID, "no frames uploaded");
     if (n_cur < 0 || cap < 0) return fail(SLAMKLT_E_INVALID, "bad shape");
     if (n_cur > 0 && !cur) return fail(SLAMKLT_E_INVALID, "cur_pts is NULL");
     if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
@@ -1891,15 +1919,28 @@ int slamklt_batch_detect(slamklt_ctx* c, slamklt_batch* b, const double* cur, in
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
     b->quiesced = false;
-    const double* d_img;
-    if (b->up_dtype == SLAMKLT_F64) d_img = (const double*)b->staging.p;
+    if ((r = prep_detect(c, a))) return r;
+    const void* d_img;
+    int d_type = b->up_dtype;
+    if (b->up_dtype == -2) {
+        // the last step shipped some chunks repacked and some plain: one Float64 copy, converted chunk by chunk
+        d_type = SLAMKLT_F64;
+        const size_t fpx = (size_t)b->g.H0 * b->g.W0;
+        if ((r = b->img64.ensure((size_t)b->n_frames * fpx * 8))) return r;
+        for (const auto& ch : b->up_chunks) {
+            c->launches += launch_convert(c->stream, ch.ptr, ch.dtype, b->g.H0, fpx, fs_of(b), 1 + ch.f0, ch.n, b->g, (double*)b->img64.p + (size_t)ch.f0 * fpx, c->hk());
+            CKL();
+        }
+        d_img = b->img64.p;
+    } else if (b->up_dtype == SLAMKLT_F64 || detect2_supported(a)) d_img = b->staging.p;  // (the register-tiled kernel converts on load)
     else {
+        d_type = SLAMKLT_F64;
         if ((r = b->img64.ensure((size_t)b->n_frames * b->g.H0 * b->g.W0 * 8))) return r;
         c->launches += launch_convert(c->stream, b->staging.p, b->up_dtype, b->g.H0, (size_t)b->g.H0 * b->g.W0, fs_of(b), 1, b->n_frames, b->g, (double*)b->img64.p, c->hk());
         CKL();
-        d_img = (const double*)b->img64.p;
+        d_img = b->img64.p;
     }
-    r = run_detect(c, a, d_img, b->n_frames, cur, cap, out_yx, n_out);
+    r = run_detect(c, a, d_img, d_type, b->n_frames, cur, cap, out_yx, n_out);
     if (r) return r;
     for (int f = 0; f < b->n_frames; ++f)
         if (n_out[f] > cap) return fail(SLAMKLT_E_CAPACITY, "frame %d: detected %d keypoints but cap is %d", f, n_out[f], cap);

@@ -99,6 +99,10 @@ struct DetArgs {
     int radius, grid_h, grid_w, cs, k_cell, hw, slots, pad_;
     double min_resp;
     double kw[33];      // 1-D mask blur weights, length 2*hw+1
+    const void* src;    // register-tiled kernel: the staged frames in their own type (src_dtype: SLAMKLT_F64 / _F32 / _U8), converted on load
+    int src_dtype, pad2_;
+    int2* bin_pts;      // register-tiled kernel, masked: per (frame, cell row) the current points within reach (k_detect_bin), or nullptr
+    int* bin_cnt;
     const double* ytab; // hw == 6 only: the 2^13 sums of tap subsets (bit t set = tap t included), added in tap order (device)
     int64_t* cell_out;  // [frame][cell][slots][2]
     int* cell_cnt;      // [frame][cell]
@@ -203,6 +207,7 @@ int lk_tma_encode(const PyrGeom& g, float* base, int n_slots, void* host_out, ch
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk);
 size_t detect_smem_bytes(int cs, int hw);
 size_t detect2_smem_bytes(int cs, int hw);
+bool detect2_supported(const DetArgs& a);  // the register-tiled kernel covers this request (it reads F32 / U8 frames directly)
 
 void iir_design(double sigma, double a[3], double* scale, double M[9]);
 void iir_dev(double sigma, int K, int KR, IirDev* out);

@@ -22,6 +22,20 @@ __device__ __forceinline__ bool in_disc(int dy, int dx, int radius) {
     return vy * vy + vx * vx < 1.0;
 }
 
+// the Float64 test is only ever needed for a lattice point exactly ON the circle: kept out of line so that the common path
+// does not carry its divisions
+__device__ __noinline__ bool in_disc_slow(int dy, int dx, int radius) { return in_disc(dy, dx, radius); }
+// largest sy >= 0 such that (sy, dx) lies inside the disc, or -1
+__device__ __forceinline__ int disc_half_height(int dx, int radius) {
+    const int rem = radius * radius - dx * dx;
+    if (rem < 0) return -1;
+    int sy = (int)sqrtf((float)rem);
+    while (sy * sy > rem) --sy;
+    while ((sy + 1) * (sy + 1) <= rem) ++sy;
+    if (sy * sy == rem && !in_disc_slow(sy, dx, radius)) --sy;
+    return sy;
+}
+
 constexpr int MAX_NEAR = 512;  // current points kept in shared memory per cell (more => slow path over the global list)
 
 // Shared-memory plan of one cell (doubles unless noted), identical on host and device:
@@ -465,6 +479,14 @@ __global__ void __launch_bounds__(DET_THREADS) k_detect_cells(DetArgs a) {
 // current points are rasterised in chunks of MAX_NEAR so that no cell ever needs a slow path.
 // Covers: no mask, or a 13-tap mask blur (sigma_mask = 3, the reference's default) with cell_size + 12 <= 64.
 // ---------------------------------------------------------------------------------------------------------------------------
+// one pixel of the staged frames as the Float64 the reference computes on: Gray{Float64}.(img) of 8-bit data is k / 255
+template <bool F64SRC>
+__device__ __forceinline__ double det_px(const DetArgs& a, size_t i) {
+    if (F64SRC || a.src_dtype == SLAMKLT_F64) return __ldg(reinterpret_cast<const double*>(a.src) + i);
+    if (a.src_dtype == SLAMKLT_U8) return (double)__ldg(reinterpret_cast<const uint8_t*>(a.src) + i) / 255.0;
+    return (double)__ldg(reinterpret_cast<const float*>(a.src) + i);
+}
+
 constexpr int DET_RS = 5;
 constexpr int DET2_HW = 6, DET2_NT = 2 * DET2_HW + 1;
 
@@ -494,10 +516,31 @@ __host__ __device__ inline Det2Smem det2_smem_plan(int cs, int hw) {
 size_t detect2_smem_bytes(int cs, int hw) { return det2_smem_plan(cs, hw).total; }
 
 // CS: the cell size as a compile-time constant (plane pitch and offsets become immediates), or 0 = taken from the arguments
+// Current points of a frame that can reach a row of cells (rounded row within radius + hw of the row's pixels), as int2 (y, x)
+// 1-based: every cell of the row then scans this short list instead of all n_cur points.  The order inside a list is arbitrary
+// (the discs are cleared with atomic ANDs).  a.bin_pts: [frame][cell row][n_cur] int2, a.bin_cnt: [frame][cell row].
+__global__ void __launch_bounds__(DET_THREADS) k_detect_bin(DetArgs a) {
+    __shared__ int s_n;
+    const int gy = blockIdx.x, f = blockIdx.y;
+    const int y0 = gy * a.cs, y1 = min((gy + 1) * a.cs, a.H);
+    const int reach = a.radius + a.hw;
+    const double* cur = a.cur + (size_t)f * a.n_cur * 2;
+    int2* out = a.bin_pts + ((size_t)f * gridDim.x + gy) * a.n_cur;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.n_cur; k += DET_THREADS) {
+        const int cy = (int)rint(cur[2 * k]), cx = (int)rint(cur[2 * k + 1]);  // Julia round(): ties to even; 1-based
+        if (cy >= y0 + 1 - reach && cy <= y1 + reach) out[atomicAdd(&s_n, 1)] = make_int2(cy, cx);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.bin_cnt[(size_t)f * gridDim.x + gy] = s_n;
+}
+
 #ifndef DET2_MINB
 #define DET2_MINB 4
 #endif
-template <bool MASKED, int CS>
+// F64SRC: the staged frames are Float64 (no run-time switch on the pixel type in the load path)
+template <bool MASKED, int CS, bool F64SRC>
 __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int RS = DET_RS, hw = MASKED ? DET2_HW : 0, nt = DET2_NT;
@@ -526,7 +569,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
     unsigned* s_maskw = (unsigned*)(smem_raw + sm.oMaskW);
     int* s_misc = (int*)(smem_raw + sm.oMisc);
 
-    const double* img = a.img + (size_t)f * H * W;
+    const size_t img0 = (size_t)f * H * W;   // first element of this frame in a.src
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const DivH dh(h), dw(w);
     const int npx = h * w;
@@ -551,18 +594,29 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
         unsigned long long* s_zero = s_full + 64;
         const double* cur = a.cur + (size_t)f * a.n_cur * 2;
         const int rh = h + 2 * hw, rw = w + 2 * hw;
-        const int r2 = a.radius * a.radius;
         const int reach = a.radius + hw;
         const unsigned long long allrows = rh == 64 ? ~0ull : ((1ull << rh) - 1ull);
         for (int i = tid; i < 64; i += DET_THREADS) { s_col[i] = allrows; s_F[i] = 0ull; s_Z[i] = 0ull; }
         const int ry0 = y0 - hw, rx0 = x0 - hw;  // image row / column (0-based) of region row / column 0
         const int ncolsd = 2 * a.radius + 1;
-        for (int k0 = 0; k0 < a.n_cur; k0 += MAX_NEAR) {
+        // half height of the disc at every column offset dx, the same for every point: the largest sy with (sy, dx) inside
+        // ImageDraw's ellipse test (-1: the column is empty).  A disc wider than the table falls back to the per-item computation.
+        int* const s_sy = s_misc + 16;
+        const bool sy_tab = ncolsd <= 48;
+        if (sy_tab) {
+            for (int i = tid; i < ncolsd; i += DET_THREADS) s_sy[i] = disc_half_height(i - a.radius, a.radius);
+        }
+        const DivH dcol(ncolsd);
+        const int2* const bin = a.bin_pts ? a.bin_pts + ((size_t)f * a.grid_h + gy) * a.n_cur : nullptr;
+        const int n_scan = bin ? a.bin_cnt[(size_t)f * a.grid_h + gy] : a.n_cur;
+        for (int k0 = 0; k0 < n_scan; k0 += MAX_NEAR) {
             if (tid == 0) s_misc[0] = 0;
             __syncthreads();
-            const int k1 = min(a.n_cur, k0 + MAX_NEAR);
+            const int k1 = min(n_scan, k0 + MAX_NEAR);
             for (int k = k0 + tid; k < k1; k += DET_THREADS) {
-                const int cy = (int)rint(cur[2 * k]), cx = (int)rint(cur[2 * k + 1]);  // Julia round(): ties to even; 1-based
+                int cy, cx;
+                if (bin) { const int2 p = __ldg(bin + k); cy = p.x; cx = p.y; }
+                else { cy = (int)rint(cur[2 * k]); cx = (int)rint(cur[2 * k + 1]); }  // Julia round(): ties to even; 1-based
                 if (cy >= y0 + 1 - reach && cy <= y1 + reach && cx >= x0 + 1 - reach && cx <= x1 + reach) {
                     const int slot = atomicAdd(&s_misc[0], 1);
                     s_near[2 * slot] = cy; s_near[2 * slot + 1] = cx;
@@ -572,26 +626,28 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
             const int n_near = s_misc[0];
             // discs column by column: one atomicAnd clears a column's rows (get_mask + ImageDraw circle)
             for (int it = tid; it < n_near * ncolsd; it += DET_THREADS) {
-                const int k = it / ncolsd, dx = it - k * ncolsd - a.radius;
+                int k, di;
+                if (n_near * ncolsd * ncolsd < (1 << 20)) dcol.split(it, di, k);   // it = di + k * ncolsd (DivH is exact while it * ncolsd < 2^20)
+                else { k = it / ncolsd; di = it - k * ncolsd; }
+                const int dx = di - a.radius;
                 const int X = s_near[2 * k + 1] - 1 + dx;  // 0-based image column
                 const int xx = X - rx0;
                 if (X < 0 || X >= W || xx < 0 || xx >= rw) continue;
-                const int rem = r2 - dx * dx;
-                int sy = (int)sqrtf((float)rem);
-                while (sy * sy > rem) --sy;
-                while ((sy + 1) * (sy + 1) <= rem) ++sy;
-                if (sy * sy == rem && !in_disc(sy, dx, a.radius)) --sy;  // only a lattice point ON the circle needs the Float64 test
+                const int sy = sy_tab ? s_sy[di] : disc_half_height(dx, a.radius);
                 if (sy < 0) continue;
                 const int Yc = s_near[2 * k] - 1;
                 const int ra = max(max(Yc - sy, 0) - ry0, 0), rb = min(min(Yc + sy, H - 1) - ry0, rh - 1);
                 if (ra > rb) continue;
-                const int len = rb - ra + 1;
-                const unsigned long long bits = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << ra;
-                atomicAnd(&s_col[xx], ~bits);
+                // rows [ra, rb] of the column word, cleared as two 32-bit halves (native shared-memory atomics)
+                unsigned* const wp = reinterpret_cast<unsigned*>(&s_col[xx]);
+                const unsigned lo = ra < 32 ? ((rb >= 31 ? ~0u : ((2u << rb) - 1u)) & ~((1u << ra) - 1u)) : 0u;
+                const unsigned hi = rb >= 32 ? ((rb >= 63 ? ~0u : ((2u << (rb - 32)) - 1u)) & (ra > 32 ? ~((1u << (ra - 32)) - 1u) : ~0u)) : 0u;
+                if (lo) atomicAnd(wp, ~lo);
+                if (hi) atomicAnd(wp + 1, ~hi);
             }
             __syncthreads();
         }
-        if (a.n_cur <= 0) __syncthreads();
+        if (n_scan <= 0) __syncthreads();
         // replicate border of the full-image mask: rows above / below the image repeat the first / last image row ...
         const int top = max(0, -ry0), bot = min(rh, H - ry0);  // region rows [top, bot) lie in the image
         const int left = max(0, -rx0), right = min(rw, W - rx0);
@@ -635,7 +691,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
         for (int i = tid; i < h * rw; i += DET_THREADS) {
             int y, xx;
             dh.split(i, y, xx);
-            s_tmp[i] = __ldg(a.ytab + ((unsigned)(s_col[xx] >> y) & pmask));
+            s_tmp[y + xx * cs] = __ldg(a.ytab + ((unsigned)(s_col[xx] >> y) & pmask));   // (pitch cs: immediates when CS is fixed)
         }
         const double sall = __ldg(a.ytab + pmask);
         double call = 0.0;
@@ -651,25 +707,26 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
             const unsigned wmask = (1u << (nx + nt - 1)) - 1u;
             const bool allz = ((unsigned)(s_zero[y] >> xa) & wmask) == wmask;   // (bits of Z / F beyond rw are zero)
             const bool allf = ((unsigned)(s_full[y] >> xa) & wmask) == wmask;
-            const double* ip = img + (size_t)(y0 + y) + (size_t)(x0 + xa) * H;
+            const size_t ip = img0 + (size_t)(y0 + y) + (size_t)(x0 + xa) * H;
             double* op = s_img + (y + 1) + (xa + 1) * P;
             if (allz || allf) {  // every 13 x 13 window of the strip is all zeros / all ones
                 const double acc = allz ? 0.0 : call;
 #pragma unroll
                 for (int j = 0; j < RS; ++j)
-                    if (j < nx) op[j * P] = ip[(size_t)j * H] * acc;
+                    if (j < nx) op[j * P] = det_px<F64SRC>(a, ip + (size_t)j * H) * acc;
             } else {
-                const double* tp = s_tmp + y + xa * h;
+                // (a short last strip reads up to RS - 1 columns past the filtered mask: still inside this block's scratch, never used)
+                const double* tp = s_tmp + y + xa * cs;
                 double v[RS + nt - 1];
 #pragma unroll
-                for (int t = 0; t < RS + nt - 1; ++t) v[t] = (t < nx + nt - 1) ? tp[t * h] : 0.0;
+                for (int t = 0; t < RS + nt - 1; ++t) v[t] = tp[t * cs];
 #pragma unroll
                 for (int j = 0; j < RS; ++j) {
                     if (j < nx) {
                         double acc = 0.0;
 #pragma unroll
                         for (int t = 0; t < nt; ++t) acc += a.kw[t] * v[j + t];
-                        op[j * P] = ip[(size_t)j * H] * acc;
+                        op[j * P] = det_px<F64SRC>(a, ip + (size_t)j * H) * acc;
                     }
                 }
             }
@@ -678,7 +735,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
         for (int i = tid; i < npx; i += DET_THREADS) {
             int y, x;
             dh.split(i, y, x);
-            s_img[(y + 1) + (x + 1) * P] = img[(size_t)(y0 + y) + (size_t)(x0 + x) * H];
+            s_img[(y + 1) + (x + 1) * P] = det_px<F64SRC>(a, img0 + (size_t)(y0 + y) + (size_t)(x0 + x) * H);
         }
     }
     __syncthreads();
@@ -855,7 +912,6 @@ bool detect2_supported(const DetArgs& a) {
 int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk) {
     const int n_cells = a.grid_h * a.grid_w;
     dim3 grid(n_cells, a.n_frames);
-    mark(hk, "k_detect_cells");
     if (detect2_supported(a)) {
         const bool masked = a.n_cur > 0;
         const size_t smem = detect2_smem_bytes(a.cs, masked ? DET2_HW : 0);
@@ -864,14 +920,27 @@ int launch_detect(cudaStream_t s, const DetArgs& a, const Hook* hk) {
             kern<<<grid, DET_THREADS, smem, s>>>(a);
         };
         // the reference's cell size (35) gets the instantiation with compile-time plane offsets
-        if (masked) { if (a.cs == 35) go(k_detect_cells2<true, 35>); else go(k_detect_cells2<true, 0>); }
-        else { if (a.cs == 35) go(k_detect_cells2<false, 35>); else go(k_detect_cells2<false, 0>); }
+        const bool f64 = a.src_dtype == SLAMKLT_F64;
+        if (masked) {
+            if (a.bin_pts) {   // current points within reach of each row of cells, once per frame instead of once per cell
+                mark(hk, "k_detect_bin");
+                k_detect_bin<<<dim3(a.grid_h, a.n_frames), DET_THREADS, 0, s>>>(a);
+            }
+            mark(hk, "k_detect_cells");
+            if (a.cs == 35) { if (f64) go(k_detect_cells2<true, 35, true>); else go(k_detect_cells2<true, 35, false>); }
+            else { if (f64) go(k_detect_cells2<true, 0, true>); else go(k_detect_cells2<true, 0, false>); }
+        } else {
+            mark(hk, "k_detect_cells");
+            if (a.cs == 35) { if (f64) go(k_detect_cells2<false, 35, true>); else go(k_detect_cells2<false, 35, false>); }
+            else { if (f64) go(k_detect_cells2<false, 0, true>); else go(k_detect_cells2<false, 0, false>); }
+        }
         mark(hk, "k_detect_compact");
         k_detect_compact<<<a.n_frames, DET_THREADS, 0, s>>>(a, n_cells);
-        return 2;
+        return (masked && a.bin_pts) ? 3 : 2;
     }
     const size_t smem = detect_smem_bytes(a.cs, a.hw);
     cudaFuncSetAttribute(k_detect_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mark(hk, "k_detect_cells");
     k_detect_cells<<<grid, DET_THREADS, smem, s>>>(a);
     mark(hk, "k_detect_compact");
     k_detect_compact<<<a.n_frames, DET_THREADS, 0, s>>>(a, n_cells);

@@ -280,6 +280,13 @@ def test_step_hybrid_upload_and_two_batches_in_flight(ctx, monkeypatch):
     ox2, sx2 = bx.step_end()
     oy2, sy2 = by.step_end()
     assert np.array_equal(sx2, ref[4]) and np.array_equal(np.nan_to_num(ox2), ref[3])
+    # detect on the frames of a step that travelled in two formats equals detect on the same frames uploaded plainly
+    ext = slamklt.Extractor(600, 17, (11, 36), 35)
+    cur = np.stack([synth.random_keypoints(900 + i, 200, H, W, border=0.0) for i in range(NF)])
+    got = by.detect(ext, cur)                              # by's last step: pin.array through step_begin (two engines)
+    bs.upload(pin.array, pts)
+    want = bs.detect(ext, cur)
+    assert all(np.array_equal(g, w_) for g, w_ in zip(got, want)) and sum(len(g) for g in got) > 1000
     for b in (bx, by, bs):
         b.close()
     pin.free(); pin_rev.free()

@@ -212,3 +212,34 @@ def test_detect_small_ragged(ctx, seq):
     assert np.array_equal(O.detect(e_o, img, cur), slamklt.detect(ctx, e_g, img, cur))
     full = np.zeros((200, 2)) + 5.0
     assert len(slamklt.detect(ctx, e_g, img, full)) == 0  # extractor.jl:64
+
+
+@pytest.mark.parametrize("case", ["cell24", "crowded", "wide_disc", "sigma2", "sigma1_5", "cell60"])
+def test_detect_kernel_variants_identical(ctx, seq, case):
+    """Round 2: detect runs a register-tiled kernel for the reference's shapes and the first kernel for the rest.  Every branch
+    of that choice must give the oracle's keypoint arrays: a cell size other than 35 (run-time plane pitch), more current points
+    near one cell than one rasterisation chunk holds, a disc wider than the half-height table, mask blurs that are not 13 taps
+    (first kernel), and a cell too large for the bit-plane mask (first kernel)."""
+    img = seq[0][0]
+    H, W = img.shape
+    rng = np.random.default_rng(77)
+    if case == "cell24":
+        e_args, cur, sig = (900, 11, (15, 51), 24), synth.random_keypoints(5, 300, H, W, border=0.0), 3.0
+    elif case == "crowded":
+        # 1500 current points, 700 of them packed around one cell: several chunks of 512 for the cells nearby
+        dense = np.stack([rng.uniform(150, 230, 700), rng.uniform(500, 600, 700)], axis=1)
+        e_args, cur, sig = (3000, 5, (11, 36), 35), np.vstack([dense, synth.random_keypoints(6, 800, H, W, border=0.0)]), 3.0
+    elif case == "wide_disc":
+        e_args, cur, sig = (1000, 30, (11, 36), 35), synth.random_keypoints(7, 120, H, W, border=0.0), 3.0
+    elif case == "sigma2":
+        e_args, cur, sig = (1000, 17, (11, 36), 35), synth.random_keypoints(8, 400, H, W, border=0.0), 2.0
+    elif case == "sigma1_5":
+        e_args, cur, sig = (1000, 17, (11, 36), 35), synth.random_keypoints(9, 400, H, W, border=0.0), 1.5
+    else:
+        e_args, cur, sig = (600, 17, (7, 21), 60), synth.random_keypoints(10, 300, H, W, border=0.0), 3.0
+    ko = O.detect(O.Extractor(*e_args), img, cur, sigma_mask=sig)
+    kg = slamklt.detect(ctx, slamklt.Extractor(*e_args), img, cur, sigma_mask=sig)
+    assert ko.shape == kg.shape and np.array_equal(ko, kg)
+    assert len(kg) > 50
+    kp = slamklt.detect(ctx, slamklt.Extractor(*e_args), img, np.zeros((0, 2)))          # and without a mask
+    assert np.array_equal(O.detect(O.Extractor(*e_args), img, np.zeros((0, 2))), kp)
