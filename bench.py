@@ -673,6 +673,10 @@ def main():
                     "host_threads": int(os.environ.get("SLAMKLT_HOST_THREADS", min(16, cores))),
                     "steps_in_flight": 2 if simple else 1,
                     "ms_per_step_one_synchronous_call": 1e3 * t_e2e1 / args.steps,
+                    "host_source_GBps_all_ranks": world * NF * (2 if cfg["stereo"] else 1) * H * W * 8 / (t_e2e / args.steps) / 1e9,
+                    "host_source_note": "bytes of Float64 frames the ranks of this box read from host memory per second (by worker threads "
+                                        "or by the copy engines): at N >= 2 this number, not the GPUs, bounds the Float64 e2e figure "
+                                        "(measured: about 180 GB/s on the 32-vCPU 8-GPU host); UInt8 frames (e2e_u8) are 8x lighter and scale",
                     "upload_engines_rank0": up,
                     "note": "Float64 host frames (the reference's Matrix{Gray{Float64}}) in page-locked memory.  When every pixel is an exact "
                             "k/255 -- 8-bit camera data, as in the reference's example -- host worker threads repack some chunks of a step to 8 "

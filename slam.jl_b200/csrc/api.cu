@@ -1018,11 +1018,13 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     // device block: [pix 2n | world 3n | undist 2n | disp 2n | tracked 2n | out_pix 2n | out_und 2n | out_pos 3n] doubles, then
     // [is_3d n | flag n | status n] bytes
     const size_t N = (size_t)n;
-    if ((r = c->match.ensure(N * 18 * 8 + N * 3))) return r;
+    // sections start at multiples of 16 bytes (the tracking kernel reads points and priors as double2): M = N rounded up to even
+    const size_t M = (N + 1) & ~(size_t)1;
+    if ((r = c->match.ensure(M * 18 * 8 + N * 3))) return r;
     double* d = (double*)c->match.p;
-    double *d_pix = d, *d_world = d + 2 * N, *d_undist = d + 5 * N, *d_disp = d + 7 * N, *d_trk = d + 9 * N, *d_opix = d + 11 * N,
-           *d_ound = d + 13 * N, *d_opos = d + 15 * N;
-    uint8_t* d_is3d = (uint8_t*)(d + 18 * N);
+    double *d_pix = d, *d_world = d + 2 * M, *d_undist = d + 5 * M, *d_disp = d + 7 * M, *d_trk = d + 9 * M, *d_opix = d + 11 * M,
+           *d_ound = d + 13 * M, *d_opos = d + 15 * M;
+    uint8_t* d_is3d = (uint8_t*)(d + 18 * M);
     uint8_t *d_flag = d_is3d + N, *d_status = d_flag + N;
     CK(cudaMemcpyAsync(d_pix, pix, N * 16, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_world, world, N * 24, cudaMemcpyHostToDevice, c->stream));

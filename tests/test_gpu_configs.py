@@ -219,6 +219,20 @@ def test_optical_flow_matching_with_geometry(ctx, stereo):
         assert np.array_equal(g_pix[ok][:, 0], pts[ok][:, 0])      # row taken from the left keypoint
 
 
+def test_optical_flow_matching_odd_keypoint_count(ctx):
+    """An odd number of keypoints (found by compute-sanitizer in round 2: the device block of the call laid its sections out
+    at multiples of 8 N bytes, and the tracking kernel reads points and priors as 16-byte pairs).  The first n keypoints must
+    get exactly what they get inside the even-sized call."""
+    pts, sc, _, (g0, g1) = _matching_case(ctx, False)
+    gcam = slamklt.Camera(**sc["camera"])
+    full = slamklt.optical_flow_matching_frame(g0, g1, pts, sc["is_3d"], sc["world"], sc["cw"], gcam, window_size=9, pyramid_levels=3)
+    for n in (1, 43, len(pts) - 1 if len(pts) % 2 == 0 else len(pts) - 2):
+        part = slamklt.optical_flow_matching_frame(g0, g1, pts[:n], sc["is_3d"][:n], sc["world"][:n], sc["cw"], gcam, window_size=9,
+                                                   pyramid_levels=3)
+        for a, b in zip(full, part):
+            assert np.array_equal(np.nan_to_num(a[:n]), np.nan_to_num(b))
+
+
 def test_optical_flow_matching_geometry_arguments(ctx):
     pts, sc, _, (g0, g1) = _matching_case(ctx, False)
     gcam = slamklt.Camera(**sc["camera"])

@@ -36,5 +36,28 @@ pts = np.stack([synth.random_keypoints(5 + i, 50, 75, 131, border=2.0) for i in 
 batch.step(slamklt.StreamBatch.pack_frames(f[1:3]), pts, slamklt.LucasKanade(pyramid_levels=2))
 batch.upload(slamklt.StreamBatch.pack_frames(fr[1:3]), pts); batch.process(slamklt.LucasKanade(pyramid_levels=2)); batch.download()
 batch.detect(e)
+# round 2: masked detect through the register-tiled kernel (row binning, chunks of current points), a cell size other than 35, a
+# mask blur that takes the first kernel; two batches in flight with page-locked Float64 frames (two upload engines); detect after
+# such a step; stereo matching of two batches
+cur = np.stack([synth.random_keypoints(40 + i, 30, 75, 131, border=0.0) for i in range(2)])
+batch.detect(e, cur)
+slamklt.detect(ctx, slamklt.Extractor(100, 5, (4, 6), 24), f[0], cur[0])
+slamklt.detect(ctx, e, f[0], cur[0], sigma_mask=2.0)
+slamklt.detect(ctx, e, fr[0], cur[0])
+nb = 8
+frs, _ = synth.make_sequence(2, nb + 1, H=376, W=400)
+fs64 = synth.to_f64(frs)
+pin = slamklt.PinnedArray((nb, 400, 376), np.float64)
+pin.array[...] = np.transpose(fs64[1:], (0, 2, 1))
+bx, by = slamklt.StreamBatch(ctx, 376, 400, 2, nb, 60), slamklt.StreamBatch(ctx, 376, 400, 2, nb, 60)
+bx.prime(fs64[0]); by.prime(fs64[0])
+p8 = np.stack([synth.random_keypoints(70 + i, 60, 376, 400, border=3.0) for i in range(nb)])
+alg2 = slamklt.LucasKanade(pyramid_levels=2)
+for _ in range(2):
+    bx.step_begin(pin.array, p8, alg2); by.step_begin(pin.array, p8, alg2)
+    bx.step_end(); by.step_end()
+bx.detect(slamklt.Extractor(300, 8, (11, 12), 35), np.stack([synth.random_keypoints(90 + i, 40, 376, 400, border=0.0) for i in range(nb)]))
+by.track_cross(bx, alg2); bx.download()
+bx.close(); by.close(); pin.free()
 batch.close(); ctx.close()
 print("sanitize_small done")
