@@ -360,6 +360,16 @@ __global__ void __launch_bounds__(256) k_cols_blur(ColArgs a, IirDev c) {
 // plane and the three y-filtered product planes T0 (yy), T1 (xx), T2 (yx).
 constexpr int GRAD_CS = 8;
 
+// (float)((double)k / 255.0) for k = 0 .. 255 -- the layer value of an 8-bit pixel (Gray{Float64}(k / 255) converted to fp32) --
+// without the Float64 division: q = k * (1/255) corrected by one Newton step on the exact remainder equals the correctly rounded
+// fp32 quotient, and that equals the doubly rounded reference value for every one of the 256 inputs (checked exhaustively:
+// tests/test_oracle.py::test_u8_unit_conversion_is_exact).
+__device__ __forceinline__ float u8_unit(unsigned k) {
+    const float kf = (float)k, r = 1.0f / 255.0f;
+    const float q = kf * r;
+    return fmaf(fmaf(-q, 255.0f, kf), r, q);
+}
+
 // SRC: 0 layer plane (fp32), 1 raw Float64, 2 raw Float32, 3 raw UInt8 (value / 255)
 template <int K, int SRC, int G = 1>
 __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y0, float (&x)[K],
@@ -396,8 +406,24 @@ __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __re
         for (int j = 0; j < K; ++j) x[j] = rg.valid(j) ? __ldg(col + y0 + j) : 0.f;
     } else {
         const uint8_t* col = reinterpret_cast<const uint8_t*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld;
+        if constexpr (G >= 4 && K % 4 == 0) {
+            // aligned variant (H, and with it every column start, is a multiple of 4): four rows per 32-bit load
 #pragma unroll
-        for (int j = 0; j < K; ++j) x[j] = rg.valid(j) ? (float)((double)__ldg(col + y0 + j) / 255.0) : 0.f;
+            for (int v = 0; v < K / 4; ++v) {
+                const unsigned w = rg.valid(4 * v) ? __ldg(reinterpret_cast<const unsigned*>(col + y0 + 4 * v)) : 0u;
+                x[4 * v] = u8_unit(w & 0xffu); x[4 * v + 1] = u8_unit((w >> 8) & 0xffu);
+                x[4 * v + 2] = u8_unit((w >> 16) & 0xffu); x[4 * v + 3] = u8_unit(w >> 24);
+            }
+        } else if constexpr (G >= 2) {
+#pragma unroll
+            for (int v = 0; v < K / 2; ++v) {
+                const unsigned w = rg.valid(2 * v) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(col + y0 + 2 * v)) : 0u;
+                x[2 * v] = u8_unit(w & 0xffu); x[2 * v + 1] = u8_unit(w >> 8);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) x[j] = rg.valid(j) ? u8_unit(__ldg(col + y0 + j)) : 0.f;
+        }
     }
 }
 

@@ -24,7 +24,8 @@ for i, kp in enumerate(kps):
     if len(kp) < 2000:
         kp = np.vstack([kp, synth.random_keypoints(1000 + i, 2000 - len(kp), 376, 1241)])
     pts[i] = np.clip(kp + rng.uniform(-0.5, 0.5, kp.shape), 1.0, [376, 1241])
-batch.upload(slamklt.StreamBatch.pack_frames(f64[1:]), pts)
+# STAGE_U8=1: the frames sit on the device as UInt8 (what a step leaves there when it repacks 8-bit data) instead of Float64
+batch.upload(slamklt.StreamBatch.pack_frames(fr[1:] if os.environ.get("STAGE_U8") else f64[1:]), pts)
 alg = slamklt.LucasKanade(iterations=30, window_size=9, pyramid_levels=3)
 batch.build(); batch.track(alg, 1.0); ctx.sync()
 ctx.stats(reset=True)
