@@ -513,6 +513,11 @@ def main():
     e2e_ok = int((outs.array & 1).sum())
     # for comparison: one synchronous slamklt_batch_step per step (nothing overlaps across steps)
     e2e1_s = e2e_loop([(packA, ptsA), (packB, ptsB)], [rpackA, rpackB], in_flight=1)[0] if simple else e2e_s
+    # re-extraction after every step is a synchronous call that keeps the host from repacking the next step: with it, one step at a
+    # time can be the faster schedule -- report the better one and say which
+    e2e_in_flight = 2 if simple else 1
+    if cfg["detect"] and e2e1_s < e2e_s:
+        e2e_s, e2e_in_flight = e2e1_s, 1
     # the same through u8 host frames: what a camera / PNG decoder hands over (the reference's example converts to Gray{Float64}
     # on the host, example/kitty/main.jl:36-40); 8x fewer PCIe bytes, bit-identical pyramids (tests/test_gpu_batch.py)
     pack8A, pack8B = packed(left_u8[1:], np.uint8), packed(left_u8[:-1][::-1], np.uint8)
@@ -523,6 +528,9 @@ def main():
         pinned += [r8A, r8B]
     e2e8_s, e2e8_h2d, e2e8_d2h = e2e_loop([(pack8A, ptsA), (pack8B, ptsB)], [r8A, r8B])
     e2e81_s = e2e_loop([(pack8A, ptsA), (pack8B, ptsB)], [r8A, r8B], in_flight=1)[0] if simple else e2e8_s
+    e2e8_in_flight = 2 if simple else 1
+    if cfg["detect"] and e2e81_s < e2e8_s:
+        e2e8_s, e2e8_in_flight = e2e81_s, 1
     up = ctx.upload_rates()
 
     # ---------------- per-frame drop-in path (one frame at a time through the reference-facing calls), c2 at N = 1 only
@@ -671,7 +679,7 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / args.steps, "tracked_ok_last_step": e2e_ok,
                     "h2d_GBps_per_rank": e2e_h2d / (t_e2e / args.steps) / 1e9,
                     "host_threads": int(os.environ.get("SLAMKLT_HOST_THREADS", min(16, cores))),
-                    "steps_in_flight": 2 if simple else 1,
+                    "steps_in_flight": e2e_in_flight,
                     "ms_per_step_one_synchronous_call": 1e3 * t_e2e1 / args.steps,
                     "host_source_GBps_all_ranks": world * NF * (2 if cfg["stereo"] else 1) * H * W * 8 / (t_e2e / args.steps) / 1e9,
                     "host_source_note": "bytes of Float64 frames the ranks of this box read from host memory per second (by worker threads "
@@ -687,7 +695,7 @@ def main():
                             "step overlap the kernels of the other; every step's uploads and result downloads are inside the timed region"},
             "e2e_u8": {"value": e2e8_val, "unit": UNIT, "h2d_bytes_per_step": int(e2e8_h2d), "d2h_bytes_per_step": int(e2e8_d2h),
                        "host_dtype": "u8", "ms_per_step": 1e3 * t_e2e8 / args.steps,
-                       "steps_in_flight": 2 if simple else 1, "ms_per_step_one_synchronous_call": 1e3 * t_e2e81 / args.steps,
+                       "steps_in_flight": e2e8_in_flight, "ms_per_step_one_synchronous_call": 1e3 * t_e2e81 / args.steps,
                        "h2d_GBps_per_rank": e2e8_h2d / (t_e2e8 / args.steps) / 1e9,
                        "note": "same call with UInt8 host frames (camera / PNG decoder output), converted on the device with the reference's "
                                "i/255 semantics; pyramids bit-identical to the Float64 upload"},

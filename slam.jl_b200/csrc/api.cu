@@ -281,6 +281,18 @@ struct slamklt_ctx {
     const Hook* hk() const { return prof_on ? &hook : nullptr; }
 };
 
+static int ensure_pool(slamklt_ctx* c) {
+    if (!c->pool) {
+        int avail = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+        const char* e = getenv("SLAMKLT_HOST_THREADS");
+        int want = e ? atoi(e) : std::min(avail, 16);
+        c->pool = new HostPool(std::max(want, 1) - 1);
+    }
+    return 0;
+}
+
 // work counters of the persistent tracking grid: a ring, one slot per launch (the launcher zeroes the slot on its stream)
 static constexpr int WORK_RING = 1024;
 static unsigned* work_slot(slamklt_ctx* c) { return reinterpret_cast<unsigned*>(c->d_counters + 2) + (c->work_idx++ % WORK_RING); }
@@ -320,6 +332,7 @@ struct slamklt_batch {
     bool primed = false;
     cudaEvent_t ev_lk_done = nullptr;  // last tracking kernel that read this batch's slots (recorded on the lk stream)
     bool lk_pending = false;
+    cudaEvent_t ev_pack = nullptr;       // last copy out of h_pack queued by slamklt_batch_upload
     cudaEvent_t ev_step_done = nullptr;  // everything slamklt_batch_step_begin queued, result copies included
     bool step_pending = false;
     struct UpChunk { int f0, n, dtype; const void* ptr; };
@@ -1369,6 +1382,7 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     b->views.resize(b->n_slots, nullptr);
     CK(cudaEventCreateWithFlags(&b->ev_lk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_step_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_pack, cudaEventDisableTiming));
     if ((r = make_maps(c, g, b->base, b->n_slots, &b->d_maps))) return r;
     // Scratch ring for the y-filtered product planes: SLAMKLT_BUILD_GROUP frames per build group (default 0 = off).  Measured on
     // B200 (64 KITTI frames, ncu --cache-control none): with groups of 8 and the L2 window the T planes never reach HBM (DRAM
@@ -1407,6 +1421,7 @@ int slamklt_batch_destroy(slamklt_ctx* c, slamklt_batch* b) {
     for (auto* v : b->views) delete v;
     if (b->ev_lk_done) cudaEventDestroy(b->ev_lk_done);
     if (b->ev_step_done) cudaEventDestroy(b->ev_step_done);
+    if (b->ev_pack) cudaEventDestroy(b->ev_pack);
     for (auto e : b->raw_ev) cudaEventDestroy(e);
     b->staging.release(); b->staging8.release(); b->img64.release(); b->pts.release(); b->outp.release(); b->status.release(); b->gtab.release();
     b->h_pack.release();
@@ -1445,8 +1460,38 @@ int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int
     CK(cudaSetDevice(c->device));
     BATCH_WAIT_LK(c, b);
     b->quiesced = false;
-    int r = upload_frames(c, b->staging, imgs, dtype, ld, frame_stride_bytes, b->n_frames, b->g.H0, b->g.W0);
-    if (r) return r;
+    int r;
+    // Float64 frames that hold 8-bit data travel as one byte per pixel here too (see batch_pipeline): lossless, the device rebuilds
+    // the identical Float64.  The staging buffer may still be read by work queued earlier on the compute stream, and the repacked
+    // bytes land at different offsets than plain frames would: order the copy behind that work (it runs on the compute stream).
+    const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
+    const size_t npx = (size_t)H * W;
+    bool packed = false;
+    if (dtype == SLAMKLT_F64 && ld == H && (frame_stride_bytes == npx * 8 || nf == 1) && (size_t)nf * npx >= (1u << 20) &&
+        getenv("SLAMKLT_NO_PACK") == nullptr) {
+        if ((r = b->h_pack.ensure((size_t)nf * npx))) return r;
+        if ((r = b->staging.ensure((size_t)nf * npx * 8))) return r;
+        if ((r = ensure_pool(c))) return r;
+        CK(cudaStreamSynchronize(c->copy_stream));  // (an earlier step or upload may still be copying out of the repack buffer)
+        CK(cudaEventSynchronize(b->ev_pack));
+        std::atomic<int> bad{0};
+        uint8_t* hp = (uint8_t*)b->h_pack.p;
+        const int cols = 64, blocks = (W + cols - 1) / cols;
+        c->pool->start(nf * blocks, [=, &bad](int item) {
+            const int f = item / blocks, x0 = (item - f * blocks) * cols, x1 = std::min(W, x0 + cols);
+            const double* sp = (const double*)imgs + (size_t)f * npx + (size_t)x0 * H;
+            if (!pack_u8_exact(sp, hp + (size_t)f * npx + (size_t)x0 * H, (size_t)(x1 - x0) * H)) bad.store(1);
+        });
+        c->pool->wait();
+        if (bad.load() == 0) {
+            CK(cudaMemcpyAsync(b->staging.p, hp, (size_t)nf * npx, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaEventRecord(b->ev_pack, c->stream));   // the repack buffer is free again once this copy has run
+            c->h2d += (uint64_t)nf * npx;
+            dtype = SLAMKLT_U8;
+            packed = true;
+        }
+    }
+    if (!packed && (r = upload_frames(c, b->staging, imgs, dtype, ld, frame_stride_bytes, b->n_frames, b->g.H0, b->g.W0))) return r;
     if (n_pts > 0) {
         CK(cudaMemcpyAsync(b->pts.p, pts, (size_t)b->n_frames * n_pts * 16, cudaMemcpyHostToDevice, c->stream));
         c->h2d += (uint64_t)b->n_frames * n_pts * 16;
@@ -1582,14 +1627,8 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
     bool try_pack = imgs && dtype == SLAMKLT_F64 && ld == H && (size_t)nf * H * W >= (1u << 20) && getenv("SLAMKLT_NO_PACK") == nullptr;
     if (try_pack) {
         if ((r = b->h_pack.ensure((size_t)nf * H * W))) return r;
-        if (!c->pool) {
-            int avail = (int)std::thread::hardware_concurrency();
-            cpu_set_t set;
-            if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
-            const char* e = getenv("SLAMKLT_HOST_THREADS");
-            int want = e ? atoi(e) : std::min(avail, 16);
-            c->pool = new HostPool(std::max(want, 1) - 1);
-        }
+        if ((r = ensure_pool(c))) return r;
+        CK(cudaEventSynchronize(b->ev_pack));   // (slamklt_batch_upload may still be copying out of the repack buffer)
         // rate of the plain copies of this batch's previous step (its events have completed: the step was waited for)
         if (!b->raw_meas.empty()) {
             double ms_sum = 0.0, bytes = 0.0;

@@ -480,8 +480,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 
 // Fused column kernel: [level 0: input conversion + layer store] + Scharr + products + y pass of the sigma=4 filter
 // + [levels < L: y pass of the pyramid blur].  One read of the source column per output column (+2 halo columns per strip).
+// experiment knob: minimum resident 4-warp CTAs per SM the register allocation of k_cols_all is bounded for (0 = unbounded)
+#ifndef COLS_MINB
+#define COLS_MINB 0
+#endif
 template <int K, int SRC, int G>
-__global__ void __launch_bounds__(128) k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
+__global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 1) k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
