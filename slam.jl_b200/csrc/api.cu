@@ -1299,7 +1299,23 @@ static int run_detect(slamklt_ctx* c, DetArgs& a, const void* src, int src_dtype
 }
 
 // Tables the register-tiled detect kernel needs (before detect2_supported is asked).
+// ImageDraw's filled circle (see detect.cu in_disc): largest sy >= 0 with (sy / r)^2 + (dx / r)^2 < 1 in Float64, or -1
+static int disc_half_height_host(int dx, int radius) {
+    int best = -1;
+    for (int sy = 0; sy <= radius; ++sy) {
+        const volatile double vy = (double)sy / (double)radius, vx = (double)dx / (double)radius;
+        const volatile double yy = vy * vy, xx = vx * vx;   // (volatile: the products are rounded before the sum, no contraction)
+        if (yy + xx < 1.0) best = sy; else break;
+    }
+    return best;
+}
+
 static int prep_detect(slamklt_ctx* c, DetArgs& a) {
+    a.sy_valid = 0;
+    if (a.n_cur > 0 && a.radius >= 1 && 2 * a.radius + 1 <= 64) {
+        for (int i = 0; i < 2 * a.radius + 1; ++i) a.sy[i] = (signed char)disc_half_height_host(i - a.radius, a.radius);
+        a.sy_valid = 1;
+    }
     if (a.n_cur > 0 && a.hw == 6) {
         // table of the 2^13 tap-subset sums of the mask blur's y pass (detect.cu, k_detect_cells2): entry `pat` adds the taps whose
         // bit is set in tap order with the same Float64 additions the tap loop performs (adding 0.0 for a clear bit changes nothing)

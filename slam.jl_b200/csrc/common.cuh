@@ -101,6 +101,8 @@ struct DetArgs {
     double kw[33];      // 1-D mask blur weights, length 2*hw+1
     const void* src;    // register-tiled kernel: the staged frames in their own type (src_dtype: SLAMKLT_F64 / _F32 / _U8), converted on load
     int src_dtype, pad2_;
+    signed char sy[64]; // register-tiled kernel, masked: half height of the disc at column offset dx = i - radius (-1 = empty), host-built
+    int sy_valid, pad3_; // 0: the disc is wider than the table (the kernel computes the half heights itself)
     int2* bin_pts;      // register-tiled kernel, masked: per (frame, cell row) the current points within reach (k_detect_bin), or nullptr
     int* bin_cnt;
     const double* ytab; // hw == 6 only: the 2^13 sums of tap subsets (bit t set = tap t included), added in tap order (device)

@@ -99,7 +99,7 @@ __device__ int block_excl_scan(int v, int* s_warp, int& total) {
 // i -> (y, x) with i = y + x*h, exact for i*h < 2^20 (h <= 64): one multiply and a shift instead of an integer division
 struct DivH {
     unsigned magic; int h;
-    __device__ DivH(int h_) : magic((1u << 20) / (unsigned)h_ + 1u), h(h_) {}
+    __device__ constexpr DivH(int h_) : magic((1u << 20) / (unsigned)h_ + 1u), h(h_) {}
     __device__ __forceinline__ void split(int i, int& y, int& x) const { x = (int)(((unsigned)i * magic) >> 20); y = i - x * h; }
 };
 
@@ -571,7 +571,8 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
 
     const size_t img0 = (size_t)f * H * W;   // first element of this frame in a.src
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const DivH dh(h), dw(w);
+    // (the magic numbers of the reference's full cells are compile-time constants; edge cells compute theirs)
+    const DivH dh = (CS && h == CS) ? DivH(CS) : DivH(h), dw = (CS && w == CS) ? DivH(CS) : DivH(w);
     const int npx = h * w;
 
     // halo of the response plane = -inf, so that out-of-cell neighbours never block a maximum.  The plane shares its bytes with
@@ -601,11 +602,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
         const int ncolsd = 2 * a.radius + 1;
         // half height of the disc at every column offset dx, the same for every point: the largest sy with (sy, dx) inside
         // ImageDraw's ellipse test (-1: the column is empty).  A disc wider than the table falls back to the per-item computation.
-        int* const s_sy = s_misc + 16;
-        const bool sy_tab = ncolsd <= 48;
-        if (sy_tab) {
-            for (int i = tid; i < ncolsd; i += DET_THREADS) s_sy[i] = disc_half_height(i - a.radius, a.radius);
-        }
+        const bool sy_tab = a.sy_valid != 0;   // (host-built: the table is the same for every cell of every frame)
         const DivH dcol(ncolsd);
         const int2* const bin = a.bin_pts ? a.bin_pts + ((size_t)f * a.grid_h + gy) * a.n_cur : nullptr;
         const int n_scan = bin ? a.bin_cnt[(size_t)f * a.grid_h + gy] : a.n_cur;
@@ -633,7 +630,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
                 const int X = s_near[2 * k + 1] - 1 + dx;  // 0-based image column
                 const int xx = X - rx0;
                 if (X < 0 || X >= W || xx < 0 || xx >= rw) continue;
-                const int sy = sy_tab ? s_sy[di] : disc_half_height(dx, a.radius);
+                const int sy = sy_tab ? (int)a.sy[di] : disc_half_height(dx, a.radius);
                 if (sy < 0) continue;
                 const int Yc = s_near[2 * k] - 1;
                 const int ra = max(max(Yc - sy, 0) - ry0, 0), rb = min(min(Yc + sy, H - 1) - ry0, rh - 1);
@@ -796,7 +793,11 @@ __global__ void __launch_bounds__(DET_THREADS, DET2_MINB) k_detect_cells2(DetArg
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int q = 0; q < 3; ++q) { sa += A[c][q]; sb += B[c][q]; sc += C[c][q]; }
-            const double resp = ((sa + sc) - sqrt((sa - sc) * (sa - sc) + 4.0 * sb * sb)) / 2.0;
+            // sqrt(0) = 0: a warp whose rows all lie in a flat (masked-out) region skips the Float64 square root, same value
+            const double disc = (sa - sc) * (sa - sc) + 4.0 * sb * sb;
+            double root = 0.0;
+            if (__any_sync(__activemask(), disc != 0.0)) root = sqrt(disc);   // (the last warp's idle lanes are outside this loop)
+            const double resp = ((sa + sc) - root) / 2.0;
             if (y < ye) orow[r] = resp;
 #pragma unroll
             for (int c = 0; c < 3; ++c) { A[c][0] = A[c][1]; B[c][0] = B[c][1]; C[c][0] = C[c][1]; A[c][1] = A[c][2]; B[c][1] = B[c][2]; C[c][1] = C[c][2]; }

@@ -32,8 +32,14 @@ namespace sk {
 #ifndef LKT_TR
 #define LKT_TR 40
 #endif
-#ifndef LKT_MX
-#define LKT_MX 4
+#ifndef LKT_MXL
+#define LKT_MXL 4
+#endif
+#ifndef LKT_MXR
+#define LKT_MXR 4
+#endif
+#ifndef LKT_SLIM
+#define LKT_SLIM 0
 #endif
 // latency experiments: G-table entry requested one stage ahead (LKT_PF_G) / next keypoint's coordinates requested during the
 // last stage of the current one (LKT_PF_PT).  Measured on B200 (forward-backward kernel, 18 CTAs per SM): neither 0.810 ms, table
@@ -51,13 +57,20 @@ struct TmaTile {
     static constexpr int RGU = (W2 + PR - 1) / PR;            // row groups that own window rows (7 of 8 for 19 rows)
     static constexpr int RSPAN = (RGU - 1) * PR + PR + 1;     // tap rows touched (idle row groups alias the last used one)
     static constexpr int CSPAN = PC * 4 + 1;                  // tap columns touched
-    static constexpr int TR = LKT_TR, MX = LKT_MX;
+    static constexpr int TR = LKT_TR, MXL = LKT_MXL, MXR = LKT_MXR;
     static constexpr int MY = (TR - RSPAN) / 2;               // margin above the first tap row when a tile is staged
-    static constexpr int TC = CSPAN + 2 * MX;
+    static constexpr int TC = CSPAN + MXL + MXR;              // margins left / right of the tap columns
     static constexpr int AR = ((RGU * PR + 3 + 3) / 4) * 4;   // template tile rows: RGU*PR read + up to 3 skipped for the 16-byte aligned box start
-    static constexpr int AC = PC * 4;                         // template tile columns in shared memory
-    static constexpr int GC = W2;                             // gradient box columns: columns >= GC of the tile stay zero
-    static constexpr unsigned T_BYTES = TC * TR * 4, I_BYTES = AC * AR * 4, G_BYTES = GC * AR * 8;
+    static constexpr int GC = W2;                             // gradient box columns
+    // LKT_SLIM: the template tiles hold exactly the W2 window columns and the gradient tile W2 + 1 rows (its box start only has
+    // to be even); the patch grid's 20th column / rows past the tile are never used (replaced by zeros with a select), their
+    // loads are clamped or fall on neighbouring tile data.  Otherwise: 20 columns x AR rows with a zero 20th column.
+    static constexpr int AC = LKT_SLIM ? W2 : PC * 4;         // layer (template) tile columns
+    static constexpr int ARG = LKT_SLIM ? W2 + 1 : AR;        // gradient tile rows (float2): its 8-byte rows only need an even box start
+    static constexpr int GSKIP = LKT_SLIM ? 1 : 3;            // mask of the rows skipped in the gradient tile (box start = (r0 - 1) & ~GSKIP)
+    static constexpr int GCS = LKT_SLIM ? GC : PC * 4;        // gradient tile columns in shared memory
+    static constexpr unsigned T_BYTES = TC * TR * 4, I_BYTES = AC * AR * 4, G_BYTES = GC * ARG * 8;
+    static_assert((ARG * 8) % 16 == 0, "gradient box rows");
     static_assert(TR >= RSPAN && TR % 4 == 0 && ((PC * TR) % 32 == 8 || (PC * TR) % 32 == 24) && PR == 3, "tile geometry");
     static_assert(PR * 8 >= W2 && PC * 4 >= W2, "patch grid must cover the window");
 };
@@ -104,7 +117,7 @@ int lk_tma_encode(const PyrGeom& g, float* base, int n_slots, void* host_out, ch
         };
         if (one(&out[l].tgt, base + plane_off(L, DP_I), (cuuint64_t)L.pitch, T::TR, T::TC)) return -1;
         if (one(&out[l].ti, base + plane_off(L, DP_I), (cuuint64_t)L.pitch, T::AR, T::AC)) return -1;
-        if (one(&out[l].tg, base + plane_off(L, DP_GRAD), (cuuint64_t)L.pitch * 2, 2 * T::AR, T::GC)) return -1;
+        if (one(&out[l].tg, base + plane_off(L, DP_GRAD), (cuuint64_t)L.pitch * 2, 2 * T::ARG, T::GC)) return -1;
     }
     return 0;
 }
@@ -231,8 +244,21 @@ __global__ void __launch_bounds__(128) k_lk_gprep(const LKArgs a, GEntry* __rest
 }
 
 // ---- tracking kernel --------------------------------------------------------------------------------------------------------
-// 10 496 bytes: with the 1 KB the hardware reserves per CTA, twenty one-warp CTAs fit the 227 KB of an SM.  The small members sit in
-// the padding between the target tile and the 128-byte aligned template tiles.
+// 10 496 bytes (LKT_SLIM: 9 536 with a 26-column target tile): with the 1 KB the hardware reserves per CTA, twenty (twenty-two)
+// one-warp CTAs fit the 227 KB of an SM.  The small members sit in the padding between the 128-byte aligned tiles.
+#if LKT_SLIM
+template <int W2, int PR, int PC>
+struct __align__(128) LKTmaSmem {
+    using T = TmaTile<W2, PR, PC>;
+    float sI[T::AC][T::AR];
+    __align__(16) double q[2];               // forward result (the backward pass starts from it; the distance gate needs it again)
+    int dsave[4];                            // displacement at the start of the current level (optflow! keeps it when the level fails)
+    __align__(8) uint64_t barT;
+    uint64_t barA;
+    __align__(128) float2 sG[T::GCS][T::ARG];
+    __align__(128) float sT[T::TC][T::TR];
+};
+#else
 template <int W2, int PR, int PC>
 struct __align__(128) LKTmaSmem {
     using T = TmaTile<W2, PR, PC>;
@@ -242,9 +268,10 @@ struct __align__(128) LKTmaSmem {
     __align__(8) uint64_t barT;
     uint64_t barA;
     __align__(128) float sI[T::AC][T::AR];
-    __align__(128) float2 sG[T::AC][T::AR];
+    __align__(128) float2 sG[T::GCS][T::ARG];
 };
-static_assert(sizeof(LKTmaSmem<19, 3, 5>) == 10496, "shared memory budget of the tracking kernel (20 CTAs per SM)");
+static_assert(LKT_MXL + LKT_MXR != 8 || sizeof(LKTmaSmem<19, 3, 5>) == 10496, "shared memory budget of the tracking kernel (20 CTAs per SM)");
+#endif
 
 // Position bookkeeping.  The reference keeps d and c as Float64 vectors; the kernel keeps the current estimate of a level as an
 // integer pixel plus an fp32 fraction in [0, 1): floor / ceil / bilinear weights / tile offsets then need no Float64 arithmetic
@@ -366,7 +393,7 @@ retry:
         float wy = dfy, wx = dfx;
         // ---- target tile around the first iteration's position: its latency overlaps the set-up below
         int ty0 = (fy - up - 1 - T::MY) & ~3;  // the innermost TMA coordinate must be a multiple of 16 bytes (tools/tma_probe.cu)
-        int tx0 = fx - left - 1 - T::MX;
+        int tx0 = fx - left - 1 - T::MXL;
         __syncwarp();
         if (lane == 0) {
             fence_async_smem();
@@ -408,7 +435,7 @@ retry:
                         mbar_expect(&sm.barA, T::I_BYTES + T::G_BYTES);
                         const int ra = (r0 - 1) & ~3;  // 16-byte aligned box start; the lanes skip (r0 - 1) & 3 rows when they read
                         tma_box(&sm.sI[0][0], &LKT_MAPS_A[lvl].ti, ra, c0 - 1, LKT_SLOT_A, &sm.barA);
-                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[lvl].tg, 2 * ra, c0 - 1, LKT_SLOT_A, &sm.barA);
+                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[lvl].tg, 2 * ((r0 - 1) & ~T::GSKIP), c0 - 1, LKT_SLOT_A, &sm.barA);
                     }
                     pendA = true;
                     tmpl_stage = s;
@@ -438,15 +465,20 @@ retry:
                 {
                     const int skip = (r0 - 1) & 3;
                     const float* const tI = &sm.sI[pj0][pi0s] + skip;
-                    const float2* const tGp = &sm.sG[pj0][pi0s] + skip;
+                    const float2* const tGp = &sm.sG[pj0][pi0s] + ((r0 - 1) & T::GSKIP);
+                    // the patch grid's 20th column (last column of the fourth column group) is not part of the 19-column window:
+                    // with slim tiles its loads are redirected to the 19th column and its gradients zeroed
+                    const bool last_ok = !LKT_SLIM || pj0 + PC - 1 < W2;
+                    const int jl = last_ok ? PC - 1 : PC - 2;
 #pragma unroll
                     for (int i = 0; i < PR; ++i) {
                         const bool in_win = pi0 + i < nrows;  // patch rows beyond the window carry real data: their gradients are zeroed
 #pragma unroll
                         for (int q = 0; q < NQT; ++q) tIp[i][q] = make_float2(tI[(2 * q) * AR + i], tI[(2 * q + 1) * AR + i]);
-                        tIl[i] = tI[(PC - 1) * AR + i];
+                        tIl[i] = tI[jl * AR + i];
 #pragma unroll
-                        for (int j = 0; j < PC; ++j) { const float2 gv = tGp[j * AR + i]; tG[i][j] = in_win ? gv : make_float2(0.f, 0.f); }
+                        for (int j = 0; j < PC - 1; ++j) { const float2 gv = tGp[j * T::ARG + i]; tG[i][j] = in_win ? gv : make_float2(0.f, 0.f); }
+                        { const float2 gv = tGp[jl * T::ARG + i]; tG[i][PC - 1] = (in_win && last_ok) ? gv : make_float2(0.f, 0.f); }
                     }
                     if (ncols < T::GC) {  // clipped (or smaller) window: gradient columns beyond it carry real data, zero them
 #pragma unroll
@@ -477,7 +509,7 @@ retry:
                         mbar_expect(&sm.barA, T::I_BYTES + T::G_BYTES);
                         const int ra = (nr0 - 1) & ~3;
                         tma_box(&sm.sI[0][0], &LKT_MAPS_A[lvl - 1].ti, ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
-                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[lvl - 1].tg, 2 * ra, nc0 - 1, LKT_SLOT_A, &sm.barA);
+                        tma_box(&sm.sG[0][0], &LKT_MAPS_A[lvl - 1].tg, 2 * ((nr0 - 1) & ~T::GSKIP), nc0 - 1, LKT_SLOT_A, &sm.barA);
                     }
                     pendA = true;
                     tmpl_stage = s + 1;
@@ -509,7 +541,7 @@ retry:
                     // the estimate walked out of the staged tile (or the window was re-clipped): stage again around it
                     __syncwarp();
                     ty0 = (fy - up - 1 - T::MY) & ~3;
-                    tx0 = fx - left - 1 - T::MX;
+                    tx0 = fx - left - 1 - T::MXL;
                     if (lane == 0) {
                         fence_async_smem();
                         mbar_expect(&sm.barT, T::T_BYTES);
@@ -649,7 +681,7 @@ __global__ void __launch_bounds__(32, MODE == 1 ? LKT_MINB : 16) k_lk_tma(const 
     __shared__ LKTmaSmem<W2, PR, PC> sm;
     const int lane = threadIdx.x;
     // the gradient tile's columns beyond the box are never written by the TMA, nor is the zero row: clear them once
-    for (int i = lane; i < TmaTile<W2, PR, PC>::AC * TmaTile<W2, PR, PC>::AR; i += 32) (&sm.sG[0][0])[i] = make_float2(0.f, 0.f);
+    for (int i = lane; i < TmaTile<W2, PR, PC>::GCS * TmaTile<W2, PR, PC>::ARG; i += 32) (&sm.sG[0][0])[i] = make_float2(0.f, 0.f);
     if (lane == 0) {
         mbar_init1(&sm.barT);
         mbar_init1(&sm.barA);
