@@ -258,6 +258,7 @@ struct slamklt_ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of the pipelined batch step
     cudaStream_t raw_stream = nullptr;   // H2D of the chunks that travel as plain Float64 while host threads repack the others
     double pack_Bps = 0.0, raw_Bps = 0.0;  // measured source bytes per second of the two upload engines (0 = not measured yet)
+    double dbg_begin_ns = 0, dbg_pack_ns = 0, dbg_wait_ns = 0, dbg_end_ns = 0; long long dbg_steps = 0;  // SLAMKLT_VERBOSE: where a step's host time goes
     cudaStream_t d2h_stream = nullptr;   // D2H of the pipelined batch step
     PyrStreams pyr_streams{};            // build DAG: main + two side streams
     cudaStream_t lk_stream = nullptr;    // tracking of chunk k overlaps the build of chunk k+1
@@ -523,6 +524,9 @@ int slamklt_ctx_create(int device, slamklt_ctx** out) {
 
 int slamklt_ctx_destroy(slamklt_ctx* c) {
     if (!c) return 0;
+    if (getenv("SLAMKLT_VERBOSE") && c->dbg_steps > 0)
+        fprintf(stderr, "[slamklt] %lld steps: begin %.3f ms (of which waiting for the repack %.3f, repack busy %.3f), end %.3f ms per step\n", c->dbg_steps,
+                c->dbg_begin_ns / c->dbg_steps * 1e-6, c->dbg_wait_ns / c->dbg_steps * 1e-6, c->dbg_pack_ns / c->dbg_steps * 1e-6, c->dbg_end_ns / c->dbg_steps * 1e-6);
     cudaSetDevice(c->device);
     // every stream of the context may still use the buffers freed below
     cudaStream_t all[] = {c->stream, c->lk_stream, c->copy_stream, c->raw_stream, c->d2h_stream, c->pyr_streams.b, c->pyr_streams.c};
@@ -1803,7 +1807,9 @@ static int batch_pipeline(slamklt_ctx* c, slamklt_batch* b, const void* imgs, in
         if (imgs) {
             if ((r = queue_raw_upto(throughput ? nchunks : k + raw_look))) return r;
             if (chunks[k].how == UP_PACK) {
+                const long long tw0 = now_ns();
                 c->pool->wait();
+                c->dbg_wait_ns += (double)(now_ns() - tw0); c->dbg_pack_ns += (double)(pack_t1.load() - pack_t0);
                 pack_ns += (double)(pack_t1.load() - pack_t0); pack_bytes += (double)n * fbytes;
                 if (pack_bad.load() != 0) {
                     // not 8-bit data: this chunk and every chunk still planned for repacking travel as plain Float64
@@ -1900,7 +1906,9 @@ static int step_begin(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int dt
     // chunks (full grids) win; measured on B200, UInt8 frames: 1.55 ms per step with one chunk against 1.63 with two
     if (throughput && dtype != SLAMKLT_F64) want = 1;
     if (forced > 0) want = forced;
+    const long long t0 = now_ns();
     if ((r = batch_pipeline(c, b, imgs, dtype, ld, frame_stride_bytes, pts, n_pts, sigma, mode, p, out_pts, status, want, throughput))) return r;
+    c->dbg_begin_ns += (double)(now_ns() - t0); c->dbg_steps += 1;
     b->step_pending = true;
     return 0;
 }
@@ -1917,7 +1925,9 @@ int slamklt_batch_step_end(slamklt_ctx* c, slamklt_batch* b) {
     {
         std::lock_guard<std::mutex> lk(c->mu);
         CK(cudaSetDevice(c->device));
+        const long long t0 = now_ns();
         CK(cudaEventSynchronize(b->ev_step_done));
+        c->dbg_end_ns += (double)(now_ns() - t0);
         b->step_pending = false;
         b->lk_pending = false;   // ev_step_done was recorded after the last tracking kernel
         b->quiesced = true;
