@@ -337,3 +337,61 @@ function optical_flow_matching!(map_manager::MapManager, frame, from_pyramid::LK
     end
     nothing
 end
+
+# ---- optional: many frames of a stream per call (INTEGRATION.md §4).  Not used by SLAM.jl's own call sites; a consumer that
+# follows several independent streams keeps one KltStreamBatch per stream and alternates step_begin! / step_end! so that the
+# uploads of one step hide behind the kernels of the other.
+mutable struct KltStreamBatch
+    handle::Ptr{Cvoid}
+    H::Int; W::Int; n_frames::Int; max_points::Int
+    keep::Any    # buffers of the step in flight (they must stay alive and untouched until step_end!)
+    function KltStreamBatch(H::Integer, W::Integer, levels::Integer, n_frames::Integer, max_points::Integer)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        _ck(ccall((:slamklt_batch_create, libslamklt), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                  klt_ctx().handle, H, W, levels, n_frames, max_points, h))
+        b = new(h[], H, W, n_frames, max_points, nothing)
+        finalizer(b -> ccall((:slamklt_batch_destroy, libslamklt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), klt_ctx().handle, b.handle), b)
+        b
+    end
+end
+
+"first frame of the stream (slot 0 of the batch)"
+function prime!(b::KltStreamBatch, image::AbstractMatrix; σ = 1.0)
+    img = reinterpret(Float64, image)
+    GC.@preserve img _ck(ccall((:slamklt_batch_prime, libslamklt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cdouble, Cint),
+                               klt_ctx().handle, b.handle, pointer(img), SLAMKLT_F64, b.H, σ, SLAMKLT_MODE_UPDATE))
+    b
+end
+
+"""
+    step_begin!(batch, frames, keypoints, alg; max_distance, σ)
+
+`frames`: H × W × n_frames array of `Gray{Float64}` / `Float64` (the next n_frames images of the stream), `keypoints`: n × n_frames
+matrix of `Point2f` (the points to track from frame i-1 to frame i).  Queues upload, pyramid construction (`update!`), forward-backward
+tracking and the result copies; returns at once.  `step_end!` returns `(new_keypoints, status)` like `fb_tracking!` does per frame.
+"""
+function step_begin!(b::KltStreamBatch, frames::AbstractArray{<:Any, 3}, keypoints::AbstractMatrix{Point2f}, alg::LucasKanade;
+                     max_distance = 1.0, σ = 1.0)
+    img = reinterpret(Float64, frames)
+    n = size(keypoints, 1)
+    new_keypoints = similar(keypoints)
+    status = Vector{UInt8}(undef, n * b.n_frames)
+    prm = Ref(SlamKltLKParams(alg.iterations, alg.window_size, alg.pyramid_levels, 0, alg.eigenvalue_threshold, alg.ϵ, max_distance))
+    b.keep = (img, keypoints, new_keypoints, status, prm)
+    _ck(ccall((:slamklt_batch_step_begin, libslamklt), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Csize_t, Ptr{Float64}, Cint, Cdouble, Cint, Ref{SlamKltLKParams}, Ptr{Float64},
+               Ptr{UInt8}),
+              klt_ctx().handle, b.handle, pointer(img), SLAMKLT_F64, b.H, b.H * b.W * 8, pointer(keypoints), n, σ, SLAMKLT_MODE_UPDATE, prm,
+              pointer(new_keypoints), pointer(status)))
+    b
+end
+
+function step_end!(b::KltStreamBatch)
+    _ck(ccall((:slamklt_batch_step_end, libslamklt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), klt_ctx().handle, b.handle))
+    _, keypoints, new_keypoints, status, _ = b.keep
+    b.keep = nothing
+    new_keypoints, reshape((status .& 0x01) .!= 0, size(keypoints))
+end
+
+"one synchronous step"
+step!(b::KltStreamBatch, frames, keypoints, alg::LucasKanade; kw...) = (step_begin!(b, frames, keypoints, alg; kw...); step_end!(b))
