@@ -1956,7 +1956,8 @@ int slamklt_batch_process(slamklt_ctx* c, slamklt_batch* b, double sigma, int mo
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     // measured on B200: chunking a device-resident batch only shrinks the grids (2.57 vs 2.30 ms per 64 frames), so one chunk
-    return batch_pipeline(c, b, nullptr, b->up_dtype, b->up_ld, 0, nullptr, b->n_pts, sigma, mode, p, nullptr, nullptr, 1);
+    static const int chunks = [] { const char* e = getenv("SLAMKLT_PROCESS_CHUNKS"); return e ? std::max(1, atoi(e)) : 1; }();  // experiment knob
+    return batch_pipeline(c, b, nullptr, b->up_dtype, b->up_ld, 0, nullptr, b->n_pts, sigma, mode, p, nullptr, nullptr, chunks);
 }
 
 int slamklt_batch_slot(slamklt_batch* b, int slot, slamklt_pyr** out) {
