@@ -269,7 +269,7 @@ struct slamklt_ctx {
     unsigned work_idx = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0;
     DevBuf staging, img64, pts, disp, outp, status, cell_out, cell_cnt, det_out, det_n, det_bin, cur, match, gtab;
-    HostBuf h_out, h_status, h_misc;
+    HostBuf h_out, h_status, h_misc, h_pack1;
     HostPool* pool = nullptr;  // created on first use
     std::map<std::pair<int, long long>, float*> norm_cache;  // (n, sigma bits) -> device 1/norm
     std::map<long long, double*> ytab_cache;                 // (first mask-blur tap bits) -> device table of tap-subset sums (detect)
@@ -535,7 +535,7 @@ int slamklt_ctx_destroy(slamklt_ctx* c) {
     for (auto& kv : c->ytab_cache) cudaFree(kv.second);
     DevBuf* bufs[] = {&c->staging, &c->img64, &c->pts, &c->disp, &c->outp, &c->status, &c->cell_out, &c->cell_cnt, &c->det_out, &c->det_n, &c->det_bin, &c->cur, &c->match, &c->gtab};
     for (DevBuf* b : bufs) b->release();
-    c->h_out.release(); c->h_status.release(); c->h_misc.release();
+    c->h_out.release(); c->h_status.release(); c->h_misc.release(); c->h_pack1.release();
     delete c->pool;
     for (auto& pe : c->prof_ev) cudaEventDestroy(pe.second);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -719,6 +719,34 @@ static int build_frames(slamklt_ctx* c, FrameSet fs, int f0, int n_frames, const
     return 0;
 }
 
+// One Float64 frame that holds 8-bit data (Gray{Float64}.(load(png)), example/kitty/main.jl:36-40) is repacked to one byte per pixel by
+// the worker pool and copied to c->staging as UInt8: lossless (the device rebuilds the identical Float64), and a pageable 3.7 MB frame
+// otherwise goes through the driver's staged copy.  Measured on the bench host: update! of a pageable KITTI frame 0.30 -> 0.15 ms.
+// *packed = false: nothing was copied (not Float64, too small, not 8-bit data, or switched off) and the caller uploads as usual.
+static int upload_one_repacked(slamklt_ctx* c, const void* img, int dtype, int ld, int H, int W, bool* packed) {
+    *packed = false;
+    const size_t npx = (size_t)H * W;
+    static const bool no_pack1 = getenv("SLAMKLT_NO_PACK1") != nullptr;
+    if (dtype != SLAMKLT_F64 || ld != H || npx < (1u << 17) || no_pack1 || getenv("SLAMKLT_NO_PACK") != nullptr) return 0;
+    int r;
+    if ((r = c->h_pack1.ensure(npx))) return r;
+    if ((r = c->staging.ensure(npx * 8))) return r;
+    if ((r = ensure_pool(c))) return r;
+    std::atomic<int> bad{0};
+    uint8_t* hp = (uint8_t*)c->h_pack1.p;   // (free again: every earlier user of this buffer waited for its copy)
+    const int cols = 16, blocks = (W + cols - 1) / cols;
+    c->pool->start(blocks, [=, &bad](int item) {
+        const int x0 = item * cols, x1 = std::min(W, x0 + cols);
+        if (!pack_u8_exact((const double*)img + (size_t)x0 * H, hp + (size_t)x0 * H, (size_t)(x1 - x0) * H)) bad.store(1);
+    });
+    c->pool->wait();
+    if (bad.load() != 0) return 0;
+    CK(cudaMemcpyAsync(c->staging.p, hp, npx, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += npx;
+    *packed = true;
+    return 0;
+}
+
 int slamklt_pyr_build(slamklt_ctx* c, slamklt_pyr* p, const void* img, int dtype, int ld, double sigma, int mode) {
     if (!c || !p || !img) return fail(SLAMKLT_E_INVALID, "NULL argument");
     if (dtype < 0 || dtype > 2) return fail(SLAMKLT_E_INVALID, "unknown dtype %d", dtype);
@@ -726,8 +754,12 @@ int slamklt_pyr_build(slamklt_ctx* c, slamklt_pyr* p, const void* img, int dtype
     if (ld < p->g.H0) return fail(SLAMKLT_E_INVALID, "ld %d < H %d", ld, p->g.H0);
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
-    int r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, p->g.H0, p->g.W0);
-    if (r) return r;
+    int r;
+    const int H = p->g.H0, W = p->g.W0;
+    bool packed = false;
+    if ((r = upload_one_repacked(c, img, dtype, ld, H, W, &packed))) return r;
+    if (packed) dtype = SLAMKLT_U8;
+    if (!packed && (r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
     r = build_frames(c, fs_of(p), 0, 1, p->g, c->staging.p, dtype, sigma, mode, nullptr);
     if (r) return r;
     CK(cudaStreamSynchronize(c->stream));  // the caller may free img right after the call
@@ -1358,8 +1390,14 @@ int slamklt_detect(slamklt_ctx* c, const void* img, int dtype, int H, int W, int
     if (r) return r;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
-    if ((r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
     if ((r = prep_detect(c, a))) return r;
+    {
+        // (the register-tiled kernel reads UInt8 frames directly: the repacked upload applies whenever it covers the request)
+        bool packed = false;
+        if (detect2_supported(a) && (r = upload_one_repacked(c, img, dtype, ld, H, W, &packed))) return r;
+        if (packed) dtype = SLAMKLT_U8;
+        else if ((r = upload_frames(c, c->staging, img, dtype, ld, 0, 1, H, W))) return r;
+    }
     const void* d_img;
     int d_type = dtype;
     if (dtype == SLAMKLT_F64 || detect2_supported(a)) d_img = c->staging.p;  // (the register-tiled kernel converts on load)
@@ -1487,7 +1525,7 @@ int slamklt_batch_upload(slamklt_ctx* c, slamklt_batch* b, const void* imgs, int
     const int H = b->g.H0, W = b->g.W0, nf = b->n_frames;
     const size_t npx = (size_t)H * W;
     bool packed = false;
-    if (dtype == SLAMKLT_F64 && ld == H && (frame_stride_bytes == npx * 8 || nf == 1) && (size_t)nf * npx >= (1u << 20) &&
+    if (dtype == SLAMKLT_F64 && ld == H && (frame_stride_bytes == npx * 8 || nf == 1) && (size_t)nf * npx >= (1u << 17) &&
         getenv("SLAMKLT_NO_PACK") == nullptr) {
         if ((r = b->h_pack.ensure((size_t)nf * npx))) return r;
         if ((r = b->staging.ensure((size_t)nf * npx * 8))) return r;
