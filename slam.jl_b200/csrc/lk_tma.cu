@@ -387,7 +387,10 @@ retry:
         const int H = a.lv[lvl].H, W = a.lv[lvl].W;
         const int py = iy0 >> lvl, px = ix0 >> lvl;  // floor(p / 2^lvl) (lucas_kanade.jl:197): floor(floor(p) / 2^lvl)
         if (MODE == 0 && lane == 0) { sm.dsave[0] = diy; sm.dsave[1] = __float_as_int(dfy); sm.dsave[2] = dix; sm.dsave[3] = __float_as_int(dfx); }
-        if (!((unsigned)(py - 1) < (unsigned)H && (unsigned)(px - 1) < (unsigned)W)) { ok = false; break; }  // empty window
+        // A keypoint closer than 2^lvl to the top / left border has level coordinate 0: get_offsets then gives up (left) = -1 and the
+        // window covers rows (columns) 1 .. down -- a valid window one pixel off the point (lucas_kanade.jl:199-212), reachable only
+        // with an initial displacement that brings the estimate into the level.  Everything below takes up / left = -1 as it comes.
+        if (!((unsigned)py <= (unsigned)H && (unsigned)px <= (unsigned)W)) { ok = false; break; }
         int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
         int fy = py + diy, fx = px + dix;  // the estimate is (fy + wy, fx + wx)
         float wy = dfy, wx = dfx;
@@ -414,8 +417,9 @@ retry:
             // get_offsets(p, pc) keeps the offsets of get_offsets(p, p) while floor(pc) >= min(p, w + 1) and
             // ceil(pc) <= max(p, size - w) (lucas_kanade.jl:199-208); a window that was re-clipped has no such box
             const int ty_lo = ty0 + up + 1, tx_lo = tx0 + left + 1;
-            const int ylo = max(min(py, w + 1), ty_lo), yhi = min(max(py, H - w) - 1, ty_lo + (TR - T::RSPAN));
-            const int xlo = max(min(px, w + 1), tx_lo), xhi = min(max(px, W - w) - 1, tx_lo + (TC - T::CSPAN));
+            // (the floor of an estimate inside the level is >= 1: explicit for level coordinates 0, where min(p, w + 1) = 0)
+            const int ylo = max(max(min(py, w + 1), 1), ty_lo), yhi = min(max(py, H - w) - 1, ty_lo + (TR - T::RSPAN));
+            const int xlo = max(max(min(px, w + 1), 1), tx_lo), xhi = min(max(px, W - w) - 1, tx_lo + (TC - T::CSPAN));
             const bool some = orig_offsets && yhi >= ylo && xhi >= xlo;
             bylo = some ? ylo : 0x40000000; byspan = some ? yhi - ylo : 0;
             bxlo = some ? xlo : 0x40000000; bxspan = some ? xhi - xlo : 0;

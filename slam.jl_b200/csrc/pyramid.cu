@@ -484,8 +484,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 #ifndef COLS_MINB
 #define COLS_MINB 0
 #endif
+#ifndef COLS_MINB_TALL
+#define COLS_MINB_TALL 0
+#endif
 template <int K, int SRC, int G>
-__global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 1) k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
+__global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : ((K >= 24 && COLS_MINB_TALL > 0) ? COLS_MINB_TALL : 1))
+    k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
