@@ -513,3 +513,60 @@ def test_detect_parameter_sweep(ctx, seed):
     for im in (img, img_u8):
         kg = slamklt.detect(ctx, slamklt.Extractor(*args), im, cur, sigma_mask=sig, min_response=min_resp)
         assert ko.shape == kg.shape and np.array_equal(ko, kg), (seed, (H, W), args, sig, n_cur, min_resp, im.dtype, len(ko), len(kg))
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("SLAMKLT_SWEEP_SEEDS", "8"))))
+def test_matching_parameter_sweep(ctx, seed):
+    """Randomised sweep over `optical_flow_matching!` as one device call (map_manager.jl:451-590): image shape, number of keypoints
+    (odd counts too), share of 3-D keypoints / wrong map points / projections outside the image, prior noise, depth of both
+    passes, window, gate distance, mono and stereo (epipolar gate).  In-image decisions exact, flags >= 99.9 % (or all but one),
+    pixels within 0.01 px on >= 99.9 % (or all but one) of the keypoints both sides updated."""
+    rng = np.random.default_rng(3100 + seed)
+    stereo = bool(seed % 2)
+    H, W = int(rng.integers(120, 380)), int(rng.integers(200, 900))
+    levels = int(rng.integers(1, 4))
+    levels3d = int(rng.integers(0, levels + 1))
+    window = int(rng.choice([5, 7, 9, 9, 11]))
+    n = int(rng.choice([1, 37, 255, 600, 1001]))
+    md = float(rng.choice([0.5, 1.0, 2.0]))
+    epi = float(rng.choice([1.0, 2.0, 4.0]))
+    if stereo:   # a rectified pair (KITTI size): the match moves along the row by the disparity
+        H, W = 376, 1241
+        l, r, disp_map = synth.stereo_pair(5300 + seed)
+        f = synth.to_f64(np.stack([l, r]))
+        pts = synth.random_keypoints(60 + seed, n, H, W, border=float(rng.choice([2.0, 12.0, 45.0])))
+        dd = disp_map[np.clip(np.rint(pts[:, 0]).astype(int) - 1, 0, H - 1), np.clip(np.rint(pts[:, 1]).astype(int) - 1, 0, W - 1)]
+        gt = pts - np.stack([np.zeros(n), dd], axis=1)
+    else:
+        fr, aff = synth.make_sequence(6100 + seed, 2, H=H, W=W)
+        f = synth.to_f64(fr)
+        pts = synth.random_keypoints(60 + seed, n, H, W, border=float(rng.choice([0.0, 2.0, 12.0])))
+        gt = synth.true_flow(aff, 0, 1, pts)
+    cam = dict(synth.KITTI_CAMERA, cx=W / 2 + 3.3, cy=H / 2 - 1.7, height=H, width=W)
+    sc = synth.matching_scene(800 + seed, pts, gt, camera=cam, baseline=0.54 if stereo else 0.0, frac_3d=float(rng.uniform(0.0, 1.0)),
+                              frac_bad=float(rng.uniform(0.0, 0.5)), frac_outside=float(rng.uniform(0.0, 0.2)), prior_noise=float(rng.uniform(0.0, 1.5)))
+    o0, o1 = O.LKPyramid(f[0], levels), O.LKPyramid(f[1], levels); o0.update(f[0]); o1.update(f[1])
+    g0, g1 = slamklt.LKPyramid(ctx, f[0], levels), slamklt.LKPyramid(ctx, f[1], levels); g0.update(f[0]); g1.update(f[1])
+    ocam = O.Camera(**sc["camera"]); orc = O.Camera(**sc["camera"], Ti0=sc["Ti0"])
+    gcam = slamklt.Camera(**sc["camera"]); grc = slamklt.Camera(**sc["camera"], Ti0=sc["Ti0"])
+    und = O.undistort_point(ocam, pts)
+    if stereo:
+        und[:, 0] += rng.choice([0.0, 0.0, 0.0, 1.5 * epi, -1.5 * epi], size=n)
+    e = O.optical_flow_matching(o0, o1, pts, sc["is_3d"], sc["world"], und, sc["cw"], ocam, orc, stereo=stereo, window_size=window,
+                                pyramid_levels=levels, max_distance=md, pyramid_levels_3d=levels3d, epipolar_error=epi)
+    g = slamklt.optical_flow_matching_frame(g0, g1, pts, sc["is_3d"], sc["world"], sc["cw"], gcam, right_camera=grc if stereo else None,
+                                            undistorted=und if stereo else None, stereo=stereo, window_size=window, pyramid_levels=levels,
+                                            pyramid_levels_3d=levels3d, max_distance=md, epipolar_error=epi)
+    (e_pix, e_und, e_pos, e_st), (g_pix, g_und, g_pos, g_st) = e, g
+    info = (seed, stereo, (H, W), levels, levels3d, window, n, md, epi)
+    assert np.array_equal(e_st == 8, g_st == 8), info
+    m = 1 | 4 | 8 | 16
+    assert np.sum((e_st & m) != (g_st & m)) <= max(1, int(0.001 * n)), (info, np.sum((e_st & m) != (g_st & m)))
+    both = ((e_st & m) == (g_st & m)) & ((e_st & 1) == 1)
+    if both.any():
+        d = np.abs(e_pix[both] - g_pix[both]).max(axis=1)
+        assert np.sum(d >= 0.01) <= max(1, int(0.001 * both.sum())) and d.max() < 0.03, (info, d.max(), np.sum(d >= 0.01))
+        ok = (g_st & 1) == 1
+        u = O.undistort_point(orc if stereo else ocam, g_pix[ok])
+        assert np.array_equal(u, g_und[ok]) and np.array_equal(O.backproject(orc if stereo else ocam, u), g_pos[ok]), info
+    assert np.all(np.isnan(g_pix[(g_st & 1) == 0])), info
