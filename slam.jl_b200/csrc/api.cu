@@ -354,7 +354,7 @@ struct slamklt_batch {
     } while (0)
 
 // LK reads up to 32 window columns without predicates; the last plane of an allocation needs that much slack
-static const size_t ALLOC_SLACK = 34 * 1100;
+static size_t alloc_slack(const PyrGeom& g) { return (size_t)34 * std::max<size_t>(1100, (size_t)g.lv[0].pitch + 12); }
 
 static int make_geom(int H, int W, int levels, PyrGeom* g) {
     if (H < 4 || W < 4) return fail(SLAMKLT_E_INVALID, "image %dx%d too small", H, W);
@@ -365,8 +365,8 @@ static int make_geom(int H, int W, int levels, PyrGeom* g) {
     int h = H, w = W;
     for (int l = 0; l < g->nl; ++l) {
         if (h < 4 || w < 4) return fail(SLAMKLT_E_INVALID, "level %d is %dx%d: recursive filter needs more than 3 samples per line", l, h, w);
-        if (pick_K(h) == 0) return fail(SLAMKLT_E_INVALID, "image height %d exceeds the supported 1088", h);
-        if (w > 2048) return fail(SLAMKLT_E_INVALID, "image width %d exceeds the supported 2048", w);
+        // levels with more than 1088 rows or 2048 columns are built by the general kernels of pyramid.cu (level_tiled)
+        if (h > 16384 || w > 16384) return fail(SLAMKLT_E_INVALID, "image %dx%d exceeds the supported 16384 x 16384", h, w);
         LevelGeom& L = g->lv[l];
         // one guard row and one guard column (kept zero) so that LK's weight-0 bilinear tap at H+1 / W+1 stays in bounds
         L.H = h; L.W = w; L.pitch = (h + 1 + 3) & ~3;
@@ -649,9 +649,9 @@ int slamklt_pyr_create(slamklt_ctx* c, int H, int W, int levels, slamklt_pyr** o
     if (r) return r;
     slamklt_pyr* p = new slamklt_pyr();
     p->g = g;
-    cudaError_t e = cudaMalloc(&p->base, (g.frame_elems + ALLOC_SLACK) * sizeof(float));
+    cudaError_t e = cudaMalloc(&p->base, (g.frame_elems + alloc_slack(g)) * sizeof(float));
     if (e != cudaSuccess) { delete p; return fail(SLAMKLT_E_CUDA, "cudaMalloc pyramid failed: %s", cudaGetErrorString(e)); }
-    cudaMemsetAsync(p->base, 0, (g.frame_elems + ALLOC_SLACK) * sizeof(float), c->stream);
+    cudaMemsetAsync(p->base, 0, (g.frame_elems + alloc_slack(g)) * sizeof(float), c->stream);
     p->owns = true;
     r = make_maps(c, g, p->base, 1, &p->d_maps);
     if (r) { cudaFree(p->base); delete p; return r; }
@@ -1431,9 +1431,9 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
     if (r) return r;
     slamklt_batch* b = new slamklt_batch();
     b->g = g; b->n_frames = n_frames; b->n_slots = n_frames + 1; b->slot0 = 0; b->max_pts = max_pts;
-    cudaError_t e = cudaMalloc(&b->base, (g.frame_elems * b->n_slots + ALLOC_SLACK) * sizeof(float));
+    cudaError_t e = cudaMalloc(&b->base, (g.frame_elems * b->n_slots + alloc_slack(g)) * sizeof(float));
     if (e != cudaSuccess) { delete b; return fail(SLAMKLT_E_CUDA, "cudaMalloc batch (%zu bytes) failed: %s", g.frame_elems * sizeof(float) * b->n_slots, cudaGetErrorString(e)); }
-    cudaMemsetAsync(b->base, 0, (g.frame_elems * b->n_slots + ALLOC_SLACK) * sizeof(float), c->stream);
+    cudaMemsetAsync(b->base, 0, (g.frame_elems * b->n_slots + alloc_slack(g)) * sizeof(float), c->stream);
     if ((r = b->pts.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
     if ((r = b->outp.ensure((size_t)n_frames * max_pts * 16 + 16))) return r;
     if ((r = b->status.ensure((size_t)n_frames * max_pts + 16))) return r;
@@ -1453,10 +1453,10 @@ int slamklt_batch_create(slamklt_ctx* c, int H, int W, int levels, int n_frames,
             for (int l = 0; l < g.nl; ++l) { b->ts.off[l] = off; off += 3 * g.lv[l].plane_elems; }
             b->ts.stride = off; b->ts.ring = want;
             const size_t bytes = off * want * sizeof(float);
-            cudaError_t e2 = cudaMalloc(&b->ts.base, bytes + ALLOC_SLACK * sizeof(float));
+            cudaError_t e2 = cudaMalloc(&b->ts.base, bytes + alloc_slack(g) * sizeof(float));
             if (e2 != cudaSuccess) { b->ts.base = nullptr; cudaGetLastError(); }
             else {
-                cudaMemsetAsync(b->ts.base, 0, bytes + ALLOC_SLACK * sizeof(float), c->stream);
+                cudaMemsetAsync(b->ts.base, 0, bytes + alloc_slack(g) * sizeof(float), c->stream);
                 b->build_group = want;
                 set_l2_window(c, b->ts.base, bytes);
             }

@@ -901,6 +901,132 @@ __global__ void k_resize(FrameSet fs, int f0, size_t o_in, int Hi, int Wi, int p
 }
 
 // ----------------------------------------------------------------------------------------------
+// Levels beyond the register-tiled kernels (more than 1088 rows: a lane would own more than 34 rows of a column; more than 2048
+// columns: more than 32 chunks per row) -- portrait 1080p, 4K frames.  Same stages, same planes, written for generality instead of
+// speed: one thread per line runs the recursion sequentially in Float64 (forward pass stored as fp32 in the output plane, backward
+// pass in place), a pointwise kernel forms the Scharr gradients and their products.  Coarser levels that fit go back to the
+// register-tiled kernels.
+// ----------------------------------------------------------------------------------------------
+struct IirGen { double a1, a2, a3, scale, inv1ma, M[9]; };
+
+static IirGen iir_gen(double sigma) {
+    IirGen o;
+    double a[3];
+    iir_design(sigma, a, &o.scale, o.M);
+    o.a1 = a[0]; o.a2 = a[1]; o.a3 = a[2];
+    o.inv1ma = 1.0 / (1.0 - (a[0] + a[1] + a[2]));
+    return o;
+}
+
+// Scharr (pyramid.jl:59,75,98-103; Fill(0) border on the ctor path, replicate on update!) + products: same fp32 expressions as k_cols_all
+__global__ void k_gen_grad(FrameSet fs, int f0, int H, int W, int pitch, int zb, size_t o_in, size_t o_grad, size_t o_t, size_t plane_elems) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x, x = blockIdx.y;
+    if (y >= H) return;
+    float* fb = fs.frame(f0 + blockIdx.z);
+    const float* I = fb + o_in;
+    auto at = [&](int yy, int xx) -> float {
+        if (zb) return (yy < 0 || yy >= H || xx < 0 || xx >= W) ? 0.f : I[yy + (size_t)xx * pitch];
+        yy = min(max(yy, 0), H - 1); xx = min(max(xx, 0), W - 1);
+        return I[yy + (size_t)xx * pitch];
+    };
+    float em[3], ec[3], ep[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { em[k] = at(y - 1 + k, x - 1); ec[k] = at(y - 1 + k, x); ep[k] = at(y - 1 + k, x + 1); }
+    const float s0 = 3.f / 16.f, s1 = 10.f / 16.f;
+    const float gy = s0 * (0.5f * (em[2] - em[0])) + s1 * (0.5f * (ec[2] - ec[0])) + s0 * (0.5f * (ep[2] - ep[0]));
+    const float gx = s0 * (0.5f * (ep[0] - em[0])) + s1 * (0.5f * (ep[1] - em[1])) + s0 * (0.5f * (ep[2] - em[2]));
+    const size_t p = y + (size_t)x * pitch;
+    reinterpret_cast<float2*>(fb + o_grad)[p] = make_float2(gy, gx);
+    float* T = fb + o_t;
+    T[p] = gy * gy; T[p + plane_elems] = gx * gx; T[p + 2 * plane_elems] = gy * gx;
+}
+
+// One thread per line of n elements with element stride es: out = IIR(in) [* inv_n[i]] (MODE 0), or the exclusive prefix sums of
+// IIR(in) along the line into n + 1 elements (MODE 1: out[0] = 0, accumulated in Float64).  in == out is allowed for MODE 0.
+// Lines are numbered fastest-first: line -> (i_line, plane, frame); the line's first element sits at i_line * ls.
+template <int MODE>
+__global__ void k_gen_iir(FrameSet fs, int f0, int n_lines, int nplanes, int n, size_t es, size_t ls, size_t o_in, size_t o_out, size_t plane_elems,
+                          int zb, const float* __restrict__ inv_n, IirGen c) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= n_lines) return;
+    float* fb = fs.frame(f0 + blockIdx.z);
+    const float* in = fb + o_in + (size_t)blockIdx.y * plane_elems + (size_t)il * ls;
+    float* out = fb + o_out + (size_t)blockIdx.y * plane_elems + (size_t)il * ls + (MODE == 1 ? es : 0);
+    const double iminus = zb ? 0.0 : (double)in[0], iplus = zb ? 0.0 : (double)in[(size_t)(n - 1) * es];
+    const double um = iminus * c.inv1ma;
+    // blocks of U elements: the loads of a block are independent of the recursion and of each other (the line is bound by memory
+    // latency, not by the Float64 chain), and a block is read before it is written, so in == out stays legal
+    constexpr int U = 8;
+    double s0 = um, s1 = um, s2 = um;
+    for (int i0 = 0; i0 < n; i0 += U) {
+        float xv[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) xv[k] = i0 + k < n ? in[(size_t)(i0 + k) * es] : 0.f;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (i0 + k < n) {
+                const double u = (double)xv[k] + c.a1 * s0 + c.a2 * s1 + c.a3 * s2;
+                out[(size_t)(i0 + k) * es] = (float)u;
+                s2 = s1; s1 = s0; s0 = u;
+            }
+        }
+    }
+    // right boundary (Triggs & Sdika): (v[n-1], v[n], v[n+1]) from the last three forward values
+    const double up = iplus * c.inv1ma, vp = up * c.inv1ma;
+    const double d0 = s0 - up, d1 = s1 - up, d2 = s2 - up;
+    double t0 = c.M[0] * d0 + c.M[1] * d1 + c.M[2] * d2 + vp;
+    double t1 = c.M[3] * d0 + c.M[4] * d1 + c.M[5] * d2 + vp;
+    double t2 = c.M[6] * d0 + c.M[7] * d1 + c.M[8] * d2 + vp;
+    {
+        float v = (float)(t0 * c.scale);
+        if (MODE == 0 && inv_n) v *= inv_n[n - 1];
+        out[(size_t)(n - 1) * es] = v;
+    }
+    for (int i1 = n - 2; i1 >= 0; i1 -= U) {   // elements i1, i1 - 1, ..., i1 - U + 1
+        float xv[U], nv[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            xv[k] = i1 - k >= 0 ? out[(size_t)(i1 - k) * es] : 0.f;
+            nv[k] = (MODE == 0 && inv_n && i1 - k >= 0) ? inv_n[i1 - k] : 1.f;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (i1 - k >= 0) {
+                const double v = (double)xv[k] + c.a1 * t0 + c.a2 * t1 + c.a3 * t2;
+                t2 = t1; t1 = t0; t0 = v;
+                float o = (float)(v * c.scale);
+                if (MODE == 0 && inv_n) o *= nv[k];
+                out[(size_t)(i1 - k) * es] = o;
+            }
+        }
+    }
+    if (MODE == 1) {
+        double run = 0.0;
+        for (int i0 = 0; i0 < n; i0 += U) {
+            float xv[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) xv[k] = i0 + k < n ? out[(size_t)(i0 + k) * es] : 0.f;
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (i0 + k < n) { run += (double)xv[k]; out[(size_t)(i0 + k) * es] = (float)run; }
+            }
+        }
+    }
+}
+
+// line filters of one level: along y (lines = columns) or along x (lines = rows)
+static void gen_iir(cudaStream_t s, FrameSet fs, int f0, int n_frames, const LevelGeom& L, bool along_y, int mode, int nplanes, size_t o_in, size_t o_out,
+                    bool zb, const float* inv_n, double sigma) {
+    const int n_lines = along_y ? L.W : L.H, n = along_y ? L.H : L.W;
+    const size_t es = along_y ? 1 : (size_t)L.pitch, ls = along_y ? (size_t)L.pitch : 1;
+    const int threads = along_y ? 32 : 128;  // columns are read with a stride: few lines per CTA keep their cache lines resident
+    dim3 grid((n_lines + threads - 1) / threads, nplanes, n_frames);
+    const IirGen c = iir_gen(sigma);
+    if (mode == 1) k_gen_iir<1><<<grid, threads, 0, s>>>(fs, f0, n_lines, nplanes, n, es, ls, o_in, o_out, L.plane_elems, zb ? 1 : 0, inv_n, c);
+    else k_gen_iir<0><<<grid, threads, 0, s>>>(fs, f0, n_lines, nplanes, n, es, ls, o_in, o_out, L.plane_elems, zb ? 1 : 0, inv_n, c);
+}
+
+// ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
 int pick_K(int H) {
@@ -909,6 +1035,11 @@ int pick_K(int H) {
     for (int k : ks)
         if (k >= need) return k;
     return 0;
+}
+
+// does the level fit the register-tiled kernels?  (SLAMKLT_FORCE_GENERIC=1 sends every level through the general kernels: tests)
+static bool level_tiled(const LevelGeom& L) {
+    return pick_K(L.H) != 0 && L.W <= 2048 && getenv("SLAMKLT_FORCE_GENERIC") == nullptr;
 }
 
 template <int K>
@@ -1125,6 +1256,41 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
     for (int l = 0; l < g.nl; ++l) {
         const LevelGeom& L = g.lv[l];
         const bool blur = l + 1 < g.nl;
+        if (!level_tiled(L)) {
+            // general kernels, all on the main stream: [conversion] -> gradients + products -> sigma = 4 along y (in place) -> along x
+            // with the row prefix sums -> [pyramid blur along y, along x -> decimation]
+            if (l == 0 && raw) {
+                mark(hk, "k_convert");
+                dim3 cgrid((L.H + 127) / 128, L.W, n_frames);
+                const size_t st = (size_t)g.H0 * g.W0, oI = plane_off(L, DP_I);
+                if (dtype == SLAMKLT_F64) k_convert<double><<<cgrid, 128, 0, sA>>>((const double*)raw, g.H0, st, fs, f0, oI, L.H, L.W, L.pitch, nullptr);
+                else if (dtype == SLAMKLT_F32) k_convert<float><<<cgrid, 128, 0, sA>>>((const float*)raw, g.H0, st, fs, f0, oI, L.H, L.W, L.pitch, nullptr);
+                else k_convert<uint8_t><<<cgrid, 128, 0, sA>>>((const uint8_t*)raw, g.H0, st, fs, f0, oI, L.H, L.W, L.pitch, nullptr);
+                launches += 1;
+            }
+            snprintf(nm, sizeof(nm), "k_gen_grad_L%d", l); mark(hk, nm);
+            k_gen_grad<<<dim3((L.H + 127) / 128, L.W, n_frames), 128, 0, sA>>>(fs, f0, L.H, L.W, L.pitch, ctor ? 1 : 0, plane_off(L, DP_I),
+                                                                              plane_off(L, DP_GRAD), plane_off(L, DP_T0), L.plane_elems);
+            snprintf(nm, sizeof(nm), "k_gen_iir_y_L%d", l); mark(hk, nm);
+            gen_iir(sA, fs, f0, n_frames, L, true, 0, 3, plane_off(L, DP_T0), plane_off(L, DP_T0), false, nullptr, 4.0);
+            snprintf(nm, sizeof(nm), "k_gen_iir_x_prefix_L%d", l); mark(hk, nm);
+            gen_iir(sA, fs, f0, n_frames, L, false, 1, 3, plane_off(L, DP_T0), plane_off(L, DP_RYY), false, nullptr, 4.0);
+            launches += 3;
+            if (blur) {
+                const LevelGeom& N = g.lv[l + 1];
+                snprintf(nm, sizeof(nm), "k_gen_blur_y_L%d", l); mark(hk, nm);
+                gen_iir(sA, fs, f0, n_frames, L, true, 0, 1, plane_off(L, DP_I), plane_off(L, DP_TMP), ctor, ctor ? inv_ny[l] : nullptr, sigma);
+                snprintf(nm, sizeof(nm), "k_gen_blur_x_L%d", l); mark(hk, nm);
+                gen_iir(sA, fs, f0, n_frames, L, false, 0, 1, plane_off(L, DP_TMP), plane_off(L, DP_BLUR), ctor, ctor ? inv_nx[l] : nullptr, sigma);
+                snprintf(nm, sizeof(nm), "k_resize_L%d", l); mark(hk, nm);
+                const int nby = (N.H + 127) / 128;
+                const int rthreads = (((N.H + nby - 1) / nby) + 31) / 32 * 32;
+                k_resize<<<dim3(nby, (N.W + RESIZE_CPB - 1) / RESIZE_CPB, n_frames), rthreads, 0, sA>>>(
+                    fs, f0, plane_off(L, DP_BLUR), L.H, L.W, L.pitch, plane_off(N, DP_I), N.H, N.W, N.pitch);
+                launches += 3;
+            }
+            continue;
+        }
         const int K = pick_K(L.H);
         IirDev c4, c1;
         iir_dev(4.0, K, krow_of(L.W), &c4);  // lucas_kanade.jl:112
@@ -1206,6 +1372,11 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
 // scratch plane into DP_TMP (the pyramid itself only keeps the row-prefix form)
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk) {
     const LevelGeom& L = g.lv[level];
+    if (!level_tiled(L)) {
+        mark(hk, "k_gen_iir_x_plain");
+        gen_iir(s, fs, f0, 1, L, false, 0, 1, plane_off(L, DP_T0 + which), plane_off(L, DP_TMP), false, nullptr, 4.0);
+        return 1;
+    }
     IirDev c;
     iir_dev(4.0, pick_K(L.H), krow_of(L.W), &c);
     RowArgs ra{};
