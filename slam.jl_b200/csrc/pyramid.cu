@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -170,12 +171,21 @@ __device__ __forceinline__ void mat3_acc(const float* __restrict__ P, float r0, 
 // The line is extended to the full 32*K elements with its border value (x[n-1] for replicate, 0 for Fill(0)): the
 // Triggs-Sdika boundary is exactly the constant-extension assumption, so the result on [0, n) is unchanged while
 // every lane becomes a full chunk and no per-element predicate is needed.
-template <int K, int NL, int G = 1>
-__device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, const int lane, const IirDev& c, const bool zero_border) {
-    const int y0 = lane * K;
+// HV = 2: the line is shared by a pair of warps (half 0: elements [0, 32 K), half 1: [32 K, 64 K); the launcher guarantees
+// n > 32 K, so the line ends in half 1).  Each half scans its own chunks; after the forward scan half 0 hands the true state at
+// its end to half 1, whose lane l adds A^(K (l + 1)) times that state (table PL, one 3 x 3 matrix per lane); after the backward
+// scan half 1 hands the state at its start to half 0, whose lane l adds A^(K (32 - l)) times it.  Two 64-thread named barriers
+// per call; the exchange buffers xch (18 floats per pair) are separate for the two directions, so calls can follow each other.
+__device__ __forceinline__ void pair_sync(int bar) { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+
+template <int K, int NL, int G = 1, int HV = 1>
+__device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, const int lane, const IirDev& c, const bool zero_border,
+                                               const int half = 0, float* xch = nullptr, const float* __restrict__ PL = nullptr, const int bar = 0) {
+    const bool first_half = HV == 1 || half == 0, last_half = HV == 1 || half == 1;
+    const int y0 = (HV == 2 ? half * 32 + lane : lane) * K;
     const int jl = n - 1 - y0;  // slot of the last element of the line, if it lives in this lane
     const float a1 = c.a1, a2 = c.a2, a3 = c.a3;
-    const int ln = (n - 1) / K;
+    const int ln = ((n - 1) / K) & 31;
     float um[NL], iplus[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -203,7 +213,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
     // forward, phase 1: chunk-local pass (lane 0 starts from the true left boundary state)
     float s0[NL], s1[NL], s2[NL];
 #pragma unroll
-    for (int l = 0; l < NL; ++l) { s0[l] = lane == 0 ? um[l] : 0.f; s1[l] = s0[l]; s2[l] = s0[l]; }
+    for (int l = 0; l < NL; ++l) { s0[l] = (lane == 0 && first_half) ? um[l] : 0.f; s1[l] = s0[l]; s2[l] = s0[l]; }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
 #pragma unroll
@@ -227,10 +237,31 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
             for (int l = 0; l < NL; ++l) mat3_acc(c.P[j], r0[l], r1[l], r2[l], s0[l], s1[l], s2[l]);
         }
     }
+    float sin_[NL][3];  // HV = 2, half 1: the state half 0 ends with
+    if constexpr (HV == 2) {
+        if (half == 0 && lane == 31) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) { xch[3 * l] = s0[l]; xch[3 * l + 1] = s1[l]; xch[3 * l + 2] = s2[l]; }
+        }
+        pair_sync(bar);
+        if (half == 1) {
+            float Pm[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Pm[i] = __ldg(PL + lane * 9 + i);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                sin_[l][0] = xch[3 * l]; sin_[l][1] = xch[3 * l + 1]; sin_[l][2] = xch[3 * l + 2];
+                mat3_acc(Pm, sin_[l][0], sin_[l][1], sin_[l][2], s0[l], s1[l], s2[l]);
+            }
+        }
+    }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         float i0 = __shfl_up_sync(FULL, s0[l], 1), i1 = __shfl_up_sync(FULL, s1[l], 1), i2 = __shfl_up_sync(FULL, s2[l], 1);
-        if (lane == 0) { i0 = um[l]; i1 = um[l]; i2 = um[l]; }
+        if (lane == 0) {
+            if (first_half) { i0 = um[l]; i1 = um[l]; i2 = um[l]; }
+            else if constexpr (HV == 2) { i0 = sin_[l][0]; i1 = sin_[l][1]; i2 = sin_[l][2]; }
+        }
         s0[l] = i0; s1[l] = i1; s2[l] = i2;
     }
     // phase 3: true pass
@@ -264,7 +295,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
         for (int l = 0; l < NL; ++l) {
             float v = fmaf(a1, t0[l], fmaf(a2, t1[l], fmaf(a3, t2[l], x[l][j])));
             t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v;
-            if (j == K - 1 && lane == 31) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
+            if (j == K - 1 && lane == 31 && last_half) { t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
         }
     }
 #pragma unroll
@@ -281,10 +312,31 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
             for (int l = 0; l < NL; ++l) mat3_acc(c.P[j], r0[l], r1[l], r2[l], t0[l], t1[l], t2[l]);
         }
     }
+    float tin_[NL][3];  // HV = 2, half 0: the state half 1 starts with
+    if constexpr (HV == 2) {
+        if (half == 1 && lane == 0) {
+#pragma unroll
+            for (int l = 0; l < NL; ++l) { xch[9 + 3 * l] = t0[l]; xch[9 + 3 * l + 1] = t1[l]; xch[9 + 3 * l + 2] = t2[l]; }
+        }
+        pair_sync(bar);
+        if (half == 0) {
+            float Pm[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Pm[i] = __ldg(PL + (31 - lane) * 9 + i);
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                tin_[l][0] = xch[9 + 3 * l]; tin_[l][1] = xch[9 + 3 * l + 1]; tin_[l][2] = xch[9 + 3 * l + 2];
+                mat3_acc(Pm, tin_[l][0], tin_[l][1], tin_[l][2], t0[l], t1[l], t2[l]);
+            }
+        }
+    }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         float i0 = __shfl_down_sync(FULL, t0[l], 1), i1 = __shfl_down_sync(FULL, t1[l], 1), i2 = __shfl_down_sync(FULL, t2[l], 1);
-        if (lane == 31) { i0 = 0.f; i1 = 0.f; i2 = 0.f; }
+        if (lane == 31) {
+            if (last_half) { i0 = 0.f; i1 = 0.f; i2 = 0.f; }
+            else if constexpr (HV == 2) { i0 = tin_[l][0]; i1 = tin_[l][1]; i2 = tin_[l][2]; }
+        }
         t0[l] = i0; t1[l] = i1; t2[l] = i2;
     }
     const float sc = c.scale;
@@ -293,7 +345,7 @@ __device__ __forceinline__ void warp_iir_lines(float (&x)[NL][K], const int n, c
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
             float v = fmaf(a1, t0[l], fmaf(a2, t1[l], fmaf(a3, t2[l], x[l][j])));
-            if (j == K - 1 && lane == 31) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
+            if (j == K - 1 && lane == 31 && last_half) { v = vr0[l]; t0[l] = vr0[l]; t1[l] = vr1[l]; t2[l] = vr2[l]; }
             else { t2[l] = t1[l]; t1[l] = t0[l]; t0[l] = v; }
             x[l][j] = v * sc;
         }
@@ -325,6 +377,9 @@ struct ColArgs {
     float* t_base;
     size_t t_stride, o_t;
     int t_ring;
+    // two warps per column (k_cols_all<..., HV = 2>): per-lane matrices A^(K (l + 1)) of the sigma = 4 and the blur recursion
+    const float* pl4;
+    const float* pl1;
 };
 
 // One warp per (frame, column).
@@ -427,13 +482,23 @@ __device__ __forceinline__ void load_col_any(const ColArgs& a, const float* __re
     }
 }
 
-// e[0] = row y0-1, e[1..K] = rows y0..y0+K-1, e[K+1] = row y0+K from the lane's own rows x[] (border rule along y applied here)
-template <int K, int G>
-__device__ __forceinline__ void halo_from_col(const float (&x)[K], int y0, int H, int lane, bool zb, float (&e)[K + 2]) {
+// one source element (row y of column xc), converted exactly like load_col_any converts it
+template <int SRC>
+__device__ __forceinline__ float load_px_any(const ColArgs& a, const float* __restrict__ I, int f, int xc, int y) {
+    if constexpr (SRC == 0) return __ldg(I + (size_t)xc * a.pitch + y);
+    else if constexpr (SRC == 1) return (float)__ldg(reinterpret_cast<const double*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld + y);
+    else if constexpr (SRC == 2) return __ldg(reinterpret_cast<const float*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld + y);
+    else return u8_unit(__ldg(reinterpret_cast<const uint8_t*>(a.raw) + (size_t)f * a.raw_stride + (size_t)xc * a.raw_ld + y));
+}
+
+// e[0] = row y0-1, e[1..K] = rows y0..y0+K-1, e[K+1] = row y0+K from the lane's own rows x[] (border rule along y applied here).
+// HV = 2: `cross` is the row on the other side of the boundary between the two halves (row 32 K for half 0, row 32 K - 1 for half 1)
+template <int K, int G, int HV = 1>
+__device__ __forceinline__ void halo_from_col(const float (&x)[K], int y0, int H, int lane, bool zb, float (&e)[K + 2], int half = 0, float cross = 0.f) {
     float upv = __shfl_up_sync(FULL, x[K - 1], 1);
     float dnv = __shfl_down_sync(FULL, x[0], 1);
-    if (lane == 0) upv = zb ? 0.f : x[0];
-    if (lane == 31) dnv = 0.f;
+    if (lane == 0) upv = (HV == 2 && half == 1) ? cross : (zb ? 0.f : x[0]);
+    if (lane == 31) dnv = (HV == 2 && half == 0) ? cross : 0.f;
     e[0] = upv;
 #pragma unroll
     for (int j = 0; j < K; ++j) e[j + 1] = x[j];
@@ -445,20 +510,22 @@ __device__ __forceinline__ void halo_from_col(const float (&x)[K], int y0, int H
     }
 }
 
-template <int K, int SRC, int G = 1>
+template <int K, int SRC, int G = 1, int HV = 1>
 __device__ __forceinline__ void load_col_halo_any(const ColArgs& a, const float* __restrict__ I, int f, int xcol, int y0, int lane, bool zb,
-                                                  float (&e)[K + 2], const RowGroups<K, G>& rg) {
+                                                  float (&e)[K + 2], const RowGroups<K, G>& rg, int half = 0) {
     const int W = a.W, H = a.H;
     float x[K];
+    float cross = 0.f;
     const bool inside = xcol >= 0 && xcol < W;
     if (inside || !zb) {
         const int xc = xcol < 0 ? 0 : (xcol >= W ? W - 1 : xcol);
         load_col_any<K, SRC, G>(a, I, f, xc, y0, x, rg);
+        if constexpr (HV == 2) cross = load_px_any<SRC>(a, I, f, xc, half == 0 ? 32 * K : 32 * K - 1);  // (H > 32 K: both rows exist)
     } else {
 #pragma unroll
         for (int j = 0; j < K; ++j) x[j] = 0.f;
     }
-    halo_from_col<K, G>(x, y0, H, lane, zb, e);
+    halo_from_col<K, G, HV>(x, y0, H, lane, zb, e, half, cross);
 }
 
 // Raw Float64 columns staged through shared memory with cp.async, one column ahead of the column loop: a lane copies its
@@ -487,20 +554,50 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 #ifndef COLS_MINB_TALL
 #define COLS_MINB_TALL 0
 #endif
-template <int K, int SRC, int G>
-__global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : ((K >= 24 && COLS_MINB_TALL > 0) ? COLS_MINB_TALL : 1))
+// two warps per column (HV = 2): resident 4-warp CTAs per SM the register allocation is bounded for
+#ifndef COLS_PAIR_MINB8
+#define COLS_PAIR_MINB8 5
+#endif
+#ifndef COLS_PAIR_MINB12
+#define COLS_PAIR_MINB12 4
+#endif
+#ifndef COLS_PAIR_MINB18
+#define COLS_PAIR_MINB18 3
+#endif
+// rows per lane of the pair kernel for frames taller than 768 rows (18: 94 % of the lanes' rows used at 1080 rows, 8-byte vectors;
+// 20: 84 %, 16-byte vectors).  Measured on B200, 16 frames of 1080 x 1920 (c5), level-0 column kernel: one warp per column (34 rows
+// per lane, 255 registers) 0.699 ms; pairs with 18 rows at 168 registers 0.485 ms, at 128 registers (spills) 0.540 ms; pairs with 20
+// rows at 168 registers 0.362 ms, at 128 registers 0.443 ms.
+// COLS_PAIR_SMALL=1 (experiment) also sends frames of 193 .. 512 rows through pairs (6 or 8 rows per lane).
+#ifndef COLS_PAIR_SMALL
+#define COLS_PAIR_SMALL 0
+#endif
+#ifndef COLS_PAIR_KBIG
+#define COLS_PAIR_KBIG 20
+#endif
+// HV = 2 (frames taller than 512 rows): a pair of warps shares a strip, warp `half` owns rows [32 K half, 32 K (half + 1)) of every
+// column -- K = 12 / 18 rows per lane instead of 24 / 34, half the registers, twice the resident warps.
+template <int K, int SRC, int G, int HV = 1>
+__global__ void __launch_bounds__(128, HV == 2 ? (K <= 8 ? COLS_PAIR_MINB8 : (K <= 12 ? COLS_PAIR_MINB12 : COLS_PAIR_MINB18))
+                                              : ((K <= 12 && COLS_MINB > 0) ? COLS_MINB : ((K >= 24 && COLS_MINB_TALL > 0) ? COLS_MINB_TALL : 1)))
     k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp = HV == 2 ? gwarp >> 1 : gwarp;                                  // strip walker: a warp, or a pair of warps
+    const int nwarps = ((gridDim.x * blockDim.x) >> 5) >> (HV == 2 ? 1 : 0);
+    const int half = HV == 2 ? (gwarp & 1) : 0;
+    const int bar = 1 + ((threadIdx.x >> 6) & 1);                                     // named barrier of this pair (two pairs per CTA)
+    __shared__ float sXch[HV == 2 ? 2 * 2 * 18 : 1];
+    float* const xch4 = sXch + (HV == 2 ? ((threadIdx.x >> 6) & 1) * 36 : 0);      // sigma = 4 filter (3 lines)
+    float* const xch1 = xch4 + (HV == 2 ? 18 : 0);                                    // pyramid blur (1 line)
     const int H = a.H, W = a.W, pitch = a.pitch;
     const int cs = a.strip;  // columns per warp strip (GRAD_CS for large batches, narrower when there are few frames)
     const int strips = (W + cs - 1) / cs;
     const int total = a.n_frames * strips;
-    const int y0 = lane * K;
+    const int y0 = (half * 32 + lane) * K;
     const bool zb = a.zero_border != 0;
     const RowGroups<K, G> rg(y0, H);
-    constexpr bool STAGED = COLS_STAGE && SRC == 1 && G > 1 && K <= 16;
+    constexpr bool STAGED = COLS_STAGE && SRC == 1 && G > 1 && K <= 16 && HV == 1;
     __shared__ __align__(16) double2 sRaw[STAGED ? 4 * 2 * RawStage<K>::STAGE_UNITS : 1];
     double2* const sMine = sRaw + (threadIdx.x >> 5) * 2 * RawStage<K>::STAGE_UNITS + lane * RawStage<K>::LU;
     for (int w = warp; w < total; w += nwarps) {
@@ -522,8 +619,8 @@ __global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 
             }
         };
         stage_issue(xb + 1);
-        load_col_halo_any<K, SRC, G>(a, I, f, xb - 1, y0, lane, zb, em, rg);
-        load_col_halo_any<K, SRC, G>(a, I, f, xb, y0, lane, zb, ec, rg);
+        load_col_halo_any<K, SRC, G, HV>(a, I, f, xb - 1, y0, lane, zb, em, rg, half);
+        load_col_halo_any<K, SRC, G, HV>(a, I, f, xb, y0, lane, zb, ec, rg, half);
         for (int xcol = xb; xcol < xe; ++xcol) {
             if constexpr (STAGED) {
                 float x[K];
@@ -555,7 +652,7 @@ __global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 
 #endif
             }
 #endif
-            load_col_halo_any<K, SRC, G>(a, I, f, xcol + 1, y0, lane, zb, ep, rg);
+            load_col_halo_any<K, SRC, G, HV>(a, I, f, xcol + 1, y0, lane, zb, ep, rg, half);
             }
             float pp[3][K];
             {
@@ -582,7 +679,7 @@ __global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 
                     }
                 }
             }
-            warp_iir_lines<K, 3, G>(pp, H, lane, c4, false);
+            warp_iir_lines<K, 3, G, HV>(pp, H, lane, c4, false, half, xch4, a.pl4, bar);
             float* o0 = (a.t_base ? a.t_base + (size_t)((a.f0 + f) % a.t_ring) * a.t_stride + a.o_t : fb + a.o_out0) + (size_t)xcol * pitch;
             if constexpr (G > 1) {
                 store_col_g<K, G>(o0, y0, rg, pp[0]);
@@ -606,7 +703,7 @@ __global__ void __launch_bounds__(128, (K <= 12 && COLS_MINB > 0) ? COLS_MINB : 
                     if (SRC != 0) store_col<K>(fb + a.o_in + (size_t)xcol * pitch, y0, pitch, H, bl[0]);  // the converted layer
                 }
                 if (a.do_blur) {
-                    warp_iir_lines<K, 1, G>(bl, H, lane, c1, zb);
+                    warp_iir_lines<K, 1, G, HV>(bl, H, lane, c1, zb, half, xch1, a.pl1, bar);
                     if (a.inv_n) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
@@ -1170,35 +1267,84 @@ static int resident_warps_of(Kern kern, int threads) {
     return r;
 }
 
-template <int K, int SRC, int G>
+template <int K, int SRC, int G, int HV>
 static void launch_cols_all_k(cudaStream_t s, ColArgs a, const IirDev& c4, const IirDev& c1) {
     const int wpb = 4;
-    auto kern = k_cols_all<K, SRC, G>;
+    auto kern = k_cols_all<K, SRC, G, HV>;
     static const int forced = [] { const char* e = getenv("SLAMKLT_COLS_STRIP"); return e ? atoi(e) : 0; }();
-    a.strip = forced > 0 ? forced : pick_strip(a.n_frames, a.W, resident_warps_of(kern, wpb * 32));
-    const int total_warps = a.n_frames * ((a.W + a.strip - 1) / a.strip);
-    const int blocks = (total_warps + wpb - 1) / wpb;  // one strip per warp; the hardware hands CTAs to SMs as slots free up
+    a.strip = forced > 0 ? forced : pick_strip(a.n_frames, a.W, resident_warps_of(kern, wpb * 32) / HV);
+    const int total_warps = HV * a.n_frames * ((a.W + a.strip - 1) / a.strip);
+    const int blocks = (total_warps + wpb - 1) / wpb;  // one strip per warp (pair); the hardware hands CTAs to SMs as slots free up
     kern<<<blocks, wpb * 32, 0, s>>>(a, c4, c1);
 }
 
-template <int K, int G>
+template <int K, int G, int HV>
 static void launch_cols_all_g(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
     switch (src) {
-        case 0: launch_cols_all_k<K, 0, G>(s, a, c4, c1); break;
-        case 1: launch_cols_all_k<K, 1, G>(s, a, c4, c1); break;
-        case 2: launch_cols_all_k<K, 2, G>(s, a, c4, c1); break;
-        default: launch_cols_all_k<K, 3, G>(s, a, c4, c1); break;
+        case 0: launch_cols_all_k<K, 0, G, HV>(s, a, c4, c1); break;
+        case 1: launch_cols_all_k<K, 1, G, HV>(s, a, c4, c1); break;
+        case 2: launch_cols_all_k<K, 2, G, HV>(s, a, c4, c1); break;
+        default: launch_cols_all_k<K, 3, G, HV>(s, a, c4, c1); break;
     }
 }
 
-template <int K>
+template <int K, int HV = 1>
 static void launch_cols_all(cudaStream_t s, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
     // group-aligned variant when the image height is a multiple of the row-group size (4 rows, or 2 when K is not a multiple of 4)
     constexpr int GA = (K % 4 == 0) ? 4 : 2;
     const bool aligned = a.H % GA == 0 && (src != 1 || ((a.raw_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.raw) & 15) == 0)) &&
                          getenv("SLAMKLT_COLS_GENERIC") == nullptr;
-    if (aligned) launch_cols_all_g<K, GA>(s, src, a, c4, c1);
-    else launch_cols_all_g<K, 1>(s, src, a, c4, c1);
+    if (aligned) launch_cols_all_g<K, GA, HV>(s, src, a, c4, c1);
+    else launch_cols_all_g<K, 1, HV>(s, src, a, c4, c1);
+}
+
+// Two warps per column for frames taller than 512 rows: rows per lane (0: one warp per column).  SLAMKLT_COLS_PAIR=0 keeps the
+// one-warp kernels (K = 24 / 34 rows per lane, 255 registers).
+static int pick_K_pair(int H) {
+    const char* e = getenv("SLAMKLT_COLS_PAIR");
+    if (e && atoi(e) == 0) return 0;
+#if COLS_PAIR_SMALL
+    if (H > 192 && H <= 384) return 6;
+    if (H > 384 && H <= 512) return 8;
+#endif
+    if (H <= 512) return 0;
+    return H <= 64 * 12 ? 12 : (H <= 64 * COLS_PAIR_KBIG ? COLS_PAIR_KBIG : 0);
+}
+
+// per-lane matrices A^(K (l + 1)), l = 0 .. 31, of the recursion with the given sigma (fp32, row-major 3 x 3), cached on the device
+static const float* lane_powers(double sigma, int K) {
+    static std::map<std::pair<int, std::pair<long long, int>>, float*> cache;  // (device, (sigma bits, K))
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    long long bits;
+    static_assert(sizeof(bits) == sizeof(sigma), "");
+    memcpy(&bits, &sigma, sizeof(bits));
+    auto key = std::make_pair(dev, std::make_pair(bits, K));
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    double a[3], sc, M[9];
+    iir_design(sigma, a, &sc, M);
+    const double A[9] = {a[0], a[1], a[2], 1, 0, 0, 0, 1, 0};
+    double AK[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, P[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    auto mul = [](const double* X, const double* Y, double* Z) {
+        double t[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) { double v = 0; for (int k = 0; k < 3; ++k) v += X[3 * i + k] * Y[3 * k + j]; t[3 * i + j] = v; }
+        for (int i = 0; i < 9; ++i) Z[i] = t[i];
+    };
+    for (int i = 0; i < K; ++i) mul(AK, A, AK);  // A^K
+    std::vector<float> tab(32 * 9);
+    for (int l = 0; l < 32; ++l) {
+        mul(P, AK, P);                           // A^(K (l + 1))
+        for (int i = 0; i < 9; ++i) tab[l * 9 + i] = (float)P[i];
+    }
+    float* d = nullptr;
+    cudaMalloc(&d, tab.size() * sizeof(float));
+    cudaMemcpy(d, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cache[key] = d;
+    return d;
 }
 
 static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
@@ -1212,6 +1358,14 @@ static void dispatch_cols_all(cudaStream_t s, int K, int src, const ColArgs& a, 
         case 24: launch_cols_all<24>(s, src, a, c4, c1); break;
         case 34: launch_cols_all<34>(s, src, a, c4, c1); break;
     }
+}
+static void dispatch_cols_all_pair(cudaStream_t s, int K2, int src, const ColArgs& a, const IirDev& c4, const IirDev& c1) {
+#if COLS_PAIR_SMALL
+    if (K2 == 6) { launch_cols_all<6, 2>(s, src, a, c4, c1); return; }
+    if (K2 == 8) { launch_cols_all<8, 2>(s, src, a, c4, c1); return; }
+#endif
+    if (K2 == 12) launch_cols_all<12, 2>(s, src, a, c4, c1);
+    else launch_cols_all<COLS_PAIR_KBIG, 2>(s, src, a, c4, c1);
 }
 
 // Build the pyramids of n_frames frames.  raw != nullptr: level 0 is read from the staged host image (dtype, compact
@@ -1298,12 +1452,22 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
         ColArgs ca = col_args(l);
         ca.inv_n = (ctor && blur) ? inv_ny[l] : nullptr;
         ca.do_blur = blur;
+        // frames taller than 512 rows: the fused column kernel runs with two warps per column (own scan matrices: K2 rows per lane)
+        const int K2 = pick_K_pair(L.H);
+        IirDev c4p, c1p;
+        if (K2) {
+            iir_dev(4.0, K2, krow_of(L.W), &c4p);
+            iir_dev(sigma, K2, krow_of(L.W), &c1p);
+            ca.pl4 = lane_powers(4.0, K2);
+            ca.pl1 = lane_powers(sigma, K2);
+        }
         if (l == 0 || !par) {
             // fused column kernel on the main stream
             const int src = (l == 0 && raw) ? (dtype == SLAMKLT_F64 ? 1 : (dtype == SLAMKLT_F32 ? 2 : 3)) : 0;
             ca.raw = src ? raw : nullptr;
             snprintf(nm, sizeof(nm), "k_cols_all_L%d", l); mark(hk, nm);
-            dispatch_cols_all(sA, K, src, ca, c4, c1);
+            if (K2) dispatch_cols_all_pair(sA, K2, src, ca, c4p, c1p);
+            else dispatch_cols_all(sA, K, src, ca, c4, c1);
             launches += 1;
             // with a scratch ring the x pass follows on the same stream: the next group's column kernel (also on this stream)
             // overwrites the ring slots, and the planes are still hot in L2
@@ -1318,7 +1482,8 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
             cg.inv_n = nullptr;
             cg.do_blur = 0;  // the fused kernel without its blur half (SRC = 0: nothing to convert)
             snprintf(nm, sizeof(nm), "k_cols_grad_L%d", l); mark(hk, nm);
-            dispatch_cols_all(sC, K, 0, cg, c4, c1);
+            if (K2) dispatch_cols_all_pair(sC, K2, 0, cg, c4p, c1p);
+            else dispatch_cols_all(sC, K, 0, cg, c4, c1);
             launches += 1;
             rows_struct(sC, l, c4);
             if (blur) {

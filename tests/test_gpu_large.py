@@ -119,3 +119,31 @@ def test_batch_step_on_tall_frames(ctx, dtype):
     for i in range(NF):
         assert np.array_equal(kps[i], slamklt.detect(ctx, e, f64[i + 1], pts[i]))
     batch.close()
+
+
+@pytest.mark.parametrize("shape,dtype,mode", [((600, 200), "f64", "update"), ((768, 130), "u8", "ctor"), ((1080, 320), "u8", "update"),
+                                              ((1080, 320), "f64", "ctor"), ((1087, 150), "f64", "update"), ((771, 90), "f32", "ctor"),
+                                              ((1088, 64), "u8", "update")])
+def test_two_warps_per_column(ctx, monkeypatch, shape, dtype, mode):
+    """Frames taller than 512 rows: the fused column kernel runs with two warps per column (12 or 18 rows per lane, states handed
+    across the pair).  Planes against the oracle, and against the one-warp kernels (SLAMKLT_COLS_PAIR=0) on the same frame."""
+    H, W = shape
+    fr, _ = synth.make_sequence(2400 + H + W, 2, H=H, W=W)
+    f = synth.to_f64(fr)
+    src = {"f64": f, "u8": fr, "f32": f.astype(np.float32)}[dtype]
+    ref = f if dtype != "f32" else src.astype(np.float64)
+    L = 2
+    op = O.LKPyramid(ref[0], L, mode="ctor")
+    pair = slamklt.LKPyramid(ctx, src[0], L)
+    monkeypatch.setenv("SLAMKLT_COLS_PAIR", "0")
+    single = slamklt.LKPyramid(ctx, src[0], L)
+    if mode == "update":
+        single.update(src[1])
+    monkeypatch.delenv("SLAMKLT_COLS_PAIR")
+    if mode == "update":
+        op.update(ref[1]); pair.update(src[1])
+    _check_planes(pair, op, L)
+    for l in range(L + 1):
+        for name in PLANES + (("blur",) if l < L else ()):
+            a, b = pair.plane(l, name), single.plane(l, name)
+            assert rel_err(a, b) < 2e-6, (l, name, rel_err(a, b))
