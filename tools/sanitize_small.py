@@ -59,5 +59,16 @@ for _ in range(2):
 bx.detect(slamklt.Extractor(300, 8, (11, 12), 35), np.stack([synth.random_keypoints(90 + i, 40, 376, 400, border=0.0) for i in range(nb)]))
 by.track_cross(bx, alg2); bx.download()
 bx.close(); by.close(); pin.free()
+# round 2c: frames taller than 512 rows (two warps per column: 12 and 20 rows per lane, odd height = per-row predicates, every
+# source type) and levels beyond the tiled kernels (general per-line kernels: tall, wide), tracking on such pyramids
+for (Ht, Wt, src_kind) in ((600, 40, "f64"), (1080, 24, "u8"), (771, 20, "f32"), (1130, 36, "f64"), (40, 2080, "u8")):
+    frt, _ = synth.make_sequence(9, 2, H=Ht, W=Wt)
+    ft = synth.to_f64(frt)
+    srct = {"f64": ft, "u8": frt, "f32": ft.astype(np.float32)}[src_kind]
+    pa = slamklt.LKPyramid(ctx, srct[0], 2)
+    pb = slamklt.LKPyramid(ctx, srct[1], 2); pb.update(srct[1])
+    ptst = synth.random_keypoints(21, 60, Ht, Wt, border=1.0)
+    slamklt.fb_tracking(pa, pb, ptst, window_size=9, pyramid_levels=2, max_distance=1.0)
+    pb.plane(0, "Sxx"); pb.plane(0, "Ryx")
 batch.close(); ctx.close()
 print("sanitize_small done")
