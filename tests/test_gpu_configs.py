@@ -454,8 +454,9 @@ def test_pyramid_parameter_sweep(ctx, seed):
     column-kernel width K and both row-chunk sizes get hit over the seeds), depth, blur sigma, host pixel type, both border regimes.
     Planes within 1e-5 of the oracle in the max norm (north_star), UInt8 / Float32 frames bit-identical to their Float64 image."""
     rng = np.random.default_rng(7300 + seed)
-    H = int(rng.choice([rng.integers(16, 64), rng.integers(64, 200), rng.integers(200, 420), rng.integers(420, 800)]))
-    W = int(rng.choice([rng.integers(16, 120), rng.integers(120, 700), rng.integers(700, 1400)]))
+    # (heights above 512 take the two-warps-per-column kernel, above 1088 / widths above 2048 the general per-line kernels)
+    H = int(rng.choice([rng.integers(16, 64), rng.integers(64, 200), rng.integers(200, 420), rng.integers(420, 800), rng.integers(800, 1300)]))
+    W = int(rng.choice([rng.integers(16, 120), rng.integers(120, 700), rng.integers(700, 1400), rng.integers(1400, 2300)]))
     levels = int(rng.integers(0, 5))
     while levels > 0 and min((H + (1 << levels) - 1) >> levels, (W + (1 << levels) - 1) >> levels) < 4:
         levels -= 1

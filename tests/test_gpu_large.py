@@ -147,3 +147,30 @@ def test_two_warps_per_column(ctx, monkeypatch, shape, dtype, mode):
         for name in PLANES + (("blur",) if l < L else ()):
             a, b = pair.plane(l, name), single.plane(l, name)
             assert rel_err(a, b) < 2e-6, (l, name, rel_err(a, b))
+
+
+def test_batch_step_1080p_equals_single_calls(ctx):
+    """Config 5 geometry through the batched stream API (two warps per column at levels 0 and 1): one step of three 1080p UInt8 frames
+    equals single pyramids + fb_tracking! bit for bit, and the step's tracks agree with the oracle."""
+    H, W, L, NF, NP = 1080, 1920, 5, 3, 1500
+    fr, _ = synth.make_sequence(2500, NF + 1, H=H, W=W)
+    f64 = synth.to_f64(fr)
+    alg = slamklt.LucasKanade(pyramid_levels=L, window_size=9)
+    batch = slamklt.StreamBatch(ctx, H, W, L, NF, NP)
+    batch.prime(fr[0], mode=slamklt.MODE_UPDATE)
+    pts = np.stack([synth.random_keypoints(130 + i, NP, H, W, border=2.0) for i in range(NF)])
+    out, st = batch.step(slamklt.StreamBatch.pack_frames(fr[1:]), pts, alg, max_distance=1.0)
+    prev = slamklt.LKPyramid(ctx, fr[0], L); prev.update(fr[0])
+    for i in range(NF):
+        cur = slamklt.LKPyramid(ctx, fr[i + 1], L); cur.update(fr[i + 1])
+        ref_pts, ref_st, ref_fst = slamklt.fb_tracking(prev, cur, pts[i], window_size=9, pyramid_levels=L, max_distance=1.0)
+        assert np.array_equal(st[i] & 1, ref_st.astype(np.uint8)) and np.array_equal((st[i] >> 1) & 1, ref_fst.astype(np.uint8))
+        assert np.array_equal(out[i][ref_fst], ref_pts[ref_fst])
+        prev = cur
+    o0 = O.LKPyramid(f64[NF - 1], L); o0.update(f64[NF - 1]); o1 = O.LKPyramid(f64[NF], L); o1.update(f64[NF])
+    po, so, fo = O.fb_tracking(o0, o1, pts[NF - 1], window_size=9, pyramid_levels=L, max_distance=1.0)
+    sg = (st[NF - 1] & 1).astype(bool)
+    assert np.mean(so == sg) >= FLAG_AGREE and so.mean() > 0.5
+    both = so & sg
+    assert np.mean(np.abs(po[both] - out[NF - 1][both]).max(axis=1) < POS_TOL) >= FLAG_AGREE
+    batch.close()
