@@ -41,6 +41,11 @@
 #ifndef COLS_PREFETCH_DIST
 #define COLS_PREFETCH_DIST 2
 #endif
+// UInt8 / Float32 / fp32-plane source columns requested one column iteration ahead into registers (K / 4 words for bytes, K for
+// floats): the loads of column x + 2 are in flight while column x is filtered
+#ifndef COLS_REGPF
+#define COLS_REGPF 1
+#endif
 
 namespace sk {
 
@@ -549,7 +554,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 // + [levels < L: y pass of the pyramid blur].  One read of the source column per output column (+2 halo columns per strip).
 // experiment knob: minimum resident 4-warp CTAs per SM the register allocation of k_cols_all is bounded for (0 = unbounded)
 #ifndef COLS_MINB
-#define COLS_MINB 0
+#define COLS_MINB 4
 #endif
 #ifndef COLS_MINB_TALL
 #define COLS_MINB_TALL 0
@@ -618,6 +623,20 @@ __global__ void __launch_bounds__(128, HV == 2 ? (K <= 8 ? COLS_PAIR_MINB8 : (K 
                 cp_async_commit_wait_all(false);
             }
         };
+        // register prefetch (UInt8 source, aligned variant): raw words of the column one iteration ahead
+        constexpr bool PF = COLS_REGPF && SRC == 3 && G >= 4 && K % 4 == 0 && HV == 1;
+        unsigned nxt[PF ? K / 4 : 1];
+        bool nxt_zero = false;
+        auto pf_issue = [&](int c) {
+            if constexpr (PF) {
+                nxt_zero = zb && c >= W;
+                const int cc = c >= W ? W - 1 : c;
+                const uint8_t* col = reinterpret_cast<const uint8_t*>(a.raw) + (size_t)f * a.raw_stride + (size_t)cc * a.raw_ld + y0;
+#pragma unroll
+                for (int v = 0; v < K / 4; ++v) nxt[v] = rg.valid(4 * v) ? __ldg(reinterpret_cast<const unsigned*>(col + 4 * v)) : 0u;
+            }
+        };
+        pf_issue(xb + 1);
         stage_issue(xb + 1);
         load_col_halo_any<K, SRC, G, HV>(a, I, f, xb - 1, y0, lane, zb, em, rg, half);
         load_col_halo_any<K, SRC, G, HV>(a, I, f, xb, y0, lane, zb, ec, rg, half);
@@ -652,6 +671,17 @@ __global__ void __launch_bounds__(128, HV == 2 ? (K <= 8 ? COLS_PAIR_MINB8 : (K 
 #endif
             }
 #endif
+            if constexpr (PF) {
+                float x[K];
+#pragma unroll
+                for (int v = 0; v < K / 4; ++v) {
+                    const unsigned wd = nxt_zero ? 0u : nxt[v];
+                    x[4 * v] = u8_unit(wd & 0xffu); x[4 * v + 1] = u8_unit((wd >> 8) & 0xffu);
+                    x[4 * v + 2] = u8_unit((wd >> 16) & 0xffu); x[4 * v + 3] = u8_unit(wd >> 24);
+                }
+                halo_from_col<K, G>(x, y0, H, lane, zb, ep);
+                if (xcol + 1 < xe) pf_issue(xcol + 2);
+            } else
             load_col_halo_any<K, SRC, G, HV>(a, I, f, xcol + 1, y0, lane, zb, ep, rg, half);
             }
             float pp[3][K];
