@@ -7,8 +7,8 @@ cd "$(dirname "$0")/../slam.jl_b200/csrc"
 name=$1; flags=$2
 mkdir -p variants/obj_$name
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
-for f in lk_tma lk_patch pyramid api lk; do
-  $NV $flags -Xptxas -v -c $f.cu -o variants/obj_$name/$f.o 2> variants/obj_$name/$f.log &
+for f in lk_tma lk_patch pyramid api lk; do sc=""; [ $f = pyramid ] && sc="--split-compile 4";
+  $NV $flags $sc -Xptxas -v -c $f.cu -o variants/obj_$name/$f.o 2> variants/obj_$name/$f.log &
 done
 $NV $flags -fmad=false -Xptxas -v -c detect.cu -o variants/obj_$name/detect.o 2> variants/obj_$name/detect.log &
 wait
