@@ -898,7 +898,8 @@ static int fill_lk_levels(const PyrGeom& g, LKArgs* a) {
 
 static int check_lk(const slamklt_lk_params* p, int nlA, int nlB) {
     if (!p) return fail(SLAMKLT_E_INVALID, "params is NULL");
-    if (p->window_size < 1 || p->window_size > 15) return fail(SLAMKLT_E_INVALID, "window_size %d outside [1,15]", p->window_size);
+    // (up to 9: TMA-staged kernel; up to 11: cp.async patch kernel; up to 15: row-per-lane kernel; beyond: any-window kernel)
+    if (p->window_size < 1 || p->window_size > 255) return fail(SLAMKLT_E_INVALID, "window_size %d outside [1,255]", p->window_size);
     if (p->iterations < 0) return fail(SLAMKLT_E_INVALID, "iterations < 0");
     if (p->pyramid_levels < 0) return fail(SLAMKLT_E_INVALID, "pyramid_levels < 0");
     if (!(nlA > p->pyramid_levels && nlB > p->pyramid_levels)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");

@@ -217,6 +217,158 @@ __global__ void __launch_bounds__(128, (W2 <= 19 ? LK_MIN_BLOCKS : (W2 <= 23 ? 3
     }
 }
 
+// Any window size (2w + 1 > 31 in the product; every size with SLAMKLT_LK_VARIANT=a).  Same control flow, same Float64 decisions
+// and the same fp32 expressions as k_lk, without the register-resident template: lane l owns window rows l, l + 32, ... and reads
+// template, gradients and the four bilinear taps of every pixel from global memory (L1 / L2 resident: a window is a few KB).  For
+// windows of at most 32 rows every lane owns one row and sums it in the same order as k_lk, so both kernels give identical bits.
+__global__ void __launch_bounds__(128) k_lk_any(const LKArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int total = a.n_frames * a.n_per_frame;
+    if (gw >= total) return;
+    const int f = gw / a.n_per_frame;
+    const float* fbA = a.A.frame(a.offA + f);
+    const float* fbB = a.B.frame(a.offB + f);
+    const double pty = a.pts[2 * (size_t)gw], ptx = a.pts[2 * (size_t)gw + 1];
+    double dy = 0.0, dx = 0.0;
+    if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
+
+    const int w = a.window;
+    const int nstage = a.levels + 1 + (a.mode ? 1 : 0);
+    unsigned int wpx = 0, nit = 0;
+    double qy = pty, qx = ptx;
+    bool ok = true;
+    uint8_t result = 0;
+
+    for (int s = 0; s < nstage; ++s) {
+        const bool back = s > a.levels;
+        const int lvl = back ? 0 : a.levels - s;
+        if (back) {  // tracker.jl:37-46
+            qy = pty + dy; qx = ptx + dx;
+            if (lane == 0 && a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
+            result = 2;
+            dy = -dy; dx = -dx;
+            const float* t = fbA; fbA = fbB; fbB = t;
+        }
+        const double eps = back ? 1e-2 : a.eps;
+        const LKLevel& L = a.lv[lvl];
+        const int H = L.H, W = L.W;
+        const size_t pitch = (size_t)L.pitch;
+        const double inv = 1.0 / (double)(1 << lvl);
+        const int py = (int)floor(qy * inv), px = (int)floor(qx * inv);
+        int up = min(w, py - 1), down = min(w, H - py), left = min(w, px - 1), right = min(w, W - px);
+        bool setup = true;
+        double g00 = 0, g01 = 0, g11 = 0;
+        double cy = 0.0, cx = 0.0;
+        int it = 0;
+        while (true) {
+            const int nrows = up + down + 1, ncols = left + right + 1;
+            const int r0 = py - up, c0 = px - left;
+            if (setup) {
+                if (nrows < 1 || ncols < 1 || r0 < 1 || c0 < 1 || py + down > H || px + right > W) { ok = false; break; }
+                float syy = 0.f, sxx = 0.f, syx = 0.f;
+                const size_t lo = (size_t)(c0 - 1) * pitch, hi = (size_t)(px + right) * pitch;
+                for (int r = lane; r < nrows; r += 32) {
+                    const float* colA = fbA + (size_t)(r0 - 1 + r);
+                    syy += __ldg(colA + L.oRyy + hi) - __ldg(colA + L.oRyy + lo);
+                    sxx += __ldg(colA + L.oRxx + hi) - __ldg(colA + L.oRxx + lo);
+                    syx += __ldg(colA + L.oRyx + hi) - __ldg(colA + L.oRyx + lo);
+                }
+                const double ga = (double)warp_sum_f(syy), gc = (double)warp_sum_f(sxx), gb = (double)warp_sum_f(syx);
+                const double E = 0.5 * (ga + gc), F = 0.5 * (ga - gc);
+                const double R = sqrt(F * F + gb * gb), Q = fabs(E);
+                const double s1 = Q + R, s2 = fabs(Q - R);
+                const double min_eig = fmin(s1, s2) / (double)(nrows * ncols);
+                if (min_eig < a.eig_thr) { ok = false; break; }
+                const double tol = 1.4901161193847656e-08;
+                if (s2 > tol) {
+                    const double id = 1.0 / (ga * gc - gb * gb);
+                    g00 = gc * id; g01 = -gb * id; g11 = ga * id;
+                } else {
+                    g00 = g01 = g11 = 0.0;
+                    const double l1 = E + (E >= 0 ? R : -R);
+                    if (fabs(l1) > tol) {
+                        double vx = gb, vy = l1 - ga;
+                        if (fabs(vx) + fabs(vy) < 1e-300) { vx = l1 - gc; vy = gb; }
+                        if (fabs(vx) + fabs(vy) < 1e-300) { vx = fabs(ga) >= fabs(gc) ? 1.0 : 0.0; vy = 1.0 - vx; }
+                        const double nn = 1.0 / ((vx * vx + vy * vy) * l1);
+                        g00 = vx * vx * nn; g01 = vx * vy * nn; g11 = vy * vy * nn;
+                    }
+                }
+                setup = false;
+            }
+            if (it >= a.iterations) break;
+            const double pcy = (double)py + (dy + cy), pcx = (double)px + (dx + cx);
+            const int fy = __double2int_rd(pcy), fx = __double2int_rd(pcx);
+            const int cyi = __double2int_ru(pcy), cxi = __double2int_ru(pcx);
+            if (!(fy >= 1 && cyi <= H && fx >= 1 && cxi <= W)) { ok = false; break; }
+            const int nup = min(w, min(py, fy) - 1), ndown = min(w, H - max(py, cyi));
+            const int nleft = min(w, min(px, fx) - 1), nright = min(w, W - max(px, cxi));
+            if (nup != up || ndown != down || nleft != left || nright != right) {
+                up = nup; down = ndown; left = nleft; right = nright;
+                setup = true;
+                continue;
+            }
+            // prepare_linear_system (lucas_kanade.jl:159-173): the same fmaf forms as k_lk (vertical lerp, horizontal lerp, difference)
+            const float wy = (float)(pcy - (double)fy), wx = (float)(pcx - (double)fx);
+            float by = 0.f, bx = 0.f;
+            for (int r = lane; r < nrows; r += 32) {
+                const float* pI = fbA + L.oI + (size_t)(r0 - 1 + r) + (size_t)(c0 - 1) * pitch;
+                const float2* pG = reinterpret_cast<const float2*>(fbA + L.oG) + (size_t)(r0 - 1 + r) + (size_t)(c0 - 1) * pitch;
+                const float* tp = fbB + L.oI + (size_t)(fy - up - 1 + r) + (size_t)(fx - left - 1) * pitch;
+                float t0 = __ldg(tp), t1 = __ldg(tp + 1);
+                float prev = fmaf(wy, t1 - t0, t0);
+                for (int k = 0; k < ncols; ++k) {
+                    const float* tq = tp + (size_t)(k + 1) * pitch;
+                    t0 = __ldg(tq); t1 = __ldg(tq + 1);
+                    const float cur = fmaf(wy, t1 - t0, t0);
+                    const float val = fmaf(wx, cur - prev, prev);
+                    const float dI = __ldg(pI + (size_t)k * pitch) - val;
+                    const float2 g2 = __ldg(pG + (size_t)k * pitch);
+                    by = fmaf(dI, g2.x, by);
+                    bx = fmaf(dI, g2.y, bx);
+                    prev = cur;
+                }
+            }
+            const double sby = (double)warp_sum_f(by), sbx = (double)warp_sum_f(bx);
+            wpx += (unsigned)(nrows * ncols);
+            nit += 1;
+            ++it;
+            const double ffy = g00 * sby + g01 * sbx, ffx = g01 * sby + g11 * sbx;
+            if (fabs(ffy) < eps && fabs(ffx) < eps) break;
+            cy += ffy; cx += ffx;
+            const double ny = pcy + ffy, nx = pcx + ffx;
+            if (!(__double2int_rd(ny) >= 1 && __double2int_ru(ny) <= H && __double2int_rd(nx) >= 1 && __double2int_ru(nx) <= W)) { ok = false; break; }
+        }
+        if (!ok) break;
+        dy += cy; dx += cx;
+        if (lvl > 0) { dy *= 2.0; dx *= 2.0; }
+    }
+
+    if (a.mode == 0) {
+        if (lane == 0) {
+            if (a.disp_out) { a.disp_out[2 * (size_t)gw] = dy; a.disp_out[2 * (size_t)gw + 1] = dx; }
+            a.status[gw] = ok ? 1 : 0;
+        }
+    } else if (lane == 0) {
+        if (result == 0) {
+            if (a.out_pts) {
+                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        } else if (ok) {
+            const double by = qy + dy, bx = qx + dx;
+            const double ey = pty - by, ex = ptx - bx;
+            if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+        }
+        a.status[gw] = result;
+    }
+    if (lane == 0 && a.counters) {
+        atomicAdd(a.counters, (unsigned long long)wpx);
+        atomicAdd(a.counters + 1, (unsigned long long)nit);
+    }
+}
+
 int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     const int total = a.n_frames * a.n_per_frame;
     if (total <= 0) return 0;
@@ -225,9 +377,11 @@ int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     const int wpb = (wpb_env >= 1 && wpb_env <= 4) ? wpb_env : 4;
     const int blocks = (total + wpb - 1) / wpb;
     const int w2 = 2 * a.window + 1;
-    // A/B knob: 'r' = row-per-lane kernel (lk.cu), 'p' = cp.async patch kernel (lk_patch.cu); default = TMA-staged patch kernel
+    // A/B knob: 'r' = row-per-lane kernel (lk.cu), 'p' = cp.async patch kernel (lk_patch.cu), 'a' = any-window kernel; default = TMA-staged patch kernel
     // (lk_tma.cu) where it covers the window, then the cp.async patch kernel, then the row kernel
-    static const char variant = getenv("SLAMKLT_LK_VARIANT") ? getenv("SLAMKLT_LK_VARIANT")[0] : 't';
+    const char* venv = getenv("SLAMKLT_LK_VARIANT");
+    const char variant = venv ? venv[0] : 't';
+    if ((variant == 'a' || w2 > 31) && a.mode != 2) { k_lk_any<<<blocks, wpb * 32, 0, s>>>(a); return 1; }
     if (variant == 't' && launch_lk_tma(s, a)) return a.gtab ? 2 : 1;
     if (variant != 'r' && launch_lk_patch(s, a)) return 1;
     if (w2 <= 19) k_lk<19><<<blocks, wpb * 32, 0, s>>>(a);

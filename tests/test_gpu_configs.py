@@ -571,3 +571,59 @@ def test_matching_parameter_sweep(ctx, seed):
         u = O.undistort_point(orc if stereo else ocam, g_pix[ok])
         assert np.array_equal(u, g_und[ok]) and np.array_equal(O.backproject(orc if stereo else ocam, u), g_pos[ok]), info
     assert np.all(np.isnan(g_pix[(g_st & 1) == 0])), info
+
+
+def _lk_inputs(ctx, seed, H, W, levels, n=400):
+    fr, _ = synth.make_sequence(1700 + seed, 2, H=H, W=W)
+    f = synth.to_f64(fr)
+    pts = synth.random_keypoints(150 + seed, n, H, W, border=0.0)
+    pts[:6] = [[1, 1], [H, W], [1, W], [H, 1], [H / 2, 1.0], [1.0, W / 2]]
+    o0, o1 = O.LKPyramid(f[0], levels), O.LKPyramid(f[1], levels); o1.update(f[1])
+    g0, g1 = slamklt.LKPyramid(ctx, f[0], levels), slamklt.LKPyramid(ctx, f[1], levels); g1.update(f[1])
+    return pts, (o0, o1), (g0, g1)
+
+
+@pytest.mark.parametrize("window", [7, 11, 15])
+def test_any_window_kernel_equals_row_kernel(ctx, monkeypatch, window):
+    """The any-window tracking kernel (k_lk_any: windows beyond 31 x 31) evaluates the same expressions in the same order as the
+    row-per-lane kernel while a window has at most 32 rows: forced on a small window (SLAMKLT_LK_VARIANT=a against =r), both
+    kernels return identical bits for fb_tracking! and optflow!."""
+    pts, _, (g0, g1) = _lk_inputs(ctx, window, 150, 230, 2)
+    disp = np.random.default_rng(window).uniform(-1.0, 1.0, pts.shape)
+    alg = slamklt.LucasKanade(iterations=30, window_size=window, pyramid_levels=2)
+    res = {}
+    for v in ("r", "a"):
+        monkeypatch.setenv("SLAMKLT_LK_VARIANT", v)
+        res[v] = (slamklt.fb_tracking(g0, g1, pts, displacement=disp.copy(), window_size=window, pyramid_levels=2, max_distance=1.0),
+                  slamklt.optflow(disp.copy(), g0, g1, pts, alg)[:2])
+    monkeypatch.delenv("SLAMKLT_LK_VARIANT")
+    (fr_, of_r), (fa_, of_a) = res["r"], res["a"]
+    for x, y in zip(fr_, fa_):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert np.array_equal(np.asarray(of_r[0]), np.asarray(of_a[0])) and np.array_equal(np.asarray(of_r[1]), np.asarray(of_a[1]))
+    assert fa_[1].mean() > 0.5
+
+
+@pytest.mark.parametrize("window,shape,levels", [(16, (200, 320), 2), (20, (260, 300), 1), (31, (300, 420), 2), (45, (376, 500), 1)])
+def test_windows_beyond_31_match_oracle(ctx, window, shape, levels):
+    """window_size > 15 (33 x 33 ... 91 x 91 windows; lucas_kanade.jl:1-7 puts no bound on it): fb_tracking! and optflow! against the
+    oracle with the tolerances of the other tracking tests."""
+    H, W = shape
+    pts, (o0, o1), (g0, g1) = _lk_inputs(ctx, window, H, W, levels)
+    n = len(pts)
+    kw = dict(iterations=30, window_size=window, pyramid_levels=levels, max_distance=1.0)
+    po, so, fo = O.fb_tracking(o0, o1, pts, **kw)
+    pg, sg, fg = slamklt.fb_tracking(g0, g1, pts, **kw)
+    assert np.sum(so != sg) <= max(1, int(0.001 * n)) and np.sum(fo != fg) <= max(1, int(0.001 * n)), (np.sum(so != sg), np.sum(fo != fg))
+    both = so & sg
+    assert both.sum() > 0.4 * n
+    d = np.abs(po[both] - pg[both]).max(axis=1)
+    assert np.sum(d >= 0.01) <= max(1, int(0.001 * both.sum())) and d.max() < 0.03, (d.max(), np.sum(d >= 0.01))
+    d0 = np.random.default_rng(window).uniform(-1.0, 1.0, pts.shape)
+    do, so2 = O.optflow(d0.copy(), o0, o1, pts, O.LucasKanade(iterations=30, window_size=window, pyramid_levels=levels))[:2]
+    dg, sg2 = slamklt.optflow(d0.copy(), g0, g1, pts, slamklt.LucasKanade(iterations=30, window_size=window, pyramid_levels=levels))[:2]
+    so2, sg2 = np.asarray(so2, bool), np.asarray(sg2, bool)
+    assert np.sum(so2 != sg2) <= max(1, int(0.001 * n))
+    ok = so2 & sg2
+    dd = np.abs(np.asarray(do)[ok] - np.asarray(dg)[ok]).max(axis=1)
+    assert np.sum(dd >= 0.01) <= max(1, int(0.001 * ok.sum())) and dd.max() < 0.03, (dd.max(), np.sum(dd >= 0.01))
