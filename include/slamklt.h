@@ -74,7 +74,7 @@ typedef struct slamklt_batch slamklt_batch;
 /* LucasKanade (lucas_kanade.jl:1-7) + fb_tracking!'s max_distance (tracker.jl:22) */
 typedef struct slamklt_lk_params {
     int32_t iterations;          /* 30 */
-    int32_t window_size;         /* half width; 9 in Params (params.jl:65); 1 .. 255 (optical_flow_matching: <= 11) */
+    int32_t window_size;         /* half width; 9 in Params (params.jl:65); 1 .. 255 */
     int32_t pyramid_levels;      /* 3 */
     int32_t reserved;
     double eigenvalue_threshold; /* 1e-4 */

@@ -995,7 +995,6 @@ int slamklt_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const slamklt_py
     int r = check_lk(p, A->g.nl, B->g.nl);
     if (r) return r;
     if (levels_3d < 0 || !(A->g.nl > levels_3d && B->g.nl > levels_3d)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");
-    if (p->window_size > 11) return fail(SLAMKLT_E_INVALID, "flow_matching supports window_size <= 11");
     if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
     if (n == 0) return 0;
     if (!pts || !prior || !has_prior || !out_pts || !status) return fail(SLAMKLT_E_INVALID, "NULL argument");
@@ -1053,7 +1052,6 @@ int slamklt_optical_flow_matching(slamklt_ctx* c, const slamklt_pyr* A, const sl
     if (r) return r;
     const int l3 = mp->pyramid_levels_3d;
     if (l3 < 0 || !(A->g.nl > l3 && B->g.nl > l3)) return fail(SLAMKLT_E_LAYERS, "Not enough layers in pyramids.");
-    if (p->window_size > 11) return fail(SLAMKLT_E_INVALID, "optical_flow_matching supports window_size <= 11");
     if (n < 0) return fail(SLAMKLT_E_INVALID, "n < 0");
     if (n == 0) return 0;  // map_manager.jl:536
     if (!pix || !is_3d || !world || !cw || !cam || !out_pix || !out_und || !out_pos || !status)

@@ -230,19 +230,38 @@ __global__ void __launch_bounds__(128) k_lk_any(const LKArgs a) {
     const float* fbA = a.A.frame(a.offA + f);
     const float* fbB = a.B.frame(a.offB + f);
     const double pty = a.pts[2 * (size_t)gw], ptx = a.pts[2 * (size_t)gw + 1];
+    // mode 2 = optical_flow_matching! (map_manager.jl:451-564): keypoints with a prior (3-D keypoints) are first tracked with that
+    // prior on levels3d levels; those that fail, and all others, are tracked from a zero displacement on all levels
+    const uint8_t prior_flag = (a.mode == 2 && a.has_prior) ? a.has_prior[gw] : (uint8_t)0;
+    if (prior_flag == 2) {  // projection outside the image: not tracked at all (map_manager.jl:489-506)
+        if (lane == 0) {
+            a.status[gw] = 8;
+            if (a.out_pts) {
+                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+        return;
+    }
+    const bool prior_first = a.mode == 2 && prior_flag != 0;
+    bool second_try = false;
+    int levels_cur = prior_first ? a.levels3d : a.levels;
+    const float* const fbA0 = fbA;
+    const float* const fbB0 = fbB;
     double dy = 0.0, dx = 0.0;
-    if (a.disp_in) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
+    if (a.disp_in && !(a.mode == 2 && !prior_first)) { dy = a.disp_in[2 * (size_t)gw]; dx = a.disp_in[2 * (size_t)gw + 1]; }
 
     const int w = a.window;
-    const int nstage = a.levels + 1 + (a.mode ? 1 : 0);
     unsigned int wpx = 0, nit = 0;
     double qy = pty, qx = ptx;
     bool ok = true;
     uint8_t result = 0;
 
+retry:
+    const int nstage = levels_cur + 1 + (a.mode ? 1 : 0);
     for (int s = 0; s < nstage; ++s) {
-        const bool back = s > a.levels;
-        const int lvl = back ? 0 : a.levels - s;
+        const bool back = s > levels_cur;
+        const int lvl = back ? 0 : levels_cur - s;
         if (back) {  // tracker.jl:37-46
             qy = pty + dy; qx = ptx + dx;
             if (lane == 0 && a.out_pts) { a.out_pts[2 * (size_t)gw] = qy; a.out_pts[2 * (size_t)gw + 1] = qx; }
@@ -345,23 +364,31 @@ __global__ void __launch_bounds__(128) k_lk_any(const LKArgs a) {
         if (lvl > 0) { dy *= 2.0; dx *= 2.0; }
     }
 
+    if (a.mode != 0 && result != 0 && ok) {  // tracker.jl:59-66
+        const double by = qy + dy, bx = qx + dx;
+        const double ey = pty - by, ex = ptx - bx;
+        if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+    }
+    if (prior_first && !second_try && result != 3) {
+        // the prior pass failed: map_manager.jl:531-536 re-queues the keypoint with the 2-D ones (no prior, all levels)
+        second_try = true;
+        levels_cur = a.levels;
+        dy = 0.0; dx = 0.0; qy = pty; qx = ptx;
+        ok = true; result = 0;
+        fbA = fbA0; fbB = fbB0;
+        goto retry;
+    }
     if (a.mode == 0) {
         if (lane == 0) {
             if (a.disp_out) { a.disp_out[2 * (size_t)gw] = dy; a.disp_out[2 * (size_t)gw + 1] = dx; }
             a.status[gw] = ok ? 1 : 0;
         }
     } else if (lane == 0) {
-        if (result == 0) {
-            if (a.out_pts) {
-                a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
-                a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
-            }
-        } else if (ok) {
-            const double by = qy + dy, bx = qx + dx;
-            const double ey = pty - by, ex = ptx - bx;
-            if (!(sqrt(ey * ey + ex * ex) >= a.max_dist)) result = 3;
+        if (result == 0 && a.out_pts) {
+            a.out_pts[2 * (size_t)gw] = __longlong_as_double(0x7ff8000000000000LL);
+            a.out_pts[2 * (size_t)gw + 1] = __longlong_as_double(0x7ff8000000000000LL);
         }
-        a.status[gw] = result;
+        a.status[gw] = result | ((prior_first && !second_try && result == 3) ? 4 : 0);  // bit2: tracked by the prior pass
     }
     if (lane == 0 && a.counters) {
         atomicAdd(a.counters, (unsigned long long)wpx);
@@ -381,7 +408,7 @@ int launch_lk(cudaStream_t s, const LKArgs& a, const Hook* hk) {
     // (lk_tma.cu) where it covers the window, then the cp.async patch kernel, then the row kernel
     const char* venv = getenv("SLAMKLT_LK_VARIANT");
     const char variant = venv ? venv[0] : 't';
-    if ((variant == 'a' || w2 > 31) && a.mode != 2) { k_lk_any<<<blocks, wpb * 32, 0, s>>>(a); return 1; }
+    if (variant == 'a' || w2 > 31 || (a.mode == 2 && w2 > 23)) { k_lk_any<<<blocks, wpb * 32, 0, s>>>(a); return 1; }
     if (variant == 't' && launch_lk_tma(s, a)) return a.gtab ? 2 : 1;
     if (variant != 'r' && launch_lk_patch(s, a)) return 1;
     if (w2 <= 19) k_lk<19><<<blocks, wpb * 32, 0, s>>>(a);

@@ -122,14 +122,18 @@ def test_invalid_arguments(ctx):
         slamklt.LKPyramid(ctx, np.zeros((40, 40)), 5)  # level 4 would be 3 x 3
     g = slamklt.LKPyramid(ctx, np.random.default_rng(0).uniform(size=(64, 64)), 1)
     with pytest.raises(slamklt.SlamKltError):
-        slamklt.fb_tracking(g, g, np.array([[5.0, 5.0]]), window_size=16)
+        slamklt.fb_tracking(g, g, np.array([[5.0, 5.0]]), window_size=256)
     with pytest.raises(slamklt.SlamKltError):
         g.update(np.zeros((64, 65)))
 
 
-def test_optical_flow_matching_two_pass(ctx):
+@pytest.mark.parametrize("window,variant", [(9, None), (9, "a"), (13, None)])
+def test_optical_flow_matching_two_pass(ctx, monkeypatch, window, variant):
     """the tracking part of optical_flow_matching! (map_manager.jl:451-564) in one launch equals the
-    reference's two fb_tracking! calls (3-D keypoints with a prior on 1 level, then failures + 2-D keypoints on 3 levels)."""
+    reference's two fb_tracking! calls (3-D keypoints with a prior on 1 level, then failures + 2-D keypoints on 3 levels).
+    window 9: TMA-staged kernel, and the any-window kernel forced; window 13 (27 x 27): any-window kernel."""
+    if variant:
+        monkeypatch.setenv("SLAMKLT_LK_VARIANT", variant)
     fr, aff = synth.make_sequence(4100, 2)
     f = synth.to_f64(fr)
     rng = np.random.default_rng(8)
@@ -146,12 +150,12 @@ def test_optical_flow_matching_two_pass(ctx):
     # reference composition
     exp_pts = np.full_like(pts, np.nan); exp_st = np.zeros(len(pts), bool); exp_3d = np.zeros(len(pts), bool)
     i3 = np.flatnonzero(is3d)
-    p3, s3, _ = O.fb_tracking(o0, o1, pts[i3], displacement=prior[i3], window_size=9, pyramid_levels=1, max_distance=1.0)
+    p3, s3, _ = O.fb_tracking(o0, o1, pts[i3], displacement=prior[i3], window_size=window, pyramid_levels=1, max_distance=1.0)
     exp_pts[i3[s3]] = p3[s3]; exp_st[i3[s3]] = True; exp_3d[i3[s3]] = True
     i2 = np.concatenate([np.flatnonzero(~is3d), i3[~s3]])
-    p2, s2, _ = O.fb_tracking(o0, o1, pts[i2], window_size=9, pyramid_levels=3, max_distance=1.0)
+    p2, s2, _ = O.fb_tracking(o0, o1, pts[i2], window_size=window, pyramid_levels=3, max_distance=1.0)
     exp_pts[i2[s2]] = p2[s2]; exp_st[i2[s2]] = True
-    got_pts, got_st, got_3d = slamklt.optical_flow_matching(g0, g1, pts, prior, is3d, window_size=9, pyramid_levels=3,
+    got_pts, got_st, got_3d = slamklt.optical_flow_matching(g0, g1, pts, prior, is3d, window_size=window, pyramid_levels=3,
                                                             pyramid_levels_3d=1, max_distance=1.0)
     assert np.mean(got_st == exp_st) >= 0.999 and np.mean(got_3d == exp_3d) >= 0.999
     both = got_st & exp_st & (got_3d == exp_3d)
