@@ -556,6 +556,12 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 #ifndef COLS_MINB
 #define COLS_MINB 4
 #endif
+// 16 rows per lane (frames of 385 .. 512 rows, e.g. 752 x 480): 203 registers unbounded = 2 CTAs per SM.  Measured on B200, build of
+// 64 frames of 480 x 752: unbounded 0.633 ms, bounded for 3 CTAs (168 registers, no spills) 0.577 ms, for 4 CTAs (128 registers, 120
+// bytes of spills) 0.623 ms; two warps per column with 8 rows per lane 0.611 ms (128 registers) / 0.688 ms (96 registers).
+#ifndef COLS_MINB16
+#define COLS_MINB16 3
+#endif
 #ifndef COLS_MINB_TALL
 #define COLS_MINB_TALL 0
 #endif
@@ -584,7 +590,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
 // column -- K = 12 / 18 rows per lane instead of 24 / 34, half the registers, twice the resident warps.
 template <int K, int SRC, int G, int HV = 1>
 __global__ void __launch_bounds__(128, HV == 2 ? (K <= 8 ? COLS_PAIR_MINB8 : (K <= 12 ? COLS_PAIR_MINB12 : COLS_PAIR_MINB18))
-                                              : ((K <= 12 && COLS_MINB > 0) ? COLS_MINB : ((K >= 24 && COLS_MINB_TALL > 0) ? COLS_MINB_TALL : 1)))
+                                              : ((K <= 12 && COLS_MINB > 0) ? COLS_MINB : ((K == 16 && COLS_MINB16 > 0) ? COLS_MINB16 : ((K >= 24 && COLS_MINB_TALL > 0) ? COLS_MINB_TALL : 1))))
     k_cols_all(ColArgs a, IirDev c4, IirDev c1) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
