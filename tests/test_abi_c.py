@@ -107,3 +107,26 @@ def test_julia_shim_ccalls_match_the_header():
             assert rettype in ("Cint", "Cstring"), (fn, name, rettype)
             n_calls += 1
     assert n_calls >= 20
+
+
+def test_julia_shim_struct_layouts():
+    """The isbits structs the shim passes by reference have the sizes the C compiler gives the header's structs (40 / 40 / 208 / 56:
+    checked against the compiled abi_smoke program in test_header_is_c99_and_layouts_match); all fields are 4- or 8-byte scalars in
+    an order that needs no padding surprises: 4-byte fields come in pairs before every 8-byte field."""
+    import re
+    size = {"Int32": 4, "Float64": 8, "Int64": 8, "NTuple{16, Float64}": 128}
+    structs = {}
+    for fn in ("SlamKLT.jl", "SlamKLTOptional.jl"):
+        src = open(os.path.join(ROOT, "julia", fn)).read()
+        for m in re.finditer(r"^struct (SlamKlt\w+)\n(.*?)^end", src, flags=re.S | re.M):
+            fields = re.findall(r"\w+::([\w{}, ]+?)(?:;|\n|$)", m.group(2))
+            off = 0
+            for t in fields:
+                t = t.strip()
+                sz = size[t] if t in size else structs[t]
+                al = min(sz, 8)
+                assert off % al == 0, (m.group(1), t, off)      # no implicit padding anywhere
+                off += sz
+            structs[m.group(1)] = off
+    assert structs == {"SlamKltLKParams": C.sizeof(slamklt.LKParams), "SlamKltDetectParams": C.sizeof(slamklt.DetectParams),
+                       "SlamKltCamera": C.sizeof(slamklt.CameraC), "SlamKltMatchingParams": C.sizeof(slamklt.MatchingParams)}, structs
