@@ -122,8 +122,8 @@ int slamklt_profile_report(slamklt_ctx* ctx, char* buf, size_t cap);
 /* ---- LKPyramid ------------------------------------------------------------------------- */
 /* allocation of LKPyramid(image, levels; reusable=true) -- pyramid.jl:40-72.
  * H x W from 4 x 4 to 16384 x 16384, every level at least 4 x 4 (the recursive filter needs more than 3 samples per line),
- * levels + 1 <= 8.  Levels of up to 1088 rows and 2048 columns are built by the register-tiled kernels, larger ones by
- * general per-line kernels (same planes, same tolerances, slower). */
+ * levels + 1 <= 8.  Levels of up to 1088 rows (level 0: 1280) and 2048 columns are built by the register-tiled kernels,
+ * larger ones by general per-line kernels (same planes, same tolerances, slower). */
 int slamklt_pyr_create(slamklt_ctx* ctx, int H, int W, int levels, slamklt_pyr** out);
 int slamklt_pyr_destroy(slamklt_ctx* ctx, slamklt_pyr* pyr);
 /* LKPyramid ctor (mode CTOR, pyramid.jl:40-79) and update!(lk, img; sigma) (mode UPDATE, pyramid.jl:81-96) */

@@ -365,7 +365,7 @@ static int make_geom(int H, int W, int levels, PyrGeom* g) {
     int h = H, w = W;
     for (int l = 0; l < g->nl; ++l) {
         if (h < 4 || w < 4) return fail(SLAMKLT_E_INVALID, "level %d is %dx%d: recursive filter needs more than 3 samples per line", l, h, w);
-        // levels with more than 1088 rows or 2048 columns are built by the general kernels of pyramid.cu (level_tiled)
+        // levels with more than 1088 rows (level 0: 1280) or 2048 columns are built by the general kernels of pyramid.cu (level_tiled)
         if (h > 16384 || w > 16384) return fail(SLAMKLT_E_INVALID, "image %dx%d exceeds the supported 16384 x 16384", h, w);
         LevelGeom& L = g->lv[l];
         // one guard row and one guard column (kept zero) so that LK's weight-0 bilinear tap at H+1 / W+1 stays in bounds

@@ -1034,7 +1034,7 @@ __global__ void k_resize(FrameSet fs, int f0, size_t o_in, int Hi, int Wi, int p
 }
 
 // ----------------------------------------------------------------------------------------------
-// Levels beyond the register-tiled kernels (more than 1088 rows: a lane would own more than 34 rows of a column; more than 2048
+// Levels beyond the register-tiled kernels (more than 1088 rows, level 0 more than 1280: a lane would own more than 34 rows of a column; more than 2048
 // columns: more than 32 chunks per row) -- portrait 1080p, 4K frames.  Same stages, same planes, written for generality instead of
 // speed: one thread per line runs the recursion sequentially in Float64 (forward pass stored as fp32 in the output plane, backward
 // pass in place), a pointwise kernel forms the Scharr gradients and their products.  Coarser levels that fit go back to the
@@ -1171,8 +1171,12 @@ int pick_K(int H) {
 }
 
 // does the level fit the register-tiled kernels?  (SLAMKLT_FORCE_GENERIC=1 sends every level through the general kernels: tests)
-static bool level_tiled(const LevelGeom& L) {
-    return pick_K(L.H) != 0 && L.W <= 2048 && getenv("SLAMKLT_FORCE_GENERIC") == nullptr;
+// Up to 1088 rows one warp, or a pair of warps, owns a column; level 0 -- always built by the fused column kernel -- also takes
+// the pair kernel's full range of 1280 rows (coarser levels need the one-warp blur kernel of the layer chain as well).
+static int pick_K_pair(int H);
+static bool level_tiled(const LevelGeom& L, int level) {
+    if (L.W > 2048 || getenv("SLAMKLT_FORCE_GENERIC") != nullptr) return false;
+    return pick_K(L.H) != 0 || (level == 0 && pick_K_pair(L.H) != 0);
 }
 
 template <int K>
@@ -1446,7 +1450,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
     for (int l = 0; l < g.nl; ++l) {
         const LevelGeom& L = g.lv[l];
         const bool blur = l + 1 < g.nl;
-        if (!level_tiled(L)) {
+        if (!level_tiled(L, l)) {
             // general kernels, all on the main stream: [conversion] -> gradients + products -> sigma = 4 along y (in place) -> along x
             // with the row prefix sums -> [pyramid blur along y, along x -> decimation]
             if (l == 0 && raw) {
@@ -1573,7 +1577,7 @@ int launch_pyramid(const PyrStreams& ps, FrameSet fs, int f0, int n_frames, cons
 // scratch plane into DP_TMP (the pyramid itself only keeps the row-prefix form)
 int launch_smoothed_plane(cudaStream_t s, FrameSet fs, int f0, const PyrGeom& g, int level, int which, const Hook* hk) {
     const LevelGeom& L = g.lv[level];
-    if (!level_tiled(L)) {
+    if (!level_tiled(L, level)) {
         mark(hk, "k_gen_iir_x_plain");
         gen_iir(s, fs, f0, 1, L, false, 0, 1, plane_off(L, DP_T0 + which), plane_off(L, DP_TMP), false, nullptr, 4.0);
         return 1;

@@ -149,6 +149,34 @@ def test_two_warps_per_column(ctx, monkeypatch, shape, dtype, mode):
             assert rel_err(a, b) < 2e-6, (l, name, rel_err(a, b))
 
 
+@pytest.mark.parametrize("shape,dtype,mode", [((1280, 200), "u8", "update"), ((1100, 130), "f64", "ctor"), ((1200, 96), "f32", "update"),
+                                              ((1089, 72), "f64", "update")])
+def test_level0_up_to_1280_rows(ctx, monkeypatch, shape, dtype, mode):
+    """Level 0 of frames with 1089 ... 1280 rows (portrait 720p) is built by the two-warps-per-column kernel (20 rows per lane),
+    the coarser levels by the ordinary tiled kernels.  Planes against the oracle, and against the general per-line kernels
+    (SLAMKLT_FORCE_GENERIC=1) on the same frame."""
+    H, W = shape
+    fr, _ = synth.make_sequence(3100 + H + W, 2, H=H, W=W)
+    f = synth.to_f64(fr)
+    src = {"f64": f, "u8": fr, "f32": f.astype(np.float32)}[dtype]
+    ref = f if dtype != "f32" else src.astype(np.float64)
+    L = 2
+    op = O.LKPyramid(ref[0], L, mode="ctor")
+    tiled = slamklt.LKPyramid(ctx, src[0], L)
+    monkeypatch.setenv("SLAMKLT_FORCE_GENERIC", "1")
+    general = slamklt.LKPyramid(ctx, src[0], L)
+    if mode == "update":
+        general.update(src[1])
+    monkeypatch.delenv("SLAMKLT_FORCE_GENERIC")
+    if mode == "update":
+        op.update(ref[1]); tiled.update(src[1])
+    _check_planes(tiled, op, L)
+    for l in range(L + 1):
+        for name in PLANES + (("blur",) if l < L else ()):
+            a, b = tiled.plane(l, name), general.plane(l, name)
+            assert rel_err(a, b) < 4e-6, (l, name, rel_err(a, b))
+
+
 def test_batch_step_1080p_equals_single_calls(ctx):
     """Config 5 geometry through the batched stream API (two warps per column at levels 0 and 1): one step of three 1080p UInt8 frames
     equals single pyramids + fb_tracking! bit for bit, and the step's tracks agree with the oracle."""
