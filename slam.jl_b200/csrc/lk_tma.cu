@@ -144,7 +144,14 @@ __device__ __forceinline__ void tma_box(void* dst, const CUtensorMap* map, int c
                  : "memory");
 }
 // generic-proxy reads of a tile must be ordered before the async proxy overwrites it
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifndef LKT_FENCE
+#define LKT_FENCE 1
+#endif
+__device__ __forceinline__ void fence_async_smem() {
+#if LKT_FENCE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ void wsum2(float a, float b, int lane, float& sa, float& sb) {
     const bool hi = lane & 16;

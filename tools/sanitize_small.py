@@ -60,8 +60,8 @@ bx.detect(slamklt.Extractor(300, 8, (11, 12), 35), np.stack([synth.random_keypoi
 by.track_cross(bx, alg2); bx.download()
 bx.close(); by.close(); pin.free()
 # round 2c: frames taller than 512 rows (two warps per column: 12 and 20 rows per lane, odd height = per-row predicates, every
-# source type) and levels beyond the tiled kernels (general per-line kernels: tall, wide), tracking on such pyramids
-for (Ht, Wt, src_kind) in ((600, 40, "f64"), (1080, 24, "u8"), (771, 20, "f32"), (1130, 36, "f64"), (40, 2080, "u8")):
+# source type; level 0 up to 1280 rows) and levels beyond the tiled kernels (general per-line kernels: tall, wide), tracking on such pyramids
+for (Ht, Wt, src_kind) in ((600, 40, "f64"), (1080, 24, "u8"), (771, 20, "f32"), (1130, 36, "f64"), (1280, 24, "u8"), (1400, 28, "f64"), (40, 2080, "u8")):
     frt, _ = synth.make_sequence(9, 2, H=Ht, W=Wt)
     ft = synth.to_f64(frt)
     srct = {"f64": ft, "u8": frt, "f32": ft.astype(np.float32)}[src_kind]
