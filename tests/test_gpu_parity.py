@@ -159,6 +159,28 @@ def test_fb_tracking_kitti(ctx, seq):
     assert np.median(np.linalg.norm(rg[0][ok] - gt[ok], axis=1)) < 0.15
 
 
+@pytest.mark.parametrize("seed", [11, 13])
+def test_fb_tracking_against_opencv_pyrlk(ctx, seed):
+    """The CUDA path against an implementation that shares nothing with the oracle: OpenCV's pyramidal LK on the same 8-bit frames
+    (own pyramid and gradients, 19 x 19 window, 4 levels, 30 iterations, eps 0.01).  No bit-level claim; both reach the same
+    sub-pixel minimum (the oracle itself: median 0.004 px, at most 0.017 px from OpenCV, tests/test_oracle.py)."""
+    cv2 = pytest.importorskip("cv2")
+    H, W = 240, 320
+    fr, _ = synth.make_sequence(seed, 2, H=H, W=W, max_step=6.0)
+    c = cv2.goodFeaturesToTrack(fr[0], 300, 0.01, 7).reshape(-1, 2)
+    c = c[(c[:, 0] > 20) & (c[:, 0] < W - 21) & (c[:, 1] > 20) & (c[:, 1] < H - 21)]
+    pts = np.stack([c[:, 1] + 1.0, c[:, 0] + 1.0], axis=1).astype(np.float64)
+    g0, g1 = slamklt.LKPyramid(ctx, fr[0], 3), slamklt.LKPyramid(ctx, fr[1], 3)   # UInt8 frames, i / 255 on the device
+    new, st, _ = slamklt.fb_tracking(g0, g1, pts, window_size=9, pyramid_levels=3, max_distance=1.0)
+    nxt, cst, _ = cv2.calcOpticalFlowPyrLK(fr[0], fr[1], c.astype(np.float32), None, winSize=(19, 19), maxLevel=3,
+                                           criteria=(cv2.TERM_CRITERIA_COUNT | cv2.TERM_CRITERIA_EPS, 30, 0.01))
+    cvp = np.stack([nxt[:, 1] + 1.0, nxt[:, 0] + 1.0], axis=1)
+    both = st.astype(bool) & (cst.ravel() == 1)
+    assert both.sum() >= 0.95 * len(pts)
+    d = np.linalg.norm(new[both] - cvp[both], axis=1)
+    assert np.median(d) < 0.01 and np.percentile(d, 95) < 0.02 and d.max() < 0.05, (np.median(d), np.percentile(d, 95), d.max())
+
+
 def test_fb_tracking_update_mode_and_prior(ctx, seq):
     f = seq[0]
     pts = synth.random_keypoints(11, 700, 376, 1241, border=3.0)  # includes near-border points (clipped windows)
