@@ -411,7 +411,11 @@ def test_tracking_parameter_sweep(ctx, seed):
     border -- level coordinate 0, a window one pixel off the point -- were failed by the TMA kernel; fixed).  window_size 1 and 2
     (3 x 3 and 5 x 5 windows) are left out: with so few pixels the iteration is ill-conditioned enough that the fp32 storage of the
     structure-tensor sums and the fp32 window arithmetic (3e-6 relative) change the path of a few points per thousand
-    (about one case in forty exceeds the 99.9 % bar); from 7 x 7 on, 200 of 200 random cases pass."""
+    (about one case in forty exceeds the 99.9 % bar); from 7 x 7 on, 200 of 200 random cases pass.  Seeds 0 .. 299 (final tree): 298
+    pass; 270 (7 x 7 window, no pyramid) and 293 (9 x 9 window) exceed the bar in the plain `optflow!` comparison only, by one and two
+    points of ~480 that ran away 12 - 20 px from their keypoint over 30 iterations (lost tracks: a chaotic path amplifies any rounding
+    difference; 0.25 / 0.05 px apart) -- the forward-backward gate rejects all three in the reference and here alike, and the
+    `fb_tracking!` comparison of both cases is clean (tools/sweep_track_probe.py, profiles/round2_sweeps.txt)."""
     rng = np.random.default_rng(4200 + seed)
     H, W = int(rng.integers(60, 260)), int(rng.integers(80, 420))
     levels = int(rng.integers(0, 4))
@@ -452,7 +456,7 @@ def test_tracking_parameter_sweep(ctx, seed):
         assert np.sum(dd >= 0.01) <= max(1, int(0.001 * ok.sum())) and dd.max() < 0.03, (seed, kw, dd.max())
 
 
-@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("SLAMKLT_SWEEP_SEEDS", "10"))))
+@pytest.mark.parametrize("seed", sorted(set(range(int(__import__("os").environ.get("SLAMKLT_SWEEP_SEEDS", "10")))) | {193}))
 def test_pyramid_parameter_sweep(ctx, seed):
     """Randomised sweep over `LKPyramid(image, levels; sigma)` / `update!(pyr, image; sigma)` (pyramid.jl:40-96): image shape (every
     column-kernel width K and both row-chunk sizes get hit over the seeds), depth, blur sigma, host pixel type, both border regimes.
@@ -477,9 +481,19 @@ def test_pyramid_parameter_sweep(ctx, seed):
     tol = 1e-5 if sigma <= 1.5 else 2e-5
     def check(tag):
         for l in range(levels + 1):
+            scale = {}
             for name in ("layer", "Iy", "Ix", "Syy", "Sxx", "Syx"):
                 a, b = gp.plane(l, name), op.plane(l, name)
-                assert a.shape == b.shape and rel_err(a, b) < tol, (seed, tag, (H, W), levels, sigma, l, name, rel_err(a, b))
+                scale[name] = float(np.abs(b).max())
+                err = rel_err(a, b)
+                if name == "Syx":
+                    # The signed cross product cancels where the diagonal planes cannot (|Syx| <= sqrt(Syy Sxx) pointwise): on a
+                    # nearly flat coarse level of pure noise max|Syx| falls far below the products it is summed from, and the fp32
+                    # rounding of those products no longer fits 1e-5 of max|Syx| (seed 193: 9 x 20 level, max|Syx| 9.9e-6 against
+                    # 3.3e-5 / 5.0e-5 on the diagonal, error 1.3e-10 = 1.3e-5 of max|Syx| but 3.2e-6 of the tensor's scale).  Syx is
+                    # consumed as the off-diagonal of G = [Syy Syx; Syx Sxx], so it is judged on G's scale when that is the larger.
+                    err = float(np.abs(a - b).max() / max(scale["Syx"], np.sqrt(scale["Syy"] * scale["Sxx"]), 1e-300))
+                assert a.shape == b.shape and err < tol, (seed, tag, (H, W), levels, sigma, l, name, err)
     check("ctor")
     op.update(f64[1], sigma=sigma); gp.update(f64[1], sigma=sigma)
     check("update")
